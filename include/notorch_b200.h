@@ -1,0 +1,186 @@
+/*
+ * notorch_b200 — C ABI of the B200-native D-MPNN hot path (libnotorch_b200.so).
+ *
+ * This is the drop-in boundary: the exact entry points a binding in the reference
+ * (davidegraff/notorch, pure Python on top of PyTorch) would call for its message-passing hot
+ * path. The reference has no FFI of its own; each function below names the reference code it
+ * replaces (paths relative to the reference tree). The Python side of this repository
+ * (notorch_b200/_lib.py, ops.py) binds them with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name ends in _host. Row-major, contiguous.
+ *  - Every function is asynchronous on `stream` (a cudaStream_t), does not allocate or free device
+ *    memory, does not synchronise, and keeps no pointer after it returns. Scratch space is passed
+ *    in by the caller (`workspace`, sized by the matching *_workspace_bytes function).
+ *  - Return value: NT_OK (0) or an nt_status error code; nt_last_error_string() describes the last
+ *    error on the calling thread. No exception crosses the ABI; nothing calls exit/abort.
+ *  - Thread-safe and re-entrant (PyTorch calls backward from its autograd thread).
+ *  - Index tensors handed to the floating-point kernels are int32 (built once per batch by
+ *    nt_graph_prepare from the reference's int64 tensors); sizes must be < 2^31.
+ *  - dtype: NT_F32 only in this round (NT_BF16 is reserved and returns NT_ERR_UNSUPPORTED).
+ */
+#ifndef NOTORCH_B200_H_
+#define NOTORCH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* nt_stream_t; /* cudaStream_t */
+
+enum nt_status {
+  NT_OK = 0,
+  NT_ERR_ARG = 1,         /* null pointer, negative size, size >= 2^31, bad enum */
+  NT_ERR_ALIGN = 2,       /* pointer / leading dimension not aligned as the kernel requires */
+  NT_ERR_UNSUPPORTED = 3, /* dtype / activation / shape this build does not implement */
+  NT_ERR_CUDA = 4,        /* a CUDA runtime call or kernel launch failed */
+  NT_ERR_WORKSPACE = 5    /* workspace too small */
+};
+
+enum nt_dtype { NT_F32 = 0, NT_BF16 = 1 };
+
+/* torch.nn activation modules accepted for ChempropLayer(act=...) (chemprop.py:17,24,37). */
+enum nt_act {
+  NT_ACT_IDENTITY = 0,
+  NT_ACT_RELU = 1,       /* nn.ReLU (reference default) */
+  NT_ACT_LEAKY_RELU = 2, /* nn.LeakyReLU, act_param = negative_slope */
+  NT_ACT_ELU = 3,        /* nn.ELU, act_param = alpha */
+  NT_ACT_SILU = 4,       /* nn.SiLU */
+  NT_ACT_GELU = 5,       /* nn.GELU (erf form) */
+  NT_ACT_TANH = 6        /* nn.Tanh */
+};
+
+/* Arithmetic path of the W contraction. */
+enum nt_gemm_mode {
+  NT_GEMM_TF32X3 = 0, /* tcgen05 tensor cores, 3xTF32 error-compensated split, fp32 accumulate in TMEM */
+  NT_GEMM_FP32 = 1,   /* fp32 FFMA on CUDA cores (strict fp32; also used when d % 4 != 0) */
+  NT_GEMM_TF32 = 2    /* tcgen05, single-pass TF32 (10-bit mantissa; NOT within the fp32 parity bound) */
+};
+
+const char* nt_last_error_string(void);
+int nt_version(void);
+/* 1 if the current device is compute capability 10.x (tcgen05 available), else 0; <0 on error. */
+int nt_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch collation  — replaces BatchedGraph.from_graphs, notorch/data/models/graph.py:186-223.
+ *
+ * Input: B molecules in packed form: num_atoms[B], num_edges[B] (int32) and the molecule-LOCAL
+ * edge_index [2,E] / rev_index [E] (int32) concatenated in batch order (the per-molecule contract of
+ * notorch/transforms/graph.py:32-43). Output: the reference's int64 tensors, bit-exact:
+ * edge_index [2,E] and rev_index [E] with the cumulative ATOM count added to BOTH (graph.py:199-200;
+ * rev_offset_mode = 0), batch_node_index [V], batch_edge_index [E]; plus the int32 molecule row
+ * pointers mol_atom_ptr [B+1], mol_edge_ptr [B+1]. rev_offset_mode = 1 adds the cumulative EDGE
+ * count to rev_index instead (structurally correct reverse edge; a labelled deviation).
+ * ---------------------------------------------------------------------------------------------- */
+size_t nt_collate_workspace_bytes(int64_t B);
+int nt_collate(const int32_t* num_atoms, const int32_t* num_edges, int64_t B,
+               const int32_t* local_edge_index, const int32_t* local_rev_index, int64_t V, int64_t E,
+               int rev_offset_mode,
+               int64_t* edge_index, int64_t* rev_index, int64_t* batch_node_index, int64_t* batch_edge_index,
+               int32_t* mol_atom_ptr, int32_t* mol_edge_ptr,
+               void* workspace, size_t workspace_bytes, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stable CSR of `n` items grouped by an int64 key in [0, num_segments): rowptr [S+1], perm [n] with
+ * perm[rowptr[s]..rowptr[s+1]) = ids of the items with key s in ASCENDING id order (so a sequential
+ * segmented sum reproduces the summation order of the reference's CPU scatter_add_).
+ * Also writes keys32 [n] = (int32) keys (nullable). *status (device int32, caller-zeroed) gets bit 0
+ * set if any key is out of range — what the reference would raise as an indexing error at
+ * chemprop.py:39-40. Replaces the index handling inside torch_scatter.scatter / aten::index.
+ * ---------------------------------------------------------------------------------------------- */
+size_t nt_build_csr_workspace_bytes(int64_t n, int64_t num_segments);
+int nt_build_csr(const int64_t* keys, int64_t n, int64_t num_segments,
+                 int32_t* keys32, int32_t* rowptr, int32_t* perm, int32_t* status,
+                 void* workspace, size_t workspace_bytes, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * out[s,:] = reduce_{j in [rowptr[s], rowptr[s+1])} act(x[perm[j],:])      (sequential, ascending j)
+ *   mean != 0 : divide by max(count, 1)  (torch_scatter.scatter_mean: a true division)
+ *   scale     : multiply the result by `scale` (1.0f = off; used by the Norm read-out extension)
+ * K1 edge->atom   : chemprop.py:37+39 (act = layer act) and chemprop.py:86 (act = identity)
+ * K3 read-out     : agg.py:27 (Sum) / agg.py:36 (Mean), rowptr/perm = CSR of batch_node_index
+ * K5 backward     : gradient of x[src] gathers (aten::index backward), rowptr/perm = CSR of src
+ * perm may be NULL (identity: segments are contiguous row ranges).
+ * ---------------------------------------------------------------------------------------------- */
+int nt_seg_reduce(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments,
+                  int act, float act_param, int mean, float scale, void* out, int dtype, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * out[i,:] = (base ? base[i,:] : 0) + scale * x[idx[i],:] / (mean_rowptr ? max(count(idx[i]),1) : 1)
+ * K0 edge_init      : chemprop.py:83  h0 = x_v[src] + x_e            (base = x_e, x = x_v, idx = src)
+ * backward of K1/K3 : g[e] = gE[e] + g_node[dst[e]] (/ indeg for mean);  g_x[v] = gH[batch[v]] (/count)
+ * ---------------------------------------------------------------------------------------------- */
+int nt_gather_add(const void* base, const void* x, const int32_t* idx, const int32_t* mean_rowptr,
+                  int64_t n, int64_t d, float scale, void* out, int dtype, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight staging for the tensor-core path: splits W [d,d] (row-major [out,in], nn.Linear layout,
+ * chemprop.py:26) into TF32 hi/lo parts and writes them as the shared-memory image the fused kernels
+ * stream with bulk TMA copies (K-blocks of 32, 128-byte-swizzled K-major tiles, zero padded).
+ * transpose = 0: B operand W (forward);  1: B operand W^T (dgrad).  Two images of
+ * nt_weight_image_bytes(d) each are written back to back into `image`.
+ * ---------------------------------------------------------------------------------------------- */
+size_t nt_weight_image_bytes(int64_t d);
+int nt_weight_prepare(const void* W, int64_t d, int transpose, void* image, int dtype, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2 — one fused message-passing depth, forward. Replaces chemprop.py:40-41 + residual.py:28:
+ *   m[e,:]  = n[src[e],:] - act(h[rev[e],:])
+ *   u[e,:]  = m[e,:] . W^T + bias                       (tcgen05 / fp32 per `gemm_mode`)
+ *   u       = dropout_p(u)        (Philox keyed by (seed, offset, e*d + c); p = 0 -> identity)
+ *   out[e,:]= (residual ? h[e,:] : 0) + u[e,:]
+ * n is K1's output (act already applied inside K1). rev is an arbitrary in-range gather index.
+ * weight_image: from nt_weight_prepare(transpose=0) (ignored for NT_GEMM_FP32, may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int nt_layer_forward(const void* h, const void* n, const int32_t* src, const int32_t* rev,
+                     const void* W, const void* weight_image, const void* bias,
+                     int64_t E, int64_t V, int64_t d, int act, float act_param, int residual,
+                     float dropout_p, uint64_t seed, uint64_t offset,
+                     void* out, int dtype, int gemm_mode, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4a — dgrad: g_m[e,:] = (mask . g[e,:] / (1-p)) . W        (backward of aten::addmm wrt input)
+ * weight_image: from nt_weight_prepare(transpose=1).
+ * ---------------------------------------------------------------------------------------------- */
+int nt_layer_backward_dgrad(const void* g, const void* W, const void* weight_image,
+                            int64_t E, int64_t d, float dropout_p, uint64_t seed, uint64_t offset,
+                            void* g_m, int dtype, int gemm_mode, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4b — wgrad: gW[o,i] = sum_e g_u[e,o] * m[e,i],  gb[o] = sum_e g_u[e,o]   (gb nullable)
+ * with g_u = mask . g / (1-p) and m recomputed from (n, h, src, rev) as in K2. Deterministic:
+ * split over edge ranges into `workspace`, then a fixed-order reduction (no atomics).
+ * ---------------------------------------------------------------------------------------------- */
+size_t nt_layer_backward_wgrad_workspace_bytes(int64_t E, int64_t d);
+int nt_layer_backward_wgrad(const void* g, const void* h, const void* n, const int32_t* src, const int32_t* rev,
+                            int64_t E, int64_t V, int64_t d, int act, float act_param,
+                            float dropout_p, uint64_t seed, uint64_t offset,
+                            void* gW, void* gb, void* workspace, size_t workspace_bytes,
+                            int dtype, int gemm_mode, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6 — backward epilogue of one depth (backward of chemprop.py:37,39,40 and residual.py:28):
+ *   g_a[e,:] = g_n[dst[e],:] / (mean ? max(indeg(dst[e]),1) : 1) - sum_{j in revinv(e)} g_m[rev_perm[j],:]
+ *   g_h[e,:] = (residual ? g[e,:] : 0) + act'(h[e,:]) * g_a[e,:]
+ * rev_rowptr/rev_perm: CSR of rev_index (the inverse map of the arbitrary gather `rev`).
+ * dst_rowptr: CSR row pointers of dst (only read when mean != 0).
+ * ---------------------------------------------------------------------------------------------- */
+int nt_layer_backward_epilogue(const void* g, const void* h, const void* g_n, const void* g_m,
+                               const int32_t* dst, const int32_t* rev_rowptr, const int32_t* rev_perm,
+                               const int32_t* dst_rowptr, int64_t E, int64_t d,
+                               int act, float act_param, int residual, int mean,
+                               void* g_h, int dtype, nt_stream_t stream);
+
+/* Dropout keep-mask exactly as K2/K4 compute it (1.0f keep / 0.0f drop), for tests. */
+int nt_dropout_mask(int64_t n_rows, int64_t d, float dropout_p, uint64_t seed, uint64_t offset,
+                    float* mask, nt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOTORCH_B200_H_ */

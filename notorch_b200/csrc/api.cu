@@ -1,0 +1,152 @@
+// extern "C" entry points that dispatch between the arithmetic paths, plus error plumbing.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace nt {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return NT_ERR_CUDA;
+}
+
+int num_sms() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev != cached_dev) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    cached = prop.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// gemm_simt.cu
+int simt_wgrad_splits(int64_t E, int64_t d);
+int simt_layer_forward(const float*, const float*, const int32_t*, const int32_t*, const float*, const float*, int64_t, int64_t, int, float, int, float,
+                       uint64_t, uint64_t, float*, cudaStream_t);
+int simt_layer_dgrad(const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, cudaStream_t);
+int simt_layer_wgrad(const float*, const float*, const float*, const int32_t*, const int32_t*, int64_t, int64_t, int, float, float, uint64_t, uint64_t,
+                     float*, float*, float*, cudaStream_t);
+// gemm_tc.cu
+size_t tc_weight_image_bytes(int64_t d);
+int tc_weight_prepare(const float*, int64_t, int, void*, cudaStream_t);
+int tc_layer_forward(const float*, const float*, const int32_t*, const int32_t*, const void*, const float*, int64_t, int64_t, int, float, int, float,
+                     uint64_t, uint64_t, float*, int, cudaStream_t);
+int tc_layer_dgrad(const float*, const void*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
+// wgrad_tc.cu
+size_t tc_wgrad_workspace_bytes(int64_t E, int64_t d);
+int tc_layer_wgrad(const float*, const float*, const float*, const int32_t*, const int32_t*, int64_t, int64_t, int, float, float, uint64_t, uint64_t,
+                   float*, float*, void*, size_t, int, cudaStream_t);
+
+static bool tc_shape_ok(int64_t d, const void* a, const void* b, const void* c, const void* e) {
+  return d % 4 == 0 && d >= 4 && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(e);
+}
+
+}  // namespace nt
+
+using namespace nt;
+
+extern "C" const char* nt_last_error_string(void) { return g_err; }
+extern "C" int nt_version(void) { return 100; }
+
+extern "C" int nt_device_supported(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
+  return major == 10 ? 1 : 0;
+}
+
+#define NT_COMMON_LAYER_CHECKS(fn)                                                                        \
+  if (dtype != NT_F32) { set_error(fn ": only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }       \
+  NT_CHECK_ARG(d > 0 && d < (1 << 20) && E >= 0 && E < INT32_MAX, fn ": bad sizes");                      \
+  NT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, fn ": dropout_p must be in [0, 1)");                  \
+  NT_CHECK_ARG(gemm_mode == NT_GEMM_TF32X3 || gemm_mode == NT_GEMM_FP32 || gemm_mode == NT_GEMM_TF32, fn ": bad gemm_mode")
+
+extern "C" size_t nt_weight_image_bytes(int64_t d) { return d > 0 ? tc_weight_image_bytes(d) : 0; }
+
+extern "C" int nt_weight_prepare(const void* W, int64_t d, int transpose, void* image, int dtype, nt_stream_t stream) {
+  if (dtype != NT_F32) { set_error("nt_weight_prepare: only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
+  NT_CHECK_ARG(W && image && d > 0 && d < (1 << 20), "nt_weight_prepare: bad arguments");
+  if (!aligned16(image)) { set_error("nt_weight_prepare: image must be 16-byte aligned"); return NT_ERR_ALIGN; }
+  return tc_weight_prepare(static_cast<const float*>(W), d, transpose != 0, image, as_stream(stream));
+}
+
+extern "C" int nt_layer_forward(const void* h, const void* n, const int32_t* src, const int32_t* rev, const void* W, const void* weight_image,
+                                const void* bias, int64_t E, int64_t V, int64_t d, int act, float act_param, int residual, float dropout_p,
+                                uint64_t seed, uint64_t offset, void* out, int dtype, int gemm_mode, nt_stream_t stream) {
+  NT_COMMON_LAYER_CHECKS("nt_layer_forward");
+  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "nt_layer_forward: bad activation");
+  NT_CHECK_ARG(V >= 0, "nt_layer_forward: bad V");
+  if (E == 0) return NT_OK;
+  NT_CHECK_ARG(h && n && src && rev && W && out, "nt_layer_forward: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, h, n, out, bias)) {
+    NT_CHECK_ARG(weight_image, "nt_layer_forward: tensor-core path needs weight_image (nt_weight_prepare)");
+    return tc_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, weight_image, static_cast<const float*>(bias), E, d,
+                            act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+  }
+  return simt_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, static_cast<const float*>(W),
+                            static_cast<const float*>(bias), E, d, act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), st);
+}
+
+extern "C" int nt_layer_backward_dgrad(const void* g, const void* W, const void* weight_image, int64_t E, int64_t d, float dropout_p, uint64_t seed,
+                                       uint64_t offset, void* g_m, int dtype, int gemm_mode, nt_stream_t stream) {
+  NT_COMMON_LAYER_CHECKS("nt_layer_backward_dgrad");
+  if (E == 0) return NT_OK;
+  NT_CHECK_ARG(g && W && g_m, "nt_layer_backward_dgrad: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, g, g_m, nullptr, nullptr)) {
+    NT_CHECK_ARG(weight_image, "nt_layer_backward_dgrad: tensor-core path needs weight_image (nt_weight_prepare, transpose=1)");
+    return tc_layer_dgrad(static_cast<const float*>(g), weight_image, E, d, dropout_p, seed, offset, static_cast<float*>(g_m),
+                          gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+  }
+  return simt_layer_dgrad(static_cast<const float*>(g), static_cast<const float*>(W), E, d, dropout_p, seed, offset, static_cast<float*>(g_m), st);
+}
+
+extern "C" size_t nt_layer_backward_wgrad_workspace_bytes(int64_t E, int64_t d) {
+  if (d <= 0) return 0;
+  size_t simt = (size_t)simt_wgrad_splits(E, d) * (size_t)d * (size_t)(d + 1) * sizeof(float);
+  size_t tcb = tc_wgrad_workspace_bytes(E, d);
+  return (simt > tcb ? simt : tcb) + 256;
+}
+
+extern "C" int nt_layer_backward_wgrad(const void* g, const void* h, const void* n, const int32_t* src, const int32_t* rev, int64_t E, int64_t V,
+                                       int64_t d, int act, float act_param, float dropout_p, uint64_t seed, uint64_t offset, void* gW, void* gb,
+                                       void* workspace, size_t workspace_bytes, int dtype, int gemm_mode, nt_stream_t stream) {
+  NT_COMMON_LAYER_CHECKS("nt_layer_backward_wgrad");
+  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "nt_layer_backward_wgrad: bad activation");
+  NT_CHECK_ARG(V >= 0 && gW, "nt_layer_backward_wgrad: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (E == 0) {
+    NT_CUDA(cudaMemsetAsync(gW, 0, (size_t)d * d * sizeof(float), st));
+    if (gb) NT_CUDA(cudaMemsetAsync(gb, 0, (size_t)d * sizeof(float), st));
+    return NT_OK;
+  }
+  NT_CHECK_ARG(g && h && n && src && rev, "nt_layer_backward_wgrad: null pointer");
+  if (!workspace || workspace_bytes < nt_layer_backward_wgrad_workspace_bytes(E, d)) {
+    set_error("nt_layer_backward_wgrad: workspace too small");
+    return NT_ERR_WORKSPACE;
+  }
+  if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, g, h, n, workspace)) {
+    int rc = tc_layer_wgrad(static_cast<const float*>(g), static_cast<const float*>(h), static_cast<const float*>(n), src, rev, E, d, act, act_param,
+                            dropout_p, seed, offset, static_cast<float*>(gW), static_cast<float*>(gb), workspace, workspace_bytes,
+                            gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+    if (rc != NT_ERR_UNSUPPORTED) return rc;
+  }
+  return simt_layer_wgrad(static_cast<const float*>(g), static_cast<const float*>(h), static_cast<const float*>(n), src, rev, E, d, act, act_param,
+                          dropout_p, seed, offset, static_cast<float*>(gW), static_cast<float*>(gb), static_cast<float*>(workspace), st);
+}

@@ -1,0 +1,491 @@
+// Tensor-core (tcgen05 / TMEM / bulk-TMA) version of K2 forward and K4a dgrad for sm_100a.
+//
+//   D[128 edges, N] = A[128, K] . B[N, K]^T        fp32 in, fp32 out, 3xTF32 error-compensated:
+//   A = A_hi + A_lo, B = B_hi + B_lo (each part exactly representable in TF32), and
+//   D = A_lo.B_hi + A_hi.B_lo + A_hi.B_hi accumulated in fp32 in tensor memory.
+//
+// Warp-specialised persistent kernel, one CTA per SM, 14 warps:
+//   warps 0-3   epilogue   tcgen05.ld accumulator -> +bias, dropout, +residual -> coalesced stores
+//   warp  4     MMA issuer one elected lane issues tcgen05.mma.kind::tf32 and tcgen05.commit; owns TMEM
+//   warp  5     W producer bulk-TMA (cp.async.bulk, SASS UBLKCP) copies of pre-swizzled weight tiles
+//   warps 6-13  A producer gathers n[src[e]] - act(h[rev[e]]) (K2) or dropout(g[e]) (K4a) rows with
+//               128-bit loads, splits hi/lo and writes the 128-byte-swizzled K-major UMMA layout
+// Pipelines (mbarriers): smem stage full/empty between producers and MMA; TMEM full/empty between
+// MMA and epilogue. A is produced by threads (generic proxy) so each producer thread executes
+// fence.proxy.async before arriving; W lands through the async proxy with complete_tx.
+//
+// The A operand cannot come from TMA (it is a gather-and-subtract), which is why only W is staged
+// by the copy engine; W is pre-split and pre-swizzled once per step by nt_weight_prepare so that
+// each (N-tile, K-block) is one contiguous bulk copy.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace nt {
+namespace tc {
+
+constexpr int TILE_M = 128;
+constexpr int BLOCK_K = 32;  // fp32 elements per K-block = one 128-byte swizzle row
+constexpr int STAGES = 2;
+constexpr int MAX_N_TILE = 304;
+constexpr int A_STAGE_BYTES = TILE_M * 128;          // 16 KiB per part
+constexpr int W_STAGE_BYTES = MAX_N_TILE * 128;      // 38 KiB per part
+constexpr int EPI_COLS = 16;                         // accumulator columns per epilogue step
+constexpr int EPI_ROW_BYTES = EPI_COLS * 4 + 16;     // padded staging row (bank-conflict-free)
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;   // 2560
+constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, W_WARP = 5, FIRST_A_WARP = 6, NUM_A_WARPS = 8;
+constexpr int NUM_A_THREADS = NUM_A_WARPS * 32;
+constexpr int THREADS = (FIRST_A_WARP + NUM_A_WARPS) * 32;  // 448
+
+constexpr int OFF_A_HI = 0;
+constexpr int OFF_A_LO = OFF_A_HI + STAGES * A_STAGE_BYTES;
+constexpr int OFF_W_HI = OFF_A_LO + STAGES * A_STAGE_BYTES;
+constexpr int OFF_W_LO = OFF_W_HI + STAGES * W_STAGE_BYTES;
+constexpr int OFF_EPI = OFF_W_LO + STAGES * W_STAGE_BYTES;
+constexpr int OFF_BAR = OFF_EPI + NUM_EPI_WARPS * EPI_WARP_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
+static_assert(OFF_W_HI % 1024 == 0 && W_STAGE_BYTES % 1024 == 0 && A_STAGE_BYTES % 1024 == 0, "swizzle-128B tiles need 1 KiB alignment");
+
+struct Geometry {
+  int d, n_tile, n_tiles, k_blocks, n_a, n_b;
+  size_t part_bytes;  // bytes of one (hi or lo) image
+};
+
+__host__ __device__ inline Geometry make_geometry(int d) {
+  Geometry g;
+  g.d = d;
+  int d16 = (d + 15) / 16 * 16;
+  g.n_tile = d16 <= MAX_N_TILE ? d16 : 256;
+  g.n_tiles = (d + g.n_tile - 1) / g.n_tile;
+  g.k_blocks = (d + BLOCK_K - 1) / BLOCK_K;
+  if (g.n_tile <= 256) { g.n_a = g.n_tile; g.n_b = 0; }
+  else { g.n_a = ((g.n_tile / 2) + 15) / 16 * 16; g.n_b = g.n_tile - g.n_a; }
+  g.part_bytes = (size_t)g.n_tiles * g.k_blocks * g.n_tile * 128;
+  return g;
+}
+
+// byte offset of (row r, 16-byte chunk c) inside a 128B-swizzled K-major tile (Swizzle<3,4,3>)
+__host__ __device__ __forceinline__ uint32_t swz128(uint32_t r, uint32_t c) {
+  return (r >> 3) * 1024u + (r & 7u) * 128u + ((c ^ (r & 7u)) << 4);
+}
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("notorch_b200: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version = 1 at bit 46,
+// layout type 2 at bits 61-63, SBO = 1024 B between 8-row groups, LBO unused for swizzled K-major).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128.
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+struct Params {
+  const float* a0;  // K2: n [V,d]      K4a: g [E,d]
+  const float* a1;  // K2: h [E,d]      K4a: unused
+  const int32_t* src;
+  const int32_t* rev;
+  const uint8_t* wimg;  // hi image followed by lo image
+  const float* bias;
+  const float* resid;  // K2 residual input h (nullable)
+  float* out;
+  int64_t E;
+  Geometry geo;
+  int act;
+  float act_param;
+  float drop_p, inv_keep;
+  uint32_t drop_thr;
+  uint64_t seed, offset;
+  int products;  // 3 = 3xTF32, 1 = single-pass TF32
+};
+
+template <int MODE>  // 0 = K2 forward, 1 = K4a dgrad
+__global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("notorch_b200: dynamic shared memory base is not 1 KiB aligned\n");
+    __trap();
+  }
+  const uint32_t bar_a_full = sbase + OFF_BAR;          // [STAGES]
+  const uint32_t bar_w_full = bar_a_full + 8 * STAGES;  // [STAGES]
+  const uint32_t bar_empty = bar_w_full + 8 * STAGES;   // [STAGES]
+  const uint32_t bar_tmem_full = bar_empty + 8 * STAGES;
+  const uint32_t bar_tmem_empty = bar_tmem_full + 8;
+  const uint32_t tmem_slot = bar_tmem_empty + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (3 * STAGES + 2));
+
+  const Geometry& geo = p.geo;
+  const int d = geo.d;
+  const int64_t m_tiles = (p.E + TILE_M - 1) / TILE_M;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_a_full + 8 * s, NUM_A_THREADS);
+      mbar_init(bar_w_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tmem_full, 1);
+    mbar_init(bar_tmem_empty, NUM_EPI_WARPS * 32);
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < NUM_EPI_WARPS) {
+    // ===================================== EPILOGUE =====================================
+    uint8_t* stage = smem + OFF_EPI + warp * EPI_WARP_BYTES;
+    uint32_t tphase = 0;
+    const int chunks = geo.n_tile / EPI_COLS;
+    for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      const int64_t row0 = tile * TILE_M + warp * 32;
+      for (int nt = 0; nt < geo.n_tiles; ++nt) {
+        mbar_wait(bar_tmem_full, tphase);
+        tc_fence_after();
+        for (int cc = 0; cc < chunks; ++cc) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * EPI_COLS), v);
+          tmem_ld_wait();
+          if (cc == chunks - 1) {  // accumulator fully read: hand TMEM back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(bar_tmem_empty);
+          }
+          // thread = row; write 16 columns to the padded staging row
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(stage + lane * EPI_ROW_BYTES + q * 16) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          // 4 lanes per row (64 contiguous bytes), 8 rows per step: coalesced global traffic
+          const int col = nt * geo.n_tile + cc * EPI_COLS + (lane & 3) * 4;
+          if (col < d) {
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == 0 && p.bias) bias4 = ldg4(p.bias + col);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + (lane >> 2);
+              const int64_t e = row0 + r;
+              if (e < p.E) {
+                float4 acc = *reinterpret_cast<const float4*>(stage + r * EPI_ROW_BYTES + (lane & 3) * 16);
+                if (MODE == 0) {
+                  acc = make_float4(acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w);
+                  if (p.drop_p > 0.f) {
+                    float4 s = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)col, p.drop_thr, p.inv_keep);
+                    acc = make_float4(acc.x * s.x, acc.y * s.y, acc.z * s.z, acc.w * s.w);
+                  }
+                  if (p.resid) {
+                    float4 hv = ldg4_stream(p.resid + e * d + col);
+                    acc = make_float4(hv.x + acc.x, hv.y + acc.y, hv.z + acc.z, hv.w + acc.w);
+                  }
+                }
+                stg4(p.out + e * d + col, acc);
+              }
+            }
+          }
+          __syncwarp();
+        }
+        tphase ^= 1;
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================================== MMA ISSUER =====================================
+    const uint32_t idesc_a = make_idesc_tf32(geo.n_a);
+    const uint32_t idesc_b = make_idesc_tf32(geo.n_b > 0 ? geo.n_b : 16);
+    int s = 0;
+    uint32_t ph = 0, tphase = 0;
+    for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      for (int nt = 0; nt < geo.n_tiles; ++nt) {
+        mbar_wait(bar_tmem_empty, tphase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < geo.k_blocks; ++kb) {
+          mbar_wait(bar_a_full + 8 * s, ph);
+          mbar_wait(bar_w_full + 8 * s, ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const int rem = d - kb * BLOCK_K;
+            const int ksteps = rem >= BLOCK_K ? BLOCK_K / 8 : (rem + 7) / 8;
+            const uint32_t a_hi = sbase + OFF_A_HI + s * A_STAGE_BYTES, a_lo = sbase + OFF_A_LO + s * A_STAGE_BYTES;
+            const uint32_t w_hi = sbase + OFF_W_HI + s * W_STAGE_BYTES, w_lo = sbase + OFF_W_LO + s * W_STAGE_BYTES;
+            for (int j = 0; j < ksteps; ++j) {
+              const uint32_t koff = j * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+              const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff), da_lo = make_kmajor_sw128_desc(a_lo + koff);
+              const uint32_t first = (kb | j) != 0 ? 1u : 0u;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                if (half == 1 && geo.n_b == 0) break;
+                const uint32_t woff = half ? (uint32_t)geo.n_a * 128u : 0u;
+                const uint32_t dcol = tmem_base + (half ? (uint32_t)geo.n_a : 0u);
+                const uint32_t idesc = half ? idesc_b : idesc_a;
+                const uint64_t db_hi = make_kmajor_sw128_desc(w_hi + woff + koff), db_lo = make_kmajor_sw128_desc(w_lo + woff + koff);
+                if (p.products == 3) {
+                  umma_tf32(dcol, da_lo, db_hi, idesc, first);  // small terms first
+                  umma_tf32(dcol, da_hi, db_lo, idesc, 1u);
+                  umma_tf32(dcol, da_hi, db_hi, idesc, 1u);
+                } else {
+                  umma_tf32(dcol, da_hi, db_hi, idesc, first);
+                }
+              }
+            }
+            umma_commit(bar_empty + 8 * s);                               // frees this smem stage when the MMAs retire
+            if (kb == geo.k_blocks - 1) umma_commit(bar_tmem_full);       // accumulator complete
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        tphase ^= 1;
+      }
+    }
+  } else if (warp == W_WARP) {
+    // ===================================== W PRODUCER (bulk TMA) =====================================
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t tile_bytes = (uint32_t)geo.n_tile * 128u;
+    for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      for (int nt = 0; nt < geo.n_tiles; ++nt) {
+        for (int kb = 0; kb < geo.k_blocks; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          if (lane == 0) {
+            const size_t off = ((size_t)nt * geo.k_blocks + kb) * tile_bytes;
+            const bool need_lo = p.products == 3;
+            mbar_arrive_expect_tx(bar_w_full + 8 * s, need_lo ? 2 * tile_bytes : tile_bytes);
+            bulk_copy_g2s(sbase + OFF_W_HI + s * W_STAGE_BYTES, p.wimg + off, tile_bytes, bar_w_full + 8 * s);
+            if (need_lo) bulk_copy_g2s(sbase + OFF_W_LO + s * W_STAGE_BYTES, p.wimg + geo.part_bytes + off, tile_bytes, bar_w_full + 8 * s);
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================================== A PRODUCER =====================================
+    const int pt = threadIdx.x - FIRST_A_WARP * 32;  // 0..255
+    const int c = pt & 7;                            // 16-byte chunk inside the 128-byte K-block row
+    const int r0 = pt >> 3;                          // rows r0, r0+32, r0+64, r0+96
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      int64_t rowA[4], rowB[4];
+      bool valid[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t e = tile * TILE_M + r0 + 32 * i;
+        valid[i] = e < p.E;
+        if (MODE == 0) {
+          rowA[i] = valid[i] ? (int64_t)__ldg(p.src + e) * d : 0;
+          rowB[i] = valid[i] ? (int64_t)__ldg(p.rev + e) * d : 0;
+        } else {
+          rowA[i] = e * d;
+          rowB[i] = 0;
+        }
+      }
+      for (int nt = 0; nt < geo.n_tiles; ++nt) {
+        for (int kb = 0; kb < geo.k_blocks; ++kb) {
+          const int k0 = kb * BLOCK_K + c * 4;
+          const bool kvalid = k0 < d;
+          float4 va[4], vb[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {  // all loads first: 8 x 16 B in flight per thread
+            va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[i] = va[i];
+            if (valid[i] && kvalid) {
+              if (MODE == 0) {
+                va[i] = ldg4(p.a0 + rowA[i] + k0);
+                vb[i] = ldg4_stream(p.a1 + rowB[i] + k0);
+              } else {
+                va[i] = ldg4_stream(p.a0 + rowA[i] + k0);
+              }
+            }
+          }
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          uint8_t* a_hi = smem + OFF_A_HI + s * A_STAGE_BYTES;
+          uint8_t* a_lo = smem + OFF_A_LO + s * A_STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 m;
+            if (MODE == 0) {
+              float4 a = act_fwd4(vb[i], p.act, p.act_param);
+              m = make_float4(va[i].x - a.x, va[i].y - a.y, va[i].z - a.z, va[i].w - a.w);
+            } else {
+              m = va[i];
+              if (p.drop_p > 0.f && valid[i] && kvalid) {
+                float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)(rowA[i] + k0), p.drop_thr, p.inv_keep);
+                m = make_float4(m.x * sc.x, m.y * sc.y, m.z * sc.z, m.w * sc.w);
+              }
+            }
+            float4 hi = make_float4(tf32_rna(m.x), tf32_rna(m.y), tf32_rna(m.z), tf32_rna(m.w));
+            float4 lo = make_float4(tf32_rna(m.x - hi.x), tf32_rna(m.y - hi.y), tf32_rna(m.z - hi.z), tf32_rna(m.w - hi.w));
+            const uint32_t off = swz128((uint32_t)(r0 + 32 * i), (uint32_t)c);
+            *reinterpret_cast<float4*>(a_hi + off) = hi;
+            *reinterpret_cast<float4*>(a_lo + off) = lo;
+          }
+          fence_proxy_async();  // make the generic-proxy writes visible to the tensor core (async proxy)
+          mbar_arrive(bar_a_full + 8 * s);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// W [d,d] -> hi/lo TF32 parts in the swizzled K-major tile image consumed by the bulk copies above.
+__global__ void __launch_bounds__(256) weight_prepare_kernel(const float* __restrict__ W, Geometry geo, int transpose, uint8_t* __restrict__ image) {
+  const int64_t total = (int64_t)geo.n_tiles * geo.k_blocks * geo.n_tile * BLOCK_K;
+  int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= total) return;
+  const int kk = (int)(t % BLOCK_K);
+  int64_t q = t / BLOCK_K;
+  const int r = (int)(q % geo.n_tile);
+  q /= geo.n_tile;
+  const int kb = (int)(q % geo.k_blocks);
+  const int nt = (int)(q / geo.k_blocks);
+  const int n = nt * geo.n_tile + r, k = kb * BLOCK_K + kk;
+  float v = 0.f;
+  if (n < geo.d && k < geo.d) v = transpose ? __ldg(W + (int64_t)k * geo.d + n) : __ldg(W + (int64_t)n * geo.d + k);
+  const float hi = tf32_rna(v);
+  const float lo = tf32_rna(v - hi);
+  const size_t off = ((size_t)nt * geo.k_blocks + kb) * geo.n_tile * 128 + swz128((uint32_t)r, (uint32_t)(kk >> 2)) + (kk & 3) * 4;
+  *reinterpret_cast<float*>(image + off) = hi;
+  *reinterpret_cast<float*>(image + geo.part_bytes + off) = lo;
+}
+
+template <int MODE>
+static int launch(const Params& p, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(layer_gemm_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(layer_gemm_tc)");
+  const int64_t m_tiles = (p.E + TILE_M - 1) / TILE_M;
+  int grid = num_sms();
+  if (grid <= 0) grid = 148;
+  if (m_tiles < grid) grid = (int)m_tiles;
+  layer_gemm_tc<MODE><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  NT_LAUNCH_CHECK("layer_gemm_tc");
+  return NT_OK;
+}
+
+static void fill_dropout(Params& p, float drop_p, uint64_t seed, uint64_t offset) {
+  p.drop_p = drop_p;
+  p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  double t = (double)drop_p * 4294967296.0;
+  p.drop_thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  p.seed = seed;
+  p.offset = offset;
+}
+
+}  // namespace tc
+
+size_t tc_weight_image_bytes(int64_t d) { return 2 * tc::make_geometry((int)d).part_bytes; }
+
+int tc_weight_prepare(const float* W, int64_t d, int transpose, void* image, cudaStream_t st) {
+  tc::Geometry geo = tc::make_geometry((int)d);
+  const int64_t total = (int64_t)geo.n_tiles * geo.k_blocks * geo.n_tile * tc::BLOCK_K;
+  tc::weight_prepare_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(W, geo, transpose, static_cast<uint8_t*>(image));
+  NT_LAUNCH_CHECK("weight_prepare_kernel");
+  return NT_OK;
+}
+
+int tc_layer_forward(const float* h, const float* n, const int32_t* src, const int32_t* rev, const void* wimg, const float* bias, int64_t E, int64_t d,
+                     int act, float act_param, int residual, float drop_p, uint64_t seed, uint64_t offset, float* out, int products, cudaStream_t st) {
+  tc::Params p{};
+  p.a0 = n; p.a1 = h; p.src = src; p.rev = rev; p.wimg = static_cast<const uint8_t*>(wimg); p.bias = bias;
+  p.resid = residual ? h : nullptr; p.out = out; p.E = E; p.geo = tc::make_geometry((int)d);
+  p.act = act; p.act_param = act_param; p.products = products;
+  tc::fill_dropout(p, drop_p, seed, offset);
+  return tc::launch<0>(p, st);
+}
+
+int tc_layer_dgrad(const float* g, const void* wimg, int64_t E, int64_t d, float drop_p, uint64_t seed, uint64_t offset, float* g_m, int products,
+                   cudaStream_t st) {
+  tc::Params p{};
+  p.a0 = g; p.wimg = static_cast<const uint8_t*>(wimg); p.out = g_m; p.E = E; p.geo = tc::make_geometry((int)d);
+  p.act = NT_ACT_IDENTITY; p.products = products;
+  tc::fill_dropout(p, drop_p, seed, offset);
+  return tc::launch<1>(p, st);
+}
+
+}  // namespace nt

@@ -1,0 +1,252 @@
+// HBM-bound row kernels: segmented reductions (K1/K3/K5), gather-add (K0 and the backward of the
+// reductions) and the backward epilogue of a message-passing depth (K6).
+//
+// Thread mapping: the [rows, d] output is flattened to (row, 16-byte chunk) work items so every lane
+// is busy for any d (d = 300 -> 75 chunks per row) and a warp always touches one contiguous span of
+// the output; gathers read whole 16-byte chunks of the source rows. Segments are accumulated
+// SEQUENTIALLY in ascending item order (no cross-lane tree over the segment), which makes K1/K3
+// bit-identical to the reference's CPU scatter_add_ and run-to-run deterministic
+// (the stock GPU path, atomicAdd in scatter_gather_elementwise_kernel, is neither).
+#include "common.cuh"
+
+namespace nt {
+
+constexpr int ROW_THREADS = 256;
+
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// ------------------------------------------------------------------------------------------------
+// seg_reduce, vectorised: one thread per (segment, float4 chunk)
+// ------------------------------------------------------------------------------------------------
+template <bool HAS_PERM>
+__global__ void __launch_bounds__(ROW_THREADS) seg_reduce_v4(const float* __restrict__ x, int d, int chunks, const int32_t* __restrict__ rowptr,
+                                                              const int32_t* __restrict__ perm, int64_t total, int act, float act_param,
+                                                              int mean, float scale, float* __restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
+  if (t >= total) return;
+  int s = (int)(t / chunks);
+  int c = (int)(t - (int64_t)s * chunks) * 4;
+  int lo = __ldg(rowptr + s), hi = __ldg(rowptr + s + 1);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int j = lo;
+  // 4 independent row loads in flight, added in ascending order
+  for (; j + 4 <= hi; j += 4) {
+    int r0, r1, r2, r3;
+    if (HAS_PERM) { r0 = __ldg(perm + j); r1 = __ldg(perm + j + 1); r2 = __ldg(perm + j + 2); r3 = __ldg(perm + j + 3); }
+    else { r0 = j; r1 = j + 1; r2 = j + 2; r3 = j + 3; }
+    float4 v0 = ldg4(x + (int64_t)r0 * d + c), v1 = ldg4(x + (int64_t)r1 * d + c);
+    float4 v2 = ldg4(x + (int64_t)r2 * d + c), v3 = ldg4(x + (int64_t)r3 * d + c);
+    if (act != NT_ACT_IDENTITY) { v0 = act_fwd4(v0, act, act_param); v1 = act_fwd4(v1, act, act_param); v2 = act_fwd4(v2, act, act_param); v3 = act_fwd4(v3, act, act_param); }
+    acc = add4(acc, v0); acc = add4(acc, v1); acc = add4(acc, v2); acc = add4(acc, v3);
+  }
+  if (j + 2 <= hi) {
+    int r0 = HAS_PERM ? __ldg(perm + j) : j, r1 = HAS_PERM ? __ldg(perm + j + 1) : j + 1;
+    float4 v0 = ldg4(x + (int64_t)r0 * d + c), v1 = ldg4(x + (int64_t)r1 * d + c);
+    if (act != NT_ACT_IDENTITY) { v0 = act_fwd4(v0, act, act_param); v1 = act_fwd4(v1, act, act_param); }
+    acc = add4(acc, v0); acc = add4(acc, v1);
+    j += 2;
+  }
+  if (j < hi) {
+    int r0 = HAS_PERM ? __ldg(perm + j) : j;
+    float4 v0 = ldg4(x + (int64_t)r0 * d + c);
+    if (act != NT_ACT_IDENTITY) v0 = act_fwd4(v0, act, act_param);
+    acc = add4(acc, v0);
+  }
+  if (mean) {
+    float cnt = (float)max(hi - lo, 1);  // torch_scatter.scatter_mean: count.clamp(min=1), true division
+    acc = make_float4(acc.x / cnt, acc.y / cnt, acc.z / cnt, acc.w / cnt);
+  }
+  if (scale != 1.f) acc = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+  stg4(out + (int64_t)s * d + c, acc);
+}
+
+// scalar fallback for d % 4 != 0 (or unaligned bases): one thread per (segment, element)
+__global__ void __launch_bounds__(ROW_THREADS) seg_reduce_s(const float* __restrict__ x, int d, const int32_t* __restrict__ rowptr,
+                                                             const int32_t* __restrict__ perm, int64_t total, int act, float act_param, int mean,
+                                                             float scale, float* __restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
+  if (t >= total) return;
+  int s = (int)(t / d);
+  int c = (int)(t - (int64_t)s * d);
+  int lo = __ldg(rowptr + s), hi = __ldg(rowptr + s + 1);
+  float acc = 0.f;
+  for (int j = lo; j < hi; ++j) {
+    int r = perm ? __ldg(perm + j) : j;
+    acc += act_fwd(__ldg(x + (int64_t)r * d + c), act, act_param);
+  }
+  if (mean) acc = acc / (float)max(hi - lo, 1);
+  if (scale != 1.f) acc *= scale;
+  out[(int64_t)s * d + c] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather_add: out[i] = base[i] + scale * x[idx[i]] / max(count(idx[i]), 1)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) gather_add_v4(const float* __restrict__ base, const float* __restrict__ x, const int32_t* __restrict__ idx,
+                                                              const int32_t* __restrict__ mean_rowptr, int d, int chunks, int64_t total, float scale,
+                                                              float* __restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
+  if (t >= total) return;
+  int i = (int)(t / chunks);
+  int c = (int)(t - (int64_t)i * chunks) * 4;
+  int r = __ldg(idx + i);
+  float4 v = ldg4(x + (int64_t)r * d + c);
+  if (mean_rowptr) {
+    float cnt = (float)max(__ldg(mean_rowptr + r + 1) - __ldg(mean_rowptr + r), 1);
+    v = make_float4(v.x / cnt, v.y / cnt, v.z / cnt, v.w / cnt);
+  }
+  if (scale != 1.f) v = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+  if (base) v = add4(ldg4_stream(base + (int64_t)i * d + c), v);
+  stg4(out + (int64_t)i * d + c, v);
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) gather_add_s(const float* __restrict__ base, const float* __restrict__ x, const int32_t* __restrict__ idx,
+                                                             const int32_t* __restrict__ mean_rowptr, int d, int64_t total, float scale,
+                                                             float* __restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
+  if (t >= total) return;
+  int i = (int)(t / d);
+  int c = (int)(t - (int64_t)i * d);
+  int r = __ldg(idx + i);
+  float v = __ldg(x + (int64_t)r * d + c);
+  if (mean_rowptr) v = v / (float)max(__ldg(mean_rowptr + r + 1) - __ldg(mean_rowptr + r), 1);
+  if (scale != 1.f) v *= scale;
+  if (base) v = __ldg(base + t) + v;
+  out[t] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6 backward epilogue
+// ------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(ROW_THREADS) layer_bwd_epilogue(const float* __restrict__ g, const float* __restrict__ h, const float* __restrict__ g_n,
+                                                                   const float* __restrict__ g_m, const int32_t* __restrict__ dst,
+                                                                   const int32_t* __restrict__ rev_rowptr, const int32_t* __restrict__ rev_perm,
+                                                                   const int32_t* __restrict__ dst_rowptr, int d, int chunks, int64_t total, int act,
+                                                                   float act_param, int residual, int mean, float* __restrict__ g_h) {
+  int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
+  if (t >= total) return;
+  int e = (int)(t / chunks);
+  int c = (int)(t - (int64_t)e * chunks) * (VEC ? 4 : 1);
+  int v = __ldg(dst + e);
+  int lo = __ldg(rev_rowptr + e), hi = __ldg(rev_rowptr + e + 1);
+  float inv_cnt_div = 1.f;
+  if (mean) inv_cnt_div = (float)max(__ldg(dst_rowptr + v + 1) - __ldg(dst_rowptr + v), 1);
+  if (VEC) {
+    float4 ga = ldg4(g_n + (int64_t)v * d + c);
+    if (mean) ga = make_float4(ga.x / inv_cnt_div, ga.y / inv_cnt_div, ga.z / inv_cnt_div, ga.w / inv_cnt_div);
+    float4 sub = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = lo; j < hi; ++j) sub = add4(sub, ldg4(g_m + (int64_t)__ldg(rev_perm + j) * d + c));
+    float4 hv = ldg4_stream(h + (int64_t)e * d + c);
+    float4 r = make_float4(act_bwd(hv.x, act, act_param) * (ga.x - sub.x), act_bwd(hv.y, act, act_param) * (ga.y - sub.y),
+                           act_bwd(hv.z, act, act_param) * (ga.z - sub.z), act_bwd(hv.w, act, act_param) * (ga.w - sub.w));
+    if (residual) r = add4(ldg4_stream(g + (int64_t)e * d + c), r);
+    stg4(g_h + (int64_t)e * d + c, r);
+  } else {
+    float ga = __ldg(g_n + (int64_t)v * d + c);
+    if (mean) ga = ga / inv_cnt_div;
+    float sub = 0.f;
+    for (int j = lo; j < hi; ++j) sub += __ldg(g_m + (int64_t)__ldg(rev_perm + j) * d + c);
+    float r = act_bwd(__ldg(h + (int64_t)e * d + c), act, act_param) * (ga - sub);
+    if (residual) r = __ldg(g + (int64_t)e * d + c) + r;
+    g_h[(int64_t)e * d + c] = r;
+  }
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) dropout_mask_kernel(int64_t total, float p, uint64_t seed, uint64_t offset, float* __restrict__ mask) {
+  int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
+  if (t >= total) return;
+  mask[t] = p > 0.f ? (dropout_scale1(seed, offset, (uint64_t)t, dropout_threshold(p), 1.f)) : 1.f;
+}
+
+}  // namespace nt
+
+using namespace nt;
+
+static bool vec_ok(int64_t d, const void* a, const void* b = nullptr, const void* c = nullptr, const void* e = nullptr, const void* f = nullptr) {
+  return d % 4 == 0 && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(e) && aligned16(f);
+}
+
+extern "C" int nt_seg_reduce(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int act, float act_param,
+                             int mean, float scale, void* out, int dtype, nt_stream_t stream) {
+  NT_CHECK_ARG(dtype == NT_F32 || dtype == NT_BF16, "nt_seg_reduce: bad dtype");
+  if (dtype != NT_F32) { set_error("nt_seg_reduce: only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
+  NT_CHECK_ARG(d > 0 && d < (1 << 20) && num_segments >= 0 && num_segments < INT32_MAX, "nt_seg_reduce: bad sizes");
+  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "nt_seg_reduce: bad activation");
+  if (num_segments == 0) return NT_OK;
+  NT_CHECK_ARG(rowptr && out, "nt_seg_reduce: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const float* xf = static_cast<const float*>(x);
+  float* of = static_cast<float*>(out);
+  if (vec_ok(d, x, out)) {
+    int chunks = (int)(d / 4);
+    int64_t total = num_segments * chunks;
+    unsigned grid = (unsigned)cdiv(total, ROW_THREADS);
+    if (perm) seg_reduce_v4<true><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, of);
+    else seg_reduce_v4<false><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, of);
+  } else {
+    int64_t total = num_segments * d;
+    seg_reduce_s<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(xf, (int)d, rowptr, perm, total, act, act_param, mean, scale, of);
+  }
+  NT_LAUNCH_CHECK("nt_seg_reduce");
+  return NT_OK;
+}
+
+extern "C" int nt_gather_add(const void* base, const void* x, const int32_t* idx, const int32_t* mean_rowptr, int64_t n, int64_t d, float scale,
+                             void* out, int dtype, nt_stream_t stream) {
+  if (dtype != NT_F32) { set_error("nt_gather_add: only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
+  NT_CHECK_ARG(d > 0 && d < (1 << 20) && n >= 0 && n < INT32_MAX, "nt_gather_add: bad sizes");
+  if (n == 0) return NT_OK;
+  NT_CHECK_ARG(x && idx && out, "nt_gather_add: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (vec_ok(d, x, out, base)) {
+    int chunks = (int)(d / 4);
+    int64_t total = n * chunks;
+    gather_add_v4<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(static_cast<const float*>(base), static_cast<const float*>(x), idx,
+                                                                              mean_rowptr, (int)d, chunks, total, scale, static_cast<float*>(out));
+  } else {
+    int64_t total = n * d;
+    gather_add_s<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(static_cast<const float*>(base), static_cast<const float*>(x), idx,
+                                                                             mean_rowptr, (int)d, total, scale, static_cast<float*>(out));
+  }
+  NT_LAUNCH_CHECK("nt_gather_add");
+  return NT_OK;
+}
+
+extern "C" int nt_layer_backward_epilogue(const void* g, const void* h, const void* g_n, const void* g_m, const int32_t* dst,
+                                          const int32_t* rev_rowptr, const int32_t* rev_perm, const int32_t* dst_rowptr, int64_t E, int64_t d,
+                                          int act, float act_param, int residual, int mean, void* g_h, int dtype, nt_stream_t stream) {
+  if (dtype != NT_F32) { set_error("nt_layer_backward_epilogue: only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
+  NT_CHECK_ARG(d > 0 && d < (1 << 20) && E >= 0 && E < INT32_MAX, "nt_layer_backward_epilogue: bad sizes");
+  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "nt_layer_backward_epilogue: bad activation");
+  if (E == 0) return NT_OK;
+  NT_CHECK_ARG(h && g_n && g_m && dst && rev_rowptr && rev_perm && g_h, "nt_layer_backward_epilogue: null pointer");
+  NT_CHECK_ARG(!residual || g, "nt_layer_backward_epilogue: residual needs g");
+  NT_CHECK_ARG(!mean || dst_rowptr, "nt_layer_backward_epilogue: mean needs dst_rowptr");
+  cudaStream_t st = as_stream(stream);
+  const float *gf = static_cast<const float*>(g), *hf = static_cast<const float*>(h), *gn = static_cast<const float*>(g_n),
+              *gm = static_cast<const float*>(g_m);
+  float* out = static_cast<float*>(g_h);
+  if (vec_ok(d, g, h, g_n, g_m, g_h)) {
+    int chunks = (int)(d / 4);
+    int64_t total = E * chunks;
+    layer_bwd_epilogue<true><<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(gf, hf, gn, gm, dst, rev_rowptr, rev_perm, dst_rowptr, (int)d,
+                                                                                         chunks, total, act, act_param, residual, mean, out);
+  } else {
+    int64_t total = E * d;
+    layer_bwd_epilogue<false><<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(gf, hf, gn, gm, dst, rev_rowptr, rev_perm, dst_rowptr, (int)d,
+                                                                                          (int)d, total, act, act_param, residual, mean, out);
+  }
+  NT_LAUNCH_CHECK("nt_layer_backward_epilogue");
+  return NT_OK;
+}
+
+extern "C" int nt_dropout_mask(int64_t n_rows, int64_t d, float dropout_p, uint64_t seed, uint64_t offset, float* mask, nt_stream_t stream) {
+  NT_CHECK_ARG(n_rows >= 0 && d > 0 && dropout_p >= 0.f && dropout_p < 1.f, "nt_dropout_mask: bad arguments");
+  int64_t total = n_rows * d;
+  if (total == 0) return NT_OK;
+  NT_CHECK_ARG(mask, "nt_dropout_mask: null pointer");
+  dropout_mask_kernel<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, as_stream(stream)>>>(total, dropout_p, seed, offset, mask);
+  NT_LAUNCH_CHECK("nt_dropout_mask");
+  return NT_OK;
+}

@@ -1,0 +1,498 @@
+"""Host-side operators of the D-MPNN hot path: thin tensor -> C-ABI wrappers and the hand-written
+autograd around them. PyTorch is plumbing here (device memory, streams, autograd graph); all
+arithmetic happens in ``libnotorch_b200.so``. CPU tensors raise — there is no fallback.
+
+Kernel legend: K0 edge_init, K1 edge->atom, K2 fused layer forward, K3 read-out,
+K4 dgrad/wgrad, K5 gather backward (segmented sum by src), K6 layer backward epilogue, K-l CSR.
+"""
+from __future__ import annotations
+
+import os
+import threading
+from dataclasses import dataclass, field
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import GEMM_FP32, GEMM_TF32, GEMM_TF32X3, NT_F32
+
+__all__ = [
+    "GraphCSR", "SegmentCSR", "build_segment_csr", "graph_csr", "segment_csr_for", "seg_reduce", "gather_add",
+    "edge_init", "edge_to_atom", "readout", "layer", "set_gemm_mode", "get_gemm_mode", "collate_packed",
+    "dropout_mask", "set_index_validation",
+]
+
+ACT_CODES = {
+    torch.nn.Identity: (_lib.ACT_IDENTITY, lambda m: 0.0),
+    torch.nn.ReLU: (_lib.ACT_RELU, lambda m: 0.0),
+    torch.nn.LeakyReLU: (_lib.ACT_LEAKY_RELU, lambda m: float(m.negative_slope)),
+    torch.nn.ELU: (_lib.ACT_ELU, lambda m: float(m.alpha)),
+    torch.nn.SiLU: (_lib.ACT_SILU, lambda m: 0.0),
+    torch.nn.GELU: (_lib.ACT_GELU, lambda m: 0.0),
+    torch.nn.Tanh: (_lib.ACT_TANH, lambda m: 0.0),
+}
+
+_GEMM_MODES = {"tf32x3": GEMM_TF32X3, "fp32": GEMM_FP32, "tf32": GEMM_TF32}
+_gemm_mode = _GEMM_MODES[os.environ.get("NOTORCH_B200_GEMM", "tf32x3").lower()]
+_validate_mode = os.environ.get("NOTORCH_B200_VALIDATE", "sync").lower()  # "sync" | "deferred" | "off"
+
+
+def set_gemm_mode(mode: str) -> None:
+    """``"tf32x3"`` (tcgen05, error-compensated; default), ``"fp32"`` (FFMA) or ``"tf32"`` (single pass)."""
+    global _gemm_mode
+    _gemm_mode = _GEMM_MODES[mode.lower()]
+
+
+def get_gemm_mode() -> str:
+    return {v: k for k, v in _GEMM_MODES.items()}[_gemm_mode]
+
+
+def set_index_validation(mode: str) -> None:
+    """When the out-of-range verdict of the CSR build is read back: ``"sync"`` (immediately; one
+    device sync per new batch), ``"deferred"`` (checked on the next batch) or ``"off"``."""
+    global _validate_mode
+    assert mode in ("sync", "deferred", "off")
+    _validate_mode = mode
+
+
+def act_code(act: torch.nn.Module | None) -> tuple[int, float]:
+    """Map an activation *module instance* to the closed set compiled into the kernels."""
+    if act is None:
+        return _lib.ACT_IDENTITY, 0.0
+    for cls, (code, param) in ACT_CODES.items():
+        if type(act) is cls:
+            if cls is torch.nn.GELU and getattr(act, "approximate", "none") != "none":
+                break
+            return code, param(act)
+    raise NotImplementedError(
+        f"notorch_b200: activation {type(act).__name__} is not compiled into the kernels "
+        f"(supported: {', '.join(c.__name__ for c in ACT_CODES)}); there is no fallback path")
+
+
+# ------------------------------------------------------------------------------------------------
+# plumbing
+# ------------------------------------------------------------------------------------------------
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _require(t: Tensor, name: str, dtype: torch.dtype | None = None, dim: int | None = None) -> Tensor:
+    if not isinstance(t, Tensor):
+        raise TypeError(f"notorch_b200: {name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"notorch_b200: {name} is on {t.device}; the hot path runs on CUDA only (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"notorch_b200: {name} must be {dtype}, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise RuntimeError(f"notorch_b200: {name} must be {dim}-D, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _require_float(t: Tensor, name: str) -> Tensor:
+    t = _require(t, name, dim=2)
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"notorch_b200: {name} has dtype {t.dtype}; this build implements float32 only")
+    return t
+
+
+_ws_lock = threading.Lock()
+_workspaces: dict[tuple[int, int], Tensor] = {}
+
+
+def _workspace(device: torch.device, nbytes: int, slot: int = 0) -> Tensor:
+    """Grow-only scratch buffer per (device, slot); kernels on one stream serialise their use of it."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    with _ws_lock:
+        ws = _workspaces.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            _workspaces[key] = ws
+        return ws
+
+
+# ------------------------------------------------------------------------------------------------
+# CSR bundles (K-l)
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class SegmentCSR:
+    """Stable CSR of items grouped by key: ``perm[rowptr[s]:rowptr[s+1]]`` = item ids with key ``s``
+    in ascending order; ``keys32`` = the int32 copy of the key vector."""
+
+    rowptr: Tensor  # [S+1] int32
+    perm: Tensor | None  # [n] int32 (None = identity / contiguous segments)
+    keys32: Tensor  # [n] int32
+    num_segments: int
+    status: Tensor | None = None  # [1] int32 device flag, bit 0 = key out of range
+
+
+_pending_checks: list[tuple[Tensor, torch.cuda.Event, str]] = []
+
+
+def _check_status(status: Tensor, what: str) -> None:
+    if _validate_mode == "off":
+        return
+    if _validate_mode == "sync":
+        if int(status.item()) != 0:
+            raise IndexError(f"notorch_b200: {what}: index out of range")
+        return
+    # deferred: look at the verdicts of earlier batches that have completed by now
+    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host.copy_(status, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _pending_checks.append((host, ev, what))
+    while _pending_checks and _pending_checks[0][1].query():
+        h, _, w = _pending_checks.pop(0)
+        if int(h[0]) != 0:
+            raise IndexError(f"notorch_b200: {w}: index out of range (detected on a later batch)")
+
+
+def build_segment_csr(keys: Tensor, num_segments: int, what: str = "index", status: Tensor | None = None,
+                      validate: bool = True) -> SegmentCSR:
+    keys = _require(keys, what, torch.int64, 1)
+    n = keys.numel()
+    dev = keys.device
+    with torch.cuda.device(dev):
+        L = _lib.lib()
+        rowptr = torch.empty(num_segments + 1, dtype=torch.int32, device=dev)
+        perm = torch.empty(n, dtype=torch.int32, device=dev)
+        keys32 = torch.empty(n, dtype=torch.int32, device=dev)
+        if status is None:
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+        nbytes = L.nt_build_csr_workspace_bytes(n, num_segments)
+        ws = _workspace(dev, nbytes)
+        _lib.check(L.nt_build_csr(_p(keys), n, num_segments, _p(keys32), _p(rowptr), _p(perm), _p(status), _p(ws), ws.numel(), _stream()),
+                   "nt_build_csr")
+    if validate:
+        _check_status(status, what)
+    return SegmentCSR(rowptr, perm, keys32, num_segments, status)
+
+
+@dataclass
+class GraphCSR:
+    """Everything the kernels need about one (batched) graph's topology, int32, built once per batch."""
+
+    V: int
+    E: int
+    by_dst: SegmentCSR  # K1: incoming edges of each atom (keys32 = dst)
+    by_src: SegmentCSR  # K5: outgoing edges of each atom (keys32 = src)
+    by_rev: SegmentCSR  # K6: inverse map of the (arbitrary) gather index rev (keys32 = rev)
+    key: tuple = field(default_factory=tuple)
+
+    @property
+    def src(self) -> Tensor:
+        return self.by_src.keys32
+
+    @property
+    def dst(self) -> Tensor:
+        return self.by_dst.keys32
+
+    @property
+    def rev(self) -> Tensor:
+        return self.by_rev.keys32
+
+
+def _tensor_key(t: Tensor) -> tuple:
+    return (t.data_ptr(), tuple(t.shape), t._version, t.device.index)
+
+
+def build_graph_csr(edge_index: Tensor, rev_index: Tensor, num_nodes: int) -> GraphCSR:
+    edge_index = _require(edge_index, "edge_index", torch.int64, 2)
+    rev_index = _require(rev_index, "rev_index", torch.int64, 1)
+    if edge_index.shape[0] != 2:
+        raise RuntimeError(f"notorch_b200: edge_index must have shape [2, E], got {tuple(edge_index.shape)}")
+    E = edge_index.shape[1]
+    if rev_index.shape[0] != E:
+        raise RuntimeError(f"notorch_b200: rev_index has {rev_index.shape[0]} entries for {E} edges")
+    status = torch.zeros(1, dtype=torch.int32, device=edge_index.device)
+    by_src = build_segment_csr(edge_index[0], num_nodes, "edge_index[0]", status, validate=False)
+    by_dst = build_segment_csr(edge_index[1], num_nodes, "edge_index[1]", status, validate=False)
+    by_rev = build_segment_csr(rev_index, E, "rev_index", status, validate=False)
+    _check_status(status, "edge_index / rev_index")
+    return GraphCSR(num_nodes, E, by_dst, by_src, by_rev)
+
+
+def graph_csr(G, num_nodes: int | None = None) -> GraphCSR:
+    """CSR bundle of a ``Graph``/``BatchedGraph``, cached on the object (``Graph.update`` makes
+    shallow copies, so the cache rides along GraphEmbedding -> ChempropBlock -> Aggregation)."""
+    V = len(G.node_feats) if num_nodes is None else num_nodes
+    key = (_tensor_key(G.edge_index), _tensor_key(G.rev_index), V)
+    cached = getattr(G, "_nt_csr", None)
+    if cached is not None and cached.key == key:
+        return cached
+    csr = build_graph_csr(G.edge_index, G.rev_index, V)
+    csr.key = key
+    try:
+        G._nt_csr = csr
+    except AttributeError:  # pragma: no cover - slotted foreign object
+        pass
+    return csr
+
+
+_layer_csr_cache: list[tuple[tuple, GraphCSR]] = []
+
+
+def graph_csr_from_tensors(edge_index: Tensor, rev_index: Tensor, num_nodes: int) -> GraphCSR:
+    """Small LRU for the stand-alone ``ChempropLayer.forward(edge_feats, node_feats, edge_index, rev_index)``."""
+    key = (_tensor_key(edge_index), _tensor_key(rev_index), num_nodes)
+    for k, c in _layer_csr_cache:
+        if k == key:
+            return c
+    csr = build_graph_csr(edge_index, rev_index, num_nodes)
+    csr.key = key
+    _layer_csr_cache.insert(0, (key, csr))
+    del _layer_csr_cache[4:]
+    return csr
+
+
+def segment_csr_for(G, attr: str, num_segments: int) -> SegmentCSR:
+    """CSR of ``G.<attr>`` (e.g. ``batch_node_index``), cached on the graph object."""
+    t = getattr(G, attr)
+    key = (_tensor_key(t), num_segments)
+    cache = getattr(G, "_nt_seg_csr", None)
+    if cache is None:
+        cache = {}
+        try:
+            G._nt_seg_csr = cache
+        except AttributeError:  # pragma: no cover
+            pass
+    hit = cache.get(attr)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    csr = build_segment_csr(t, num_segments, attr)
+    cache[attr] = (key, csr)
+    return csr
+
+
+# ------------------------------------------------------------------------------------------------
+# raw kernels
+# ------------------------------------------------------------------------------------------------
+
+def _seg_reduce_raw(x: Tensor, csr: SegmentCSR, act: int = 0, act_param: float = 0.0, mean: bool = False, scale: float = 1.0) -> Tensor:
+    d = x.shape[1]
+    out = torch.empty((csr.num_segments, d), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().nt_seg_reduce(_p(x), d, _p(csr.rowptr), _p(csr.perm), csr.num_segments, act, act_param, int(mean), scale,
+                                        _p(out), NT_F32, _stream()), "nt_seg_reduce")
+    return out
+
+
+def _gather_add_raw(base: Tensor | None, x: Tensor, idx32: Tensor, mean_rowptr: Tensor | None, scale: float = 1.0) -> Tensor:
+    n, d = idx32.numel(), x.shape[1]
+    out = torch.empty((n, d), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().nt_gather_add(_p(base), _p(x), _p(idx32), _p(mean_rowptr), n, d, scale, _p(out), NT_F32, _stream()), "nt_gather_add")
+    return out
+
+
+def _weight_image(W: Tensor, transpose: bool) -> Tensor | None:
+    if _gemm_mode == GEMM_FP32 or W.shape[0] % 4 != 0:
+        return None
+    L = _lib.lib()
+    d = W.shape[0]
+    img = torch.empty(L.nt_weight_image_bytes(d), dtype=torch.uint8, device=W.device)
+    _lib.check(L.nt_weight_prepare(_p(W), d, int(transpose), _p(img), NT_F32, _stream()), "nt_weight_prepare")
+    return img
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd
+# ------------------------------------------------------------------------------------------------
+
+class _SegReduce(torch.autograd.Function):
+    """K1 (no activation) / K3: out[s] = sum|mean of x over segment s; backward is a row gather."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, csr: SegmentCSR, mean: bool, scale: float):
+        x = _require_float(x, "x")
+        if x.shape[0] != csr.keys32.numel():
+            raise RuntimeError(f"notorch_b200: {x.shape[0]} rows but the index has {csr.keys32.numel()} entries")
+        with torch.cuda.device(x.device):
+            out = _seg_reduce_raw(x, csr, 0, 0.0, mean, scale)
+        ctx.csr, ctx.mean, ctx.scale = csr, mean, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        csr = ctx.csr
+        g = g.contiguous()
+        with torch.cuda.device(g.device):
+            gx = _gather_add_raw(None, g, csr.keys32, csr.rowptr if ctx.mean else None, ctx.scale)
+        return gx, None, None, None
+
+
+class _GatherAdd(torch.autograd.Function):
+    """K0: out[i] = base[i] + x[idx[i]]  (chemprop.py:83); backward of the gather is K5."""
+
+    @staticmethod
+    def forward(ctx, base: Tensor, x: Tensor, csr: SegmentCSR):
+        base, x = _require_float(base, "edge_feats"), _require_float(x, "node_feats")
+        if base.shape[0] != csr.keys32.numel() or x.shape[0] != csr.num_segments or base.shape[1] != x.shape[1]:
+            raise RuntimeError(f"notorch_b200: edge_init shape mismatch: node_feats {tuple(x.shape)}, edge_feats {tuple(base.shape)}, "
+                               f"E={csr.keys32.numel()}, V={csr.num_segments}")
+        with torch.cuda.device(x.device):
+            out = _gather_add_raw(base, x, csr.keys32, None)
+        ctx.csr = csr
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        g = g.contiguous()
+        gx = None
+        if ctx.needs_input_grad[1]:
+            with torch.cuda.device(g.device):
+                gx = _seg_reduce_raw(g, ctx.csr)
+        return (g if ctx.needs_input_grad[0] else None), gx, None
+
+
+_dropout_calls = 0
+
+
+class _Layer(torch.autograd.Function):
+    """One message-passing depth: K1 + K2 forward, K4a + K4b + K5 + K6 backward.
+
+    h' = [h +] Dropout(Linear(n[src] - act(h)[rev])),  n = reduce_dst(act(h))   (chemprop.py:36-41, residual.py:28)
+    """
+
+    @staticmethod
+    def forward(ctx, h: Tensor, W: Tensor, b: Tensor | None, csr: GraphCSR, act: int, act_param: float, mean: bool,
+                residual: bool, p: float, seed: int, offset: int, mode: int):
+        h = _require_float(h, "edge_feats")
+        W = _require_float(W, "weight")
+        E, d = h.shape
+        if E != csr.E:
+            raise RuntimeError(f"notorch_b200: edge_feats has {E} rows but edge_index has {csr.E} edges")
+        if W.shape != (d, d):
+            raise RuntimeError(f"notorch_b200: weight {tuple(W.shape)} does not match hidden size {d}")
+        if b is not None:
+            b = _require(b, "bias", torch.float32, 1)
+        L = _lib.lib()
+        with torch.cuda.device(h.device):
+            n = _seg_reduce_raw(h, csr.by_dst, act, act_param, mean)  # K1
+            img = _weight_image(W, False) if mode != GEMM_FP32 else None
+            out = torch.empty_like(h)
+            _lib.check(L.nt_layer_forward(_p(h), _p(n), _p(csr.src), _p(csr.rev), _p(W), _p(img), _p(b), E, csr.V, d, act, act_param,
+                                          int(residual), p, seed, offset, _p(out), NT_F32, mode, _stream()), "nt_layer_forward")  # K2
+        ctx.save_for_backward(h, n, W)
+        ctx.csr, ctx.cfg, ctx.has_bias = csr, (act, act_param, mean, residual, p, seed, offset, mode), b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        h, n, W = ctx.saved_tensors
+        csr = ctx.csr
+        act, act_param, mean, residual, p, seed, offset, mode = ctx.cfg
+        E, d = h.shape
+        g = g.contiguous()
+        L = _lib.lib()
+        gW = gb = gh = None
+        with torch.cuda.device(g.device):
+            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                gW = torch.empty_like(W)
+                gb = torch.empty(d, dtype=W.dtype, device=W.device) if ctx.has_bias else None
+                nbytes = L.nt_layer_backward_wgrad_workspace_bytes(E, d)
+                ws = _workspace(g.device, nbytes, slot=1)
+                _lib.check(L.nt_layer_backward_wgrad(_p(g), _p(h), _p(n), _p(csr.src), _p(csr.rev), E, csr.V, d, act, act_param, p, seed, offset,
+                                                     _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream()), "nt_layer_backward_wgrad")  # K4b
+            if ctx.needs_input_grad[0]:
+                img_t = _weight_image(W, True) if mode != GEMM_FP32 else None
+                g_m = torch.empty_like(h)
+                _lib.check(L.nt_layer_backward_dgrad(_p(g), _p(W), _p(img_t), E, d, p, seed, offset, _p(g_m), NT_F32, mode, _stream()),
+                           "nt_layer_backward_dgrad")  # K4a
+                g_n = _seg_reduce_raw(g_m, csr.by_src)  # K5
+                gh = torch.empty_like(h)
+                _lib.check(L.nt_layer_backward_epilogue(_p(g), _p(h), _p(g_n), _p(g_m), _p(csr.dst), _p(csr.by_rev.rowptr), _p(csr.by_rev.perm),
+                                                        _p(csr.by_dst.rowptr), E, d, act, act_param, int(residual), int(mean), _p(gh), NT_F32,
+                                                        _stream()), "nt_layer_backward_epilogue")  # K6
+        return gh, gW, gb, None, None, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# public functional API
+# ------------------------------------------------------------------------------------------------
+
+def seg_reduce(x: Tensor, csr: SegmentCSR, reduce: str = "sum", scale: float = 1.0) -> Tensor:
+    if reduce not in ("sum", "mean"):
+        raise NotImplementedError(f"notorch_b200: reduce='{reduce}' is not implemented (sum and mean are); no fallback")
+    return _SegReduce.apply(x, csr, reduce == "mean", float(scale))
+
+
+def gather_add(base: Tensor, x: Tensor, csr: SegmentCSR) -> Tensor:
+    return _GatherAdd.apply(base, x, csr)
+
+
+def edge_init(node_feats: Tensor, edge_feats: Tensor, csr: GraphCSR) -> Tensor:
+    """K0: ``h0 = node_feats[src] + edge_feats`` (chemprop.py:83)."""
+    return _GatherAdd.apply(edge_feats, node_feats, csr.by_src)
+
+
+def edge_to_atom(edge_feats: Tensor, csr: GraphCSR, reduce: str = "sum") -> Tensor:
+    """K1 without activation: ``scatter(edge_feats, dst, dim_size=V, reduce)`` (chemprop.py:86)."""
+    return seg_reduce(edge_feats, csr.by_dst, reduce)
+
+
+def readout(node_feats: Tensor, mol_csr: SegmentCSR, kind: str = "sum", norm: float = 100.0) -> Tensor:
+    """K3: ``scatter_sum`` / ``scatter_mean`` over ``batch_node_index`` (agg.py:27,36); ``norm`` = sum / constant."""
+    if kind == "norm":
+        return seg_reduce(node_feats, mol_csr, "sum", 1.0 / norm)
+    return seg_reduce(node_feats, mol_csr, kind)
+
+
+def layer(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, *, act: tuple[int, float] = (_lib.ACT_RELU, 0.0),
+          reduce: str = "sum", residual: bool = True, dropout: float = 0.0, training: bool = False) -> Tensor:
+    """One fused message-passing depth (K1+K2; hand-written backward K4-K6)."""
+    global _dropout_calls
+    if reduce not in ("sum", "mean"):
+        raise NotImplementedError(f"notorch_b200: reduce='{reduce}' is not implemented (sum and mean are); no fallback")
+    p = float(dropout) if training else 0.0
+    if not 0.0 <= p < 1.0:
+        if p == 1.0:
+            raise NotImplementedError("notorch_b200: dropout p=1.0 is not supported")
+        raise ValueError(f"dropout probability has to be between 0 and 1, but got {p}")
+    seed = offset = 0
+    if p > 0.0:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())  # CPU generator: follows torch.manual_seed, no device sync
+        _dropout_calls += 1
+        offset = _dropout_calls
+    return _Layer.apply(h, weight, bias, csr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)
+
+
+def dropout_mask(n_rows: int, d: int, p: float, seed: int, offset: int, device) -> Tensor:
+    """The keep-mask K2/K4 derive from (seed, offset) — exposed for tests."""
+    mask = torch.empty((n_rows, d), dtype=torch.float32, device=device)
+    with torch.cuda.device(mask.device):
+        _lib.check(_lib.lib().nt_dropout_mask(n_rows, d, p, seed, offset, _p(mask), _stream()), "nt_dropout_mask")
+    return mask
+
+
+def collate_packed(num_atoms: Tensor, num_edges: Tensor, local_edge_index: Tensor, local_rev_index: Tensor,
+                   V: int, E: int, fixed_rev: bool = False) -> dict[str, Tensor]:
+    """K-l: device-side ``BatchedGraph.from_graphs`` on packed int32 inputs already on the GPU
+    (graph.py:186-223). Returns the reference's int64 index tensors plus int32 molecule row pointers."""
+    num_atoms = _require(num_atoms, "num_atoms", torch.int32, 1)
+    num_edges = _require(num_edges, "num_edges", torch.int32, 1)
+    lei = _require(local_edge_index, "local_edge_index", torch.int32, 2)
+    lrev = _require(local_rev_index, "local_rev_index", torch.int32, 1)
+    B, dev = num_atoms.numel(), num_atoms.device
+    if lei.shape != (2, E) or lrev.shape != (E,) or num_edges.numel() != B:
+        raise RuntimeError("notorch_b200: packed molecule arrays have inconsistent shapes")
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        out = {
+            "edge_index": torch.empty((2, E), dtype=torch.int64, device=dev),
+            "rev_index": torch.empty(E, dtype=torch.int64, device=dev),
+            "batch_node_index": torch.empty(V, dtype=torch.int64, device=dev),
+            "batch_edge_index": torch.empty(E, dtype=torch.int64, device=dev),
+            "mol_atom_ptr": torch.empty(B + 1, dtype=torch.int32, device=dev),
+            "mol_edge_ptr": torch.empty(B + 1, dtype=torch.int32, device=dev),
+        }
+        ws = _workspace(dev, L.nt_collate_workspace_bytes(B))
+        _lib.check(L.nt_collate(_p(num_atoms), _p(num_edges), B, _p(lei), _p(lrev), V, E, int(fixed_rev), _p(out["edge_index"]),
+                                _p(out["rev_index"]), _p(out["batch_node_index"]), _p(out["batch_edge_index"]), _p(out["mol_atom_ptr"]),
+                                _p(out["mol_edge_ptr"]), _p(ws), ws.numel(), _stream()), "nt_collate")
+    return out
