@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the D-MPNN hot path — BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, one process per GPU)
+    python bench.py --impl reference --steps K --warmup W     # reference CPU path (oracle port) on host cores
+
+metric   : molecules/sec, forward + backward, D-MPNN depth 3 hidden 300 (configs[1]: batch 4096
+           ZINC-size synthetic graphs per GPU, fp32, Sum read-out)
+a step   : collation + CSR build of one batch -> ChempropBlock -> Sum -> loss = H.square().mean()
+           -> backward -> (N > 1: NCCL all-reduce of the flat gradient) -> fused Adam step
+value    : whole-job molecules/s with the batch already resident in HBM (CUDA events, max over ranks)
+e2e      : same step through the public API starting from pinned HOST buffers (H2D of the step's inputs
+           and a D2H read of the loss inside the timed region)
+roofline : dominant kernel's algorithmic bytes / its CUDA-event time / measured HBM peak
+cpu_baseline : the CPU oracle port (same ATen op sequence as the reference) on this box's host cores
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "molecules/sec fwd+bwd, D-MPNN d=3 h=300"
+UNIT = "molecules/s"
+
+WORKLOADS = {
+    # name: (synthetic config id, batch per GPU, hidden, depth, readout)
+    "c2": dict(config=2, batch=4096, d=300, depth=3, agg="sum", desc="BASELINE configs[1]: D-MPNN depth=3 hidden=300 Sum readout, "
+                                                                     "batch 4096 synthetic ZINC-size graphs per GPU, fp32 training step"),
+    "c1": dict(config=1, batch=64, d=300, depth=3, agg="sum", desc="BASELINE configs[0]: batch 64 ~25-atom molecules"),
+    "c3": dict(config=3, batch=16384, d=1024, depth=5, agg="mean", desc="BASELINE configs[2]: depth=5 hidden=1024 Mean readout, batch 16384 per GPU"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="override molecules per GPU")
+    ap.add_argument("--gemm", default=None, choices=["tf32x3", "fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel-table", action="store_true", help="print the per-kernel table to stderr")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------
+
+def make_workload(wl: dict, rank: int, batch: int):
+    from notorch_b200.synth import config_seed, make_molecules
+
+    seed = config_seed(wl["config"], rank)
+    mols = make_molecules(batch, wl["config"], seed=seed)
+    gen = torch.Generator().manual_seed(seed)
+    V, E, d = mols.total_atoms, mols.total_edges, wl["d"]
+    x_v = torch.randn(V, d, generator=gen)
+    x_e = torch.randn(E, d, generator=gen)
+    return mols, x_v, x_e
+
+
+def algorithmic_bytes(V: int, E: int, B: int, d: int, L: int, s: int = 4) -> dict[str, float]:
+    """Per-launch algorithmic bytes of each kernel class, and the whole step."""
+    return {
+        "K0": (V + 2 * E) * d * s + 4 * E,
+        "K1": (E + V) * d * s + 4 * (E + V + 1),
+        "K5": (E + V) * d * s + 4 * (E + V + 1),
+        "K2": (V + 3 * E) * d * s + d * d * s + 8 * E,
+        "K3": (V + B) * d * s + 4 * (B + 1),
+        "K4a": 2 * E * d * s + d * d * s,  # dgrad: reads g, writes g_m
+        "K4b": (V + 2 * E) * d * s + d * d * s,  # wgrad: reads g, n[src], h[rev]; writes gW
+        "K6": (V + 4 * E) * d * s + 12 * E,
+        "K1bwd": (V + 2 * E) * d * s + 4 * E,  # g_hL = gE + g_node[dst]
+        "K3bwd": (V + B) * d * s + 4 * V,
+        "step": d * s * (6 * E + 5 * V + B + L * (12 * E + 5 * V)),
+    }
+
+
+def gemm_flops(E: int, d: int) -> float:
+    return 2.0 * E * d * d
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows: list[list[str]] = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg (oracle port) — the checker used as the timed CPU baseline, nothing from it is shipped
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_run(wl: dict, batch: int, steps: int, warmup: int, budget_s: float) -> dict:
+    from oracle import dmpnn_oracle as O
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    mols, x_v, x_e = make_workload(wl, 0, batch)
+    # bounded sample: shrink the per-step batch until (warmup + steps) fits the budget
+    sample = batch
+    model = O.CpuPort(hidden_dim=wl["d"], depth=wl["depth"], agg=wl["agg"])
+
+    def prep(nmol):
+        sub = mols.shard(0, batch // nmol) if nmol < batch else mols
+        c = O.collate(sub.split())
+        V, E = sub.total_atoms, sub.total_edges
+        return (x_v[:V].clone().requires_grad_(True), x_e[:E].clone().requires_grad_(True), torch.from_numpy(c["edge_index"]),
+                torch.from_numpy(c["rev_index"]), torch.from_numpy(c["batch_node_index"]), len(sub))
+
+    args = prep(sample)
+    t0 = time.perf_counter()
+    O.train_step_cpu(model, *args)
+    one = time.perf_counter() - t0
+    while sample > 64 and one * (steps + warmup) > budget_s:
+        sample //= 2
+        args = prep(sample)
+        t0 = time.perf_counter()
+        O.train_step_cpu(model, *args)
+        one = time.perf_counter() - t0
+    for _ in range(warmup):
+        O.train_step_cpu(model, *args)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.train_step_cpu(model, *args)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": sample * steps / total, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} timed steps (after {warmup} warm-up) of zero_grad+forward+backward on {sample} of the {batch} molecules of the "
+                      f"workload batch, torch CPU fp32, {threads} threads",
+            "ms_per_step": 1e3 * total / steps, "sample_molecules": sample}
+
+
+def run_reference_arm(args, wl, batch):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_run(wl, batch, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "hidden": wl["d"], "depth": wl["depth"], "readout": wl["agg"], "batch_per_step": res["sample_molecules"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA leg
+# ------------------------------------------------------------------------------------------------
+
+def run_ours(args, wl, batch):
+    import torch.distributed as dist
+
+    from notorch_b200 import BatchedGraph, _lib, ops
+    from notorch_b200.nn import ChempropBlock, Mean, Sum
+    from notorch_b200.parallel import FlatGradients
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU leg")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gemm:
+        ops.set_gemm_mode(args.gemm)
+    ops.set_index_validation("deferred")  # no per-batch device sync; an out-of-range index still raises (one batch late)
+
+    mols, x_v, x_e = make_workload(wl, rank, batch)
+    V, E, d, L = mols.total_atoms, mols.total_edges, wl["d"], wl["depth"]
+    torch.manual_seed(0)
+    block = ChempropBlock(hidden_dim=d, depth=L).to(dev)
+    agg = (Sum if wl["agg"] == "sum" else Mean)()
+    params = list(block.parameters())
+    flat = FlatGradients(params)
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+
+    # pinned host copies (e2e leg) and device-resident copies (value leg)
+    host = {"x_v": x_v.pin_memory(), "x_e": x_e.pin_memory(),
+            "num_atoms": torch.from_numpy(mols.num_atoms).pin_memory(), "num_edges": torch.from_numpy(mols.num_edges).pin_memory(),
+            "edge_index": torch.from_numpy(mols.edge_index).pin_memory(), "rev_index": torch.from_numpy(mols.rev_index).pin_memory()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    class Packed:
+        def __init__(self, t):
+            self.num_atoms, self.num_edges, self.edge_index, self.rev_index = t["num_atoms"], t["num_edges"], t["edge_index"], t["rev_index"]
+
+    def step(src: dict, from_host: bool):
+        if from_host:
+            t = {k: v.to(dev, non_blocking=True) for k, v in src.items()}
+        else:
+            t = src
+        xv, xe = t["x_v"].detach().requires_grad_(True), t["x_e"].detach().requires_grad_(True)
+        G = BatchedGraph.from_packed(Packed(t), xv, xe, device=dev)  # collation kernel (K-l)
+        H = agg(block(G))  # CSR build + K0 + L x (K1, K2) + K1 + K3
+        loss = H.square().mean()
+        flat.zero()
+        loss.backward()  # K3bwd, K1bwd, L x (K4b, K4a, K5, K6), K5
+        flat.all_reduce_mean()  # NCCL over NVLink when world > 1 (no-op otherwise)
+        opt.step()
+        return loss
+
+    def timed(nsteps: int, src: dict, from_host: bool):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        last = None
+        for _ in range(nsteps):
+            loss = step(src, from_host)
+            if from_host:
+                last = float(loss)  # D2H read of the step's result inside the timed region
+        ev1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = ev0.elapsed_time(ev1)
+        if from_host:
+            ms = max(ms, wall * 1e3)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt)
+        return ms, last
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident, False)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.lib().nt_kernel_launch_count()
+    ms_total, _ = timed(args.steps, resident, False)
+    launches = _lib.lib().nt_kernel_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    value = world * batch * args.steps / (ms_total * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step(host, True)
+        e2e_ms, _ = timed(args.steps, host, True)
+        e2e = {"value": world * batch * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+               "ms_per_step": e2e_ms / args.steps,
+               "inputs": "float node/edge features [V,d],[E,d] fp32 + packed int32 topology, from pinned host memory"}
+
+    # ---- per-kernel CUDA-event timing (a separate instrumented pass over the same steps) ----
+    roof = kernels = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        nprof = min(args.steps, 10)
+        with ops.KernelTimer() as kt:
+            for _ in range(nprof):
+                step(resident, False)
+        summ = kt.summary()
+        alg = algorithmic_bytes(V, E, batch, d, L)
+        kernels = []
+        for tag, rec in sorted(summ.items(), key=lambda kv: -kv[1]["total_ms"]):
+            cls = tag.split(":")[0]
+            row = {"kernel": tag, "launches_per_step": rec["launches"] / nprof, "avg_ms": rec["avg_ms"], "ms_per_step": rec["total_ms"] / nprof}
+            if cls in alg:
+                row["alg_bytes"] = alg[cls]
+                row["gbs"] = alg[cls] / (rec["avg_ms"] * 1e-3) / 1e9
+                row["hbm_frac"] = row["gbs"] / hbm_peak
+            if cls in ("K2", "K4a", "K4b"):
+                row["alg_tflops"] = gemm_flops(E, d) / (rec["avg_ms"] * 1e-3) / 1e12
+            kernels.append(row)
+        dom = next((k for k in kernels if "alg_bytes" in k), None)
+        if dom is not None:
+            roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"],
+                    "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": dom["avg_ms"],
+                    "measured_over": f"{nprof} instrumented steps after the timed region (CUDA events around every C-ABI call)",
+                    "step_alg_bytes": alg["step"], "step_hbm_frac": alg["step"] / (ms_total / args.steps * 1e-3) / 1e9 / hbm_peak}
+        if args.kernel_table:
+            for k in kernels:
+                print(json.dumps(k), file=sys.stderr)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_run(wl, batch, steps=3, warmup=1, budget_s=25.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "hidden": d, "depth": L, "readout": wl["agg"], "batch_per_gpu": batch, "atoms_per_gpu": V,
+                       "edges_per_gpu": E, "gemm": ops.get_gemm_mode(), "parallelism": f"dp{world}",
+                       "step": "collate+CSR, forward, loss, backward, grad all-reduce (N>1), fused Adam",
+                       "l2": "working set per step (>1.5 GB) exceeds the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    wl = WORKLOADS[args.workload]
+    batch = args.batch or wl["batch"]
+    if args.impl == "reference":
+        run_reference_arm(args, wl, batch)
+    else:
+        run_ours(args, wl, batch)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,8 @@ enum nt_gemm_mode {
 
 const char* nt_last_error_string(void);
 int nt_version(void);
+/* Number of kernels this library has launched in this process so far (all threads). */
+long long nt_kernel_launch_count(void);
 /* 1 if the current device is compute capability 10.x (tcgen05 available), else 0; <0 on error. */
 int nt_device_supported(void);
 

@@ -25,6 +25,7 @@ _i64, _int, _f32, _u64, _sz = C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_siz
 SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "nt_last_error_string": (C.c_char_p, []),
     "nt_version": (_int, []),
+    "nt_kernel_launch_count": (C.c_longlong, []),
     "nt_device_supported": (_int, []),
     "nt_collate_workspace_bytes": (_sz, [_i64]),
     "nt_collate": (_int, [_i32p, _i32p, _i64, _i32p, _i32p, _i64, _i64, _int, _i64p, _i64p, _i64p, _i64p, _i32p, _i32p, _vp, _sz, _vp]),

@@ -1,5 +1,7 @@
 // extern "C" entry points that dispatch between the arithmetic paths, plus error plumbing.
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -7,6 +9,9 @@
 namespace nt {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -61,6 +66,7 @@ using namespace nt;
 
 extern "C" const char* nt_last_error_string(void) { return g_err; }
 extern "C" int nt_version(void) { return 100; }
+extern "C" long long nt_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int nt_device_supported(void) {
   int dev = 0;

@@ -27,10 +27,12 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return nt::cuda_fail(e__, #call);  \
   } while (0)
 
-#define NT_LAUNCH_CHECK(name)                                       \
+// checks the launch(es) just issued and adds `n` to the process-wide kernel-launch counter
+#define NT_LAUNCH_CHECK(name, n)                                    \
   do {                                                              \
     cudaError_t e__ = cudaGetLastError();                           \
     if (e__ != cudaSuccess) return nt::cuda_fail(e__, name);        \
+    nt::count_launches(n);                                          \
   } while (0)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -38,6 +40,7 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline cudaStream_t as_stream(nt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int num_sms();
+void count_launches(int n);
 
 // ---- activations (closed set compiled into every kernel; chemprop.py:17,24,37) -------------
 __device__ __forceinline__ float act_fwd(float x, int act, float p) {

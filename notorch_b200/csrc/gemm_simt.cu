@@ -182,7 +182,7 @@ int simt_layer_forward(const float* h, const float* n, const int32_t* src, const
   pr.W = W; pr.bias = bias; pr.h = h; pr.out = out; pr.drop = make_drop(p, seed, offset); pr.residual = residual;
   dim3 grid((unsigned)cdiv(E, BM), (unsigned)cdiv(d, BN), 1);
   simt_gemm_kernel<ForwardProblem><<<grid, GEMM_THREADS, 0, st>>>(pr);
-  NT_LAUNCH_CHECK("simt_layer_forward");
+  NT_LAUNCH_CHECK("simt_layer_forward", 1);
   return NT_OK;
 }
 
@@ -192,7 +192,7 @@ int simt_layer_dgrad(const float* g, const float* W, int64_t E, int64_t d, float
   pr.g = g; pr.W = W; pr.g_m = g_m; pr.drop = make_drop(p, seed, offset);
   dim3 grid((unsigned)cdiv(E, BM), (unsigned)cdiv(d, BN), 1);
   simt_gemm_kernel<DgradProblem><<<grid, GEMM_THREADS, 0, st>>>(pr);
-  NT_LAUNCH_CHECK("simt_layer_dgrad");
+  NT_LAUNCH_CHECK("simt_layer_dgrad", 1);
   return NT_OK;
 }
 
@@ -211,7 +211,7 @@ int simt_layer_wgrad(const float* g, const float* h, const float* n, const int32
   simt_gemm_kernel<WgradProblem><<<grid, GEMM_THREADS, 0, st>>>(pr);
   int64_t total = d * (d + 1);
   wgrad_reduce<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(partial, splits, (int)d, gW, gb);
-  NT_LAUNCH_CHECK("simt_layer_wgrad");
+  NT_LAUNCH_CHECK("simt_layer_wgrad", 2);
   return NT_OK;
 }
 

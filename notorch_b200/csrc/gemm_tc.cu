@@ -444,7 +444,7 @@ static int launch(const Params& p, cudaStream_t st) {
   if (grid <= 0) grid = 148;
   if (m_tiles < grid) grid = (int)m_tiles;
   layer_gemm_tc<MODE><<<grid, THREADS, SMEM_BYTES, st>>>(p);
-  NT_LAUNCH_CHECK("layer_gemm_tc");
+  NT_LAUNCH_CHECK("layer_gemm_tc", 1);
   return NT_OK;
 }
 
@@ -465,7 +465,7 @@ int tc_weight_prepare(const float* W, int64_t d, int transpose, void* image, cud
   tc::Geometry geo = tc::make_geometry((int)d);
   const int64_t total = (int64_t)geo.n_tiles * geo.k_blocks * geo.n_tile * tc::BLOCK_K;
   tc::weight_prepare_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(W, geo, transpose, static_cast<uint8_t*>(image));
-  NT_LAUNCH_CHECK("weight_prepare_kernel");
+  NT_LAUNCH_CHECK("weight_prepare_kernel", 1);
   return NT_OK;
 }
 

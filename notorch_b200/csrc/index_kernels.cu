@@ -99,7 +99,7 @@ static int exclusive_scan(const int32_t* in, int64_t n, int32_t* out, int32_t* s
   scan_tile_sums<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, scratch);
   scan_tile_offsets<<<1, 1024, 0, st>>>(scratch, tiles);
   scan_apply<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, scratch, out);
-  NT_LAUNCH_CHECK("exclusive_scan");
+  NT_LAUNCH_CHECK("exclusive_scan", 3);
   return NT_OK;
 }
 
@@ -210,7 +210,7 @@ extern "C" int nt_collate(const int32_t* num_atoms, const int32_t* num_edges, in
     collate_edges<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(mol_atom_ptr, mol_edge_ptr, (int)B, local_edge_index, local_rev_index, E,
                                                           rev_offset_mode, edge_index, rev_index, batch_edge_index);
   }
-  NT_LAUNCH_CHECK("nt_collate");
+  NT_LAUNCH_CHECK("nt_collate", (V > 0) + (E > 0));
   return NT_OK;
 }
 
@@ -244,6 +244,6 @@ extern "C" int nt_build_csr(const int64_t* keys, int64_t n, int64_t num_segments
     csr_fill<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(keys, n, num_segments, rowptr, cursor, perm_unsorted);
     csr_rank_sort<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(keys, n, num_segments, rowptr, perm_unsorted, perm);
   }
-  NT_LAUNCH_CHECK("nt_build_csr");
+  NT_LAUNCH_CHECK("nt_build_csr", n > 0 ? 3 : 0);
   return NT_OK;
 }

@@ -188,7 +188,7 @@ extern "C" int nt_seg_reduce(const void* x, int64_t d, const int32_t* rowptr, co
     int64_t total = num_segments * d;
     seg_reduce_s<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(xf, (int)d, rowptr, perm, total, act, act_param, mean, scale, of);
   }
-  NT_LAUNCH_CHECK("nt_seg_reduce");
+  NT_LAUNCH_CHECK("nt_seg_reduce", 1);
   return NT_OK;
 }
 
@@ -209,7 +209,7 @@ extern "C" int nt_gather_add(const void* base, const void* x, const int32_t* idx
     gather_add_s<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(static_cast<const float*>(base), static_cast<const float*>(x), idx,
                                                                              mean_rowptr, (int)d, total, scale, static_cast<float*>(out));
   }
-  NT_LAUNCH_CHECK("nt_gather_add");
+  NT_LAUNCH_CHECK("nt_gather_add", 1);
   return NT_OK;
 }
 
@@ -237,7 +237,7 @@ extern "C" int nt_layer_backward_epilogue(const void* g, const void* h, const vo
     layer_bwd_epilogue<false><<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(gf, hf, gn, gm, dst, rev_rowptr, rev_perm, dst_rowptr, (int)d,
                                                                                           (int)d, total, act, act_param, residual, mean, out);
   }
-  NT_LAUNCH_CHECK("nt_layer_backward_epilogue");
+  NT_LAUNCH_CHECK("nt_layer_backward_epilogue", 1);
   return NT_OK;
 }
 
@@ -247,6 +247,6 @@ extern "C" int nt_dropout_mask(int64_t n_rows, int64_t d, float dropout_p, uint6
   if (total == 0) return NT_OK;
   NT_CHECK_ARG(mask, "nt_dropout_mask: null pointer");
   dropout_mask_kernel<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, as_stream(stream)>>>(total, dropout_p, seed, offset, mask);
-  NT_LAUNCH_CHECK("nt_dropout_mask");
+  NT_LAUNCH_CHECK("nt_dropout_mask", 1);
   return NT_OK;
 }

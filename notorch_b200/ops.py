@@ -20,7 +20,7 @@ from ._lib import GEMM_FP32, GEMM_TF32, GEMM_TF32X3, NT_F32
 __all__ = [
     "GraphCSR", "SegmentCSR", "build_segment_csr", "graph_csr", "segment_csr_for", "seg_reduce", "gather_add",
     "edge_init", "edge_to_atom", "readout", "layer", "set_gemm_mode", "get_gemm_mode", "collate_packed",
-    "dropout_mask", "set_index_validation",
+    "dropout_mask", "set_index_validation", "KernelTimer",
 ]
 
 ACT_CODES = {
@@ -101,6 +101,51 @@ def _require_float(t: Tensor, name: str) -> Tensor:
     return t
 
 
+class KernelTimer:
+    """Optional per-kernel CUDA-event timing (used by bench.py for the roofline numbers): while
+    active, every C-ABI call is bracketed by two events on the launching stream."""
+
+    def __init__(self):
+        self.records: list[tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
+
+    def __enter__(self):
+        global _timer
+        _timer = self
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = None
+
+    def summary(self) -> dict[str, dict[str, float]]:
+        torch.cuda.synchronize()
+        out: dict[str, dict[str, float]] = {}
+        for tag, s, e in self.records:
+            rec = out.setdefault(tag, {"launches": 0, "total_ms": 0.0})
+            rec["launches"] += 1
+            rec["total_ms"] += s.elapsed_time(e)
+        for rec in out.values():
+            rec["avg_ms"] = rec["total_ms"] / rec["launches"]
+        return out
+
+
+_timer: KernelTimer | None = None
+
+
+def _run(tag: str, fn, *args) -> None:
+    """Call one C-ABI entry point; raise on a non-zero status."""
+    t = _timer
+    if t is None:
+        _lib.check(fn(*args), tag)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
+    t.records.append((tag, s, e))
+    _lib.check(rc, tag)
+
+
 _ws_lock = threading.Lock()
 _workspaces: dict[tuple[int, int], Tensor] = {}
 
@@ -168,8 +213,8 @@ def build_segment_csr(keys: Tensor, num_segments: int, what: str = "index", stat
             status = torch.zeros(1, dtype=torch.int32, device=dev)
         nbytes = L.nt_build_csr_workspace_bytes(n, num_segments)
         ws = _workspace(dev, nbytes)
-        _lib.check(L.nt_build_csr(_p(keys), n, num_segments, _p(keys32), _p(rowptr), _p(perm), _p(status), _p(ws), ws.numel(), _stream()),
-                   "nt_build_csr")
+        _run("csr:nt_build_csr", L.nt_build_csr, _p(keys), n, num_segments, _p(keys32), _p(rowptr), _p(perm), _p(status), _p(ws), ws.numel(),
+             _stream())
     if validate:
         _check_status(status, what)
     return SegmentCSR(rowptr, perm, keys32, num_segments, status)
@@ -275,18 +320,20 @@ def segment_csr_for(G, attr: str, num_segments: int) -> SegmentCSR:
 # raw kernels
 # ------------------------------------------------------------------------------------------------
 
-def _seg_reduce_raw(x: Tensor, csr: SegmentCSR, act: int = 0, act_param: float = 0.0, mean: bool = False, scale: float = 1.0) -> Tensor:
+def _seg_reduce_raw(x: Tensor, csr: SegmentCSR, act: int = 0, act_param: float = 0.0, mean: bool = False, scale: float = 1.0,
+                    tag: str = "K1") -> Tensor:
     d = x.shape[1]
     out = torch.empty((csr.num_segments, d), dtype=x.dtype, device=x.device)
-    _lib.check(_lib.lib().nt_seg_reduce(_p(x), d, _p(csr.rowptr), _p(csr.perm), csr.num_segments, act, act_param, int(mean), scale,
-                                        _p(out), NT_F32, _stream()), "nt_seg_reduce")
+    _run(f"{tag}:nt_seg_reduce", _lib.lib().nt_seg_reduce, _p(x), d, _p(csr.rowptr), _p(csr.perm), csr.num_segments, act, act_param, int(mean),
+         scale, _p(out), NT_F32, _stream())
     return out
 
 
-def _gather_add_raw(base: Tensor | None, x: Tensor, idx32: Tensor, mean_rowptr: Tensor | None, scale: float = 1.0) -> Tensor:
+def _gather_add_raw(base: Tensor | None, x: Tensor, idx32: Tensor, mean_rowptr: Tensor | None, scale: float = 1.0,
+                    tag: str = "K0") -> Tensor:
     n, d = idx32.numel(), x.shape[1]
     out = torch.empty((n, d), dtype=x.dtype, device=x.device)
-    _lib.check(_lib.lib().nt_gather_add(_p(base), _p(x), _p(idx32), _p(mean_rowptr), n, d, scale, _p(out), NT_F32, _stream()), "nt_gather_add")
+    _run(f"{tag}:nt_gather_add", _lib.lib().nt_gather_add, _p(base), _p(x), _p(idx32), _p(mean_rowptr), n, d, scale, _p(out), NT_F32, _stream())
     return out
 
 
@@ -296,7 +343,7 @@ def _weight_image(W: Tensor, transpose: bool) -> Tensor | None:
     L = _lib.lib()
     d = W.shape[0]
     img = torch.empty(L.nt_weight_image_bytes(d), dtype=torch.uint8, device=W.device)
-    _lib.check(L.nt_weight_prepare(_p(W), d, int(transpose), _p(img), NT_F32, _stream()), "nt_weight_prepare")
+    _run("Wprep:nt_weight_prepare", L.nt_weight_prepare, _p(W), d, int(transpose), _p(img), NT_F32, _stream())
     return img
 
 
@@ -308,13 +355,13 @@ class _SegReduce(torch.autograd.Function):
     """K1 (no activation) / K3: out[s] = sum|mean of x over segment s; backward is a row gather."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, csr: SegmentCSR, mean: bool, scale: float):
+    def forward(ctx, x: Tensor, csr: SegmentCSR, mean: bool, scale: float, tag: str):
         x = _require_float(x, "x")
         if x.shape[0] != csr.keys32.numel():
             raise RuntimeError(f"notorch_b200: {x.shape[0]} rows but the index has {csr.keys32.numel()} entries")
         with torch.cuda.device(x.device):
-            out = _seg_reduce_raw(x, csr, 0, 0.0, mean, scale)
-        ctx.csr, ctx.mean, ctx.scale = csr, mean, scale
+            out = _seg_reduce_raw(x, csr, 0, 0.0, mean, scale, tag=tag)
+        ctx.csr, ctx.mean, ctx.scale, ctx.tag = csr, mean, scale, tag
         return out
 
     @staticmethod
@@ -322,8 +369,8 @@ class _SegReduce(torch.autograd.Function):
         csr = ctx.csr
         g = g.contiguous()
         with torch.cuda.device(g.device):
-            gx = _gather_add_raw(None, g, csr.keys32, csr.rowptr if ctx.mean else None, ctx.scale)
-        return gx, None, None, None
+            gx = _gather_add_raw(None, g, csr.keys32, csr.rowptr if ctx.mean else None, ctx.scale, tag=ctx.tag + "bwd")
+        return gx, None, None, None, None
 
 
 class _GatherAdd(torch.autograd.Function):
@@ -346,7 +393,7 @@ class _GatherAdd(torch.autograd.Function):
         gx = None
         if ctx.needs_input_grad[1]:
             with torch.cuda.device(g.device):
-                gx = _seg_reduce_raw(g, ctx.csr)
+                gx = _seg_reduce_raw(g, ctx.csr, tag="K5")
         return (g if ctx.needs_input_grad[0] else None), gx, None
 
 
@@ -373,11 +420,11 @@ class _Layer(torch.autograd.Function):
             b = _require(b, "bias", torch.float32, 1)
         L = _lib.lib()
         with torch.cuda.device(h.device):
-            n = _seg_reduce_raw(h, csr.by_dst, act, act_param, mean)  # K1
+            n = _seg_reduce_raw(h, csr.by_dst, act, act_param, mean, tag="K1")
             img = _weight_image(W, False) if mode != GEMM_FP32 else None
             out = torch.empty_like(h)
-            _lib.check(L.nt_layer_forward(_p(h), _p(n), _p(csr.src), _p(csr.rev), _p(W), _p(img), _p(b), E, csr.V, d, act, act_param,
-                                          int(residual), p, seed, offset, _p(out), NT_F32, mode, _stream()), "nt_layer_forward")  # K2
+            _run("K2:nt_layer_forward", L.nt_layer_forward, _p(h), _p(n), _p(csr.src), _p(csr.rev), _p(W), _p(img), _p(b), E, csr.V, d, act,
+                 act_param, int(residual), p, seed, offset, _p(out), NT_F32, mode, _stream())
         ctx.save_for_backward(h, n, W)
         ctx.csr, ctx.cfg, ctx.has_bias = csr, (act, act_param, mean, residual, p, seed, offset, mode), b is not None
         return out
@@ -397,18 +444,18 @@ class _Layer(torch.autograd.Function):
                 gb = torch.empty(d, dtype=W.dtype, device=W.device) if ctx.has_bias else None
                 nbytes = L.nt_layer_backward_wgrad_workspace_bytes(E, d)
                 ws = _workspace(g.device, nbytes, slot=1)
-                _lib.check(L.nt_layer_backward_wgrad(_p(g), _p(h), _p(n), _p(csr.src), _p(csr.rev), E, csr.V, d, act, act_param, p, seed, offset,
-                                                     _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream()), "nt_layer_backward_wgrad")  # K4b
+                _run("K4b:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(g), _p(h), _p(n), _p(csr.src), _p(csr.rev), E, csr.V, d, act,
+                     act_param, p, seed, offset, _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream())
             if ctx.needs_input_grad[0]:
                 img_t = _weight_image(W, True) if mode != GEMM_FP32 else None
                 g_m = torch.empty_like(h)
-                _lib.check(L.nt_layer_backward_dgrad(_p(g), _p(W), _p(img_t), E, d, p, seed, offset, _p(g_m), NT_F32, mode, _stream()),
-                           "nt_layer_backward_dgrad")  # K4a
-                g_n = _seg_reduce_raw(g_m, csr.by_src)  # K5
+                _run("K4a:nt_layer_backward_dgrad", L.nt_layer_backward_dgrad, _p(g), _p(W), _p(img_t), E, d, p, seed, offset, _p(g_m), NT_F32,
+                     mode, _stream())
+                g_n = _seg_reduce_raw(g_m, csr.by_src, tag="K5")
                 gh = torch.empty_like(h)
-                _lib.check(L.nt_layer_backward_epilogue(_p(g), _p(h), _p(g_n), _p(g_m), _p(csr.dst), _p(csr.by_rev.rowptr), _p(csr.by_rev.perm),
-                                                        _p(csr.by_dst.rowptr), E, d, act, act_param, int(residual), int(mean), _p(gh), NT_F32,
-                                                        _stream()), "nt_layer_backward_epilogue")  # K6
+                _run("K6:nt_layer_backward_epilogue", L.nt_layer_backward_epilogue, _p(g), _p(h), _p(g_n), _p(g_m), _p(csr.dst),
+                     _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr), E, d, act, act_param, int(residual), int(mean), _p(gh),
+                     NT_F32, _stream())
         return gh, gW, gb, None, None, None, None, None, None, None, None, None
 
 
@@ -416,10 +463,10 @@ class _Layer(torch.autograd.Function):
 # public functional API
 # ------------------------------------------------------------------------------------------------
 
-def seg_reduce(x: Tensor, csr: SegmentCSR, reduce: str = "sum", scale: float = 1.0) -> Tensor:
+def seg_reduce(x: Tensor, csr: SegmentCSR, reduce: str = "sum", scale: float = 1.0, tag: str = "K1") -> Tensor:
     if reduce not in ("sum", "mean"):
         raise NotImplementedError(f"notorch_b200: reduce='{reduce}' is not implemented (sum and mean are); no fallback")
-    return _SegReduce.apply(x, csr, reduce == "mean", float(scale))
+    return _SegReduce.apply(x, csr, reduce == "mean", float(scale), tag)
 
 
 def gather_add(base: Tensor, x: Tensor, csr: SegmentCSR) -> Tensor:
@@ -439,8 +486,8 @@ def edge_to_atom(edge_feats: Tensor, csr: GraphCSR, reduce: str = "sum") -> Tens
 def readout(node_feats: Tensor, mol_csr: SegmentCSR, kind: str = "sum", norm: float = 100.0) -> Tensor:
     """K3: ``scatter_sum`` / ``scatter_mean`` over ``batch_node_index`` (agg.py:27,36); ``norm`` = sum / constant."""
     if kind == "norm":
-        return seg_reduce(node_feats, mol_csr, "sum", 1.0 / norm)
-    return seg_reduce(node_feats, mol_csr, kind)
+        return seg_reduce(node_feats, mol_csr, "sum", 1.0 / norm, tag="K3")
+    return seg_reduce(node_feats, mol_csr, kind, tag="K3")
 
 
 def layer(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, *, act: tuple[int, float] = (_lib.ACT_RELU, 0.0),
@@ -466,7 +513,7 @@ def dropout_mask(n_rows: int, d: int, p: float, seed: int, offset: int, device) 
     """The keep-mask K2/K4 derive from (seed, offset) — exposed for tests."""
     mask = torch.empty((n_rows, d), dtype=torch.float32, device=device)
     with torch.cuda.device(mask.device):
-        _lib.check(_lib.lib().nt_dropout_mask(n_rows, d, p, seed, offset, _p(mask), _stream()), "nt_dropout_mask")
+        _run("nt_dropout_mask", _lib.lib().nt_dropout_mask, n_rows, d, p, seed, offset, _p(mask), _stream())
     return mask
 
 
@@ -492,7 +539,7 @@ def collate_packed(num_atoms: Tensor, num_edges: Tensor, local_edge_index: Tenso
             "mol_edge_ptr": torch.empty(B + 1, dtype=torch.int32, device=dev),
         }
         ws = _workspace(dev, L.nt_collate_workspace_bytes(B))
-        _lib.check(L.nt_collate(_p(num_atoms), _p(num_edges), B, _p(lei), _p(lrev), V, E, int(fixed_rev), _p(out["edge_index"]),
-                                _p(out["rev_index"]), _p(out["batch_node_index"]), _p(out["batch_edge_index"]), _p(out["mol_atom_ptr"]),
-                                _p(out["mol_edge_ptr"]), _p(ws), ws.numel(), _stream()), "nt_collate")
+        _run("collate:nt_collate", L.nt_collate, _p(num_atoms), _p(num_edges), B, _p(lei), _p(lrev), V, E, int(fixed_rev), _p(out["edge_index"]),
+             _p(out["rev_index"]), _p(out["batch_node_index"]), _p(out["batch_edge_index"]), _p(out["mol_atom_ptr"]), _p(out["mol_edge_ptr"]),
+             _p(ws), ws.numel(), _stream())
     return out
