@@ -138,12 +138,14 @@ int nt_weight_prepare(const void* W, int64_t d, int transpose, void* image, int 
  *   out[e,:]= (residual ? h[e,:] : 0) + u[e,:]
  * n is K1's output (act already applied inside K1). rev is an arbitrary in-range gather index.
  * weight_image: from nt_weight_prepare(transpose=0) (ignored for NT_GEMM_FP32, may be NULL).
+ * m_out (nullable, [E,d]): if given, the message tensor m is also written out (saved for K4b so that the
+ * weight gradient can stream it with TMA instead of gathering it again).
  * ---------------------------------------------------------------------------------------------- */
 int nt_layer_forward(const void* h, const void* n, const int32_t* src, const int32_t* rev,
                      const void* W, const void* weight_image, const void* bias,
                      int64_t E, int64_t V, int64_t d, int act, float act_param, int residual,
                      float dropout_p, uint64_t seed, uint64_t offset,
-                     void* out, int dtype, int gemm_mode, nt_stream_t stream);
+                     void* out, void* m_out, int dtype, int gemm_mode, nt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4a — dgrad: g_m[e,:] = (mask . g[e,:] / (1-p)) . W        (backward of aten::addmm wrt input)
@@ -155,11 +157,12 @@ int nt_layer_backward_dgrad(const void* g, const void* W, const void* weight_ima
 
 /* ------------------------------------------------------------------------------------------------
  * K4b — wgrad: gW[o,i] = sum_e g_u[e,o] * m[e,i],  gb[o] = sum_e g_u[e,o]   (gb nullable)
- * with g_u = mask . g / (1-p) and m recomputed from (n, h, src, rev) as in K2. Deterministic:
- * split over edge ranges into `workspace`, then a fixed-order reduction (no atomics).
+ * with g_u = mask . g / (1-p). m is either the tensor K2 saved (`m` != NULL: both operands are streamed
+ * by TMA) or recomputed from (n, h, src, rev) as in K2 (`m` == NULL). Deterministic: split over edge
+ * ranges into `workspace`, then a fixed-order reduction (no atomics).
  * ---------------------------------------------------------------------------------------------- */
 size_t nt_layer_backward_wgrad_workspace_bytes(int64_t E, int64_t d);
-int nt_layer_backward_wgrad(const void* g, const void* h, const void* n, const int32_t* src, const int32_t* rev,
+int nt_layer_backward_wgrad(const void* g, const void* m, const void* h, const void* n, const int32_t* src, const int32_t* rev,
                             int64_t E, int64_t V, int64_t d, int act, float act_param,
                             float dropout_p, uint64_t seed, uint64_t offset,
                             void* gW, void* gb, void* workspace, size_t workspace_bytes,

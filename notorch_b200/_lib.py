@@ -35,10 +35,10 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "nt_gather_add": (_int, [_vp, _vp, _i32p, _i32p, _i64, _i64, _f32, _vp, _int, _vp]),
     "nt_weight_image_bytes": (_sz, [_i64]),
     "nt_weight_prepare": (_int, [_vp, _i64, _int, _vp, _int, _vp]),
-    "nt_layer_forward": (_int, [_vp, _vp, _i32p, _i32p, _vp, _vp, _vp, _i64, _i64, _i64, _int, _f32, _int, _f32, _u64, _u64, _vp, _int, _int, _vp]),
+    "nt_layer_forward": (_int, [_vp, _vp, _i32p, _i32p, _vp, _vp, _vp, _i64, _i64, _i64, _int, _f32, _int, _f32, _u64, _u64, _vp, _vp, _int, _int, _vp]),
     "nt_layer_backward_dgrad": (_int, [_vp, _vp, _vp, _i64, _i64, _f32, _u64, _u64, _vp, _int, _int, _vp]),
     "nt_layer_backward_wgrad_workspace_bytes": (_sz, [_i64, _i64]),
-    "nt_layer_backward_wgrad": (_int, [_vp, _vp, _vp, _i32p, _i32p, _i64, _i64, _i64, _int, _f32, _f32, _u64, _u64, _vp, _vp, _vp, _sz, _int, _int, _vp]),
+    "nt_layer_backward_wgrad": (_int, [_vp, _vp, _vp, _vp, _i32p, _i32p, _i64, _i64, _i64, _int, _f32, _f32, _u64, _u64, _vp, _vp, _vp, _sz, _int, _int, _vp]),
     "nt_layer_backward_epilogue": (_int, [_vp, _vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _int, _vp, _int, _vp]),
     "nt_dropout_mask": (_int, [_i64, _i64, _f32, _u64, _u64, _vp, _vp]),
 }

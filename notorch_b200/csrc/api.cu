@@ -49,9 +49,13 @@ int simt_layer_wgrad(const float*, const float*, const float*, const int32_t*, c
 size_t tc_weight_image_bytes(int64_t d);
 int tc_weight_prepare(const float*, int64_t, int, void*, cudaStream_t);
 int tc_layer_forward(const float*, const float*, const int32_t*, const int32_t*, const void*, const float*, int64_t, int64_t, int, float, int, float,
-                     uint64_t, uint64_t, float*, int, cudaStream_t);
+                     uint64_t, uint64_t, float*, float*, int, cudaStream_t);
 int tc_layer_dgrad(const float*, const void*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
+// wgrad_tma.cu
+size_t tma_wgrad_workspace_bytes(int64_t E, int64_t d);
+int tma_layer_wgrad(const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, float*, void*, size_t, int, cudaStream_t);
 // wgrad_tc.cu
+int tc_bias_grad(const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace_bytes(int64_t E, int64_t d);
 int tc_layer_wgrad(const float*, const float*, const float*, const int32_t*, const int32_t*, int64_t, int64_t, int, float, float, uint64_t, uint64_t,
                    float*, float*, void*, size_t, int, cudaStream_t);
@@ -93,18 +97,20 @@ extern "C" int nt_weight_prepare(const void* W, int64_t d, int transpose, void* 
 
 extern "C" int nt_layer_forward(const void* h, const void* n, const int32_t* src, const int32_t* rev, const void* W, const void* weight_image,
                                 const void* bias, int64_t E, int64_t V, int64_t d, int act, float act_param, int residual, float dropout_p,
-                                uint64_t seed, uint64_t offset, void* out, int dtype, int gemm_mode, nt_stream_t stream) {
+                                uint64_t seed, uint64_t offset, void* out, void* m_out, int dtype, int gemm_mode, nt_stream_t stream) {
   NT_COMMON_LAYER_CHECKS("nt_layer_forward");
   NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "nt_layer_forward: bad activation");
   NT_CHECK_ARG(V >= 0, "nt_layer_forward: bad V");
   if (E == 0) return NT_OK;
   NT_CHECK_ARG(h && n && src && rev && W && out, "nt_layer_forward: null pointer");
   cudaStream_t st = as_stream(stream);
-  if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, h, n, out, bias)) {
+  if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, h, n, out, bias) && aligned16(m_out)) {
     NT_CHECK_ARG(weight_image, "nt_layer_forward: tensor-core path needs weight_image (nt_weight_prepare)");
     return tc_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, weight_image, static_cast<const float*>(bias), E, d,
-                            act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+                            act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), static_cast<float*>(m_out),
+                            gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
   }
+  if (m_out) { set_error("nt_layer_forward: m_out is only produced by the tensor-core path"); return NT_ERR_UNSUPPORTED; }
   return simt_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, static_cast<const float*>(W),
                             static_cast<const float*>(bias), E, d, act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), st);
 }
@@ -127,10 +133,12 @@ extern "C" size_t nt_layer_backward_wgrad_workspace_bytes(int64_t E, int64_t d) 
   if (d <= 0) return 0;
   size_t simt = (size_t)simt_wgrad_splits(E, d) * (size_t)d * (size_t)(d + 1) * sizeof(float);
   size_t tcb = tc_wgrad_workspace_bytes(E, d);
+  size_t tmab = tma_wgrad_workspace_bytes(E, d);
+  if (tmab > tcb) tcb = tmab;
   return (simt > tcb ? simt : tcb) + 256;
 }
 
-extern "C" int nt_layer_backward_wgrad(const void* g, const void* h, const void* n, const int32_t* src, const int32_t* rev, int64_t E, int64_t V,
+extern "C" int nt_layer_backward_wgrad(const void* g, const void* m, const void* h, const void* n, const int32_t* src, const int32_t* rev, int64_t E, int64_t V,
                                        int64_t d, int act, float act_param, float dropout_p, uint64_t seed, uint64_t offset, void* gW, void* gb,
                                        void* workspace, size_t workspace_bytes, int dtype, int gemm_mode, nt_stream_t stream) {
   NT_COMMON_LAYER_CHECKS("nt_layer_backward_wgrad");
@@ -142,11 +150,26 @@ extern "C" int nt_layer_backward_wgrad(const void* g, const void* h, const void*
     if (gb) NT_CUDA(cudaMemsetAsync(gb, 0, (size_t)d * sizeof(float), st));
     return NT_OK;
   }
-  NT_CHECK_ARG(g && h && n && src && rev, "nt_layer_backward_wgrad: null pointer");
+  NT_CHECK_ARG(g && (m || (h && n && src && rev)), "nt_layer_backward_wgrad: null pointer");
   if (!workspace || workspace_bytes < nt_layer_backward_wgrad_workspace_bytes(E, d)) {
     set_error("nt_layer_backward_wgrad: workspace too small");
     return NT_ERR_WORKSPACE;
   }
+  if (m) {  // both operands dense: TMA-streamed tensor-core kernel
+    if (gemm_mode == NT_GEMM_FP32 || !tc_shape_ok(d, g, m, workspace, nullptr)) {
+      set_error("nt_layer_backward_wgrad: a saved m needs the tensor-core path (d %% 4 == 0, 16-byte aligned)");
+      return NT_ERR_UNSUPPORTED;
+    }
+    int rc = tma_layer_wgrad(static_cast<const float*>(g), static_cast<const float*>(m), E, d, dropout_p, seed, offset, static_cast<float*>(gW),
+                             static_cast<float*>(gb), workspace, workspace_bytes, gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+    if (rc != NT_ERR_UNSUPPORTED) return rc;
+    // d % 128 == 0: no spare row for the bias gradient -> weight gradient here, column sums of g_u below
+    rc = tma_layer_wgrad(static_cast<const float*>(g), static_cast<const float*>(m), E, d, dropout_p, seed, offset, static_cast<float*>(gW), nullptr,
+                         workspace, workspace_bytes, gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+    if (rc) return rc;
+    return tc_bias_grad(static_cast<const float*>(g), E, d, dropout_p, seed, offset, static_cast<float*>(gb), workspace, workspace_bytes, st);
+  }
+  NT_CHECK_ARG(h && n && src && rev, "nt_layer_backward_wgrad: null pointer");
   if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, g, h, n, workspace)) {
     int rc = tc_layer_wgrad(static_cast<const float*>(g), static_cast<const float*>(h), static_cast<const float*>(n), src, rev, E, d, act, act_param,
                             dropout_p, seed, offset, static_cast<float*>(gW), static_cast<float*>(gb), workspace, workspace_bytes,

@@ -30,8 +30,7 @@ constexpr int MAX_N_TILE = 304;
 constexpr int A_STAGE_BYTES = TILE_M * 128;          // 16 KiB per part
 constexpr int W_STAGE_BYTES = MAX_N_TILE * 128;      // 38 KiB per part
 constexpr int EPI_COLS = 16;                         // accumulator columns per epilogue step
-constexpr int EPI_ROW_BYTES = EPI_COLS * 4 + 16;     // padded staging row (bank-conflict-free)
-constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;   // 2560
+constexpr int EPI_WARP_BYTES = 32 * EPI_COLS * 4;    // 2 KiB staging tile per epilogue warp (XOR-swizzled)
 constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, W_WARP = 5, FIRST_A_WARP = 6, NUM_A_WARPS = 8;
 constexpr int NUM_A_THREADS = NUM_A_WARPS * 32;
 constexpr int THREADS = (FIRST_A_WARP + NUM_A_WARPS) * 32;  // 448
@@ -73,6 +72,7 @@ struct Params {
   const float* bias;
   const float* resid;  // K2 residual input h (nullable)
   float* out;
+  float* m_out;  // K2: optional copy of the message tensor m [E,d] (saved for the weight gradient)
   int64_t E;
   Geometry geo;
   int act;
@@ -125,48 +125,68 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
 
   if (warp < NUM_EPI_WARPS) {
     // ===================================== EPILOGUE =====================================
+    // Per (tile, N tile): TMEM stays occupied until the last accumulator column has been read, and the next
+    // tile's MMAs wait for it, so nothing in this loop may wait on DRAM: the residual rows are prefetched into
+    // L2 while the MMAs of this tile are still running and then software-pipelined EPI_PF chunks ahead.
     uint8_t* stage = smem + OFF_EPI + warp * EPI_WARP_BYTES;
     uint32_t tphase = 0;
     const int chunks = geo.n_tile / EPI_COLS;
+    const int sub = lane & 3, rsub = lane >> 2;
+    const bool has_resid = MODE == 0 && p.resid != nullptr;
     for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
       const int64_t row0 = tile * TILE_M + warp * 32;
+      if (has_resid && row0 + lane < p.E) l2_prefetch_bulk(p.resid + (row0 + lane) * d, (uint32_t)d * 4u);
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
+        auto load_resid = [&](int cc, float4 (&dst)[4]) {
+          const int col = nt * geo.n_tile + cc * EPI_COLS + sub * 4;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int64_t e = row0 + it * 8 + rsub;
+            dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_resid && cc < chunks && col < d && e < p.E) dst[it] = ldg4_stream(p.resid + e * d + col);
+          }
+        };
+        float4 r0[4], r1[4], r2[4];
+        load_resid(0, r0);
+        load_resid(1, r1);
+        load_resid(2, r2);
         mbar_wait(bar_tmem_full, tphase);
         tc_fence_after();
         for (int cc = 0; cc < chunks; ++cc) {
           uint32_t v[16];
           tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * EPI_COLS), v);
+          float4 cur[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) { cur[it] = r0[it]; r0[it] = r1[it]; r1[it] = r2[it]; }
+          load_resid(cc + 3, r2);
           tmem_ld_wait();
           if (cc == chunks - 1) {  // accumulator fully read: hand TMEM back to the MMA warp
             tc_fence_before();
             mbar_arrive(bar_tmem_empty);
           }
-          // thread = row; write 16 columns to the padded staging row
+          // thread = accumulator row: 16 columns into the XOR-swizzled staging tile (conflict-free both ways)
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(stage + lane * EPI_ROW_BYTES + q * 16) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           __syncwarp();
           // 4 lanes per row (64 contiguous bytes), 8 rows per step: coalesced global traffic
-          const int col = nt * geo.n_tile + cc * EPI_COLS + (lane & 3) * 4;
+          const int col = nt * geo.n_tile + cc * EPI_COLS + sub * 4;
           if (col < d) {
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (MODE == 0 && p.bias) bias4 = ldg4(p.bias + col);
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-              const int r = it * 8 + (lane >> 2);
+              const int r = it * 8 + rsub;
               const int64_t e = row0 + r;
               if (e < p.E) {
-                float4 acc = *reinterpret_cast<const float4*>(stage + r * EPI_ROW_BYTES + (lane & 3) * 16);
+                float4 acc = *reinterpret_cast<const float4*>(stage + r * 64 + ((sub ^ ((r >> 1) & 3)) << 4));
                 if (MODE == 0) {
                   acc = make_float4(acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w);
                   if (p.drop_p > 0.f) {
-                    float4 s = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)col, p.drop_thr, p.inv_keep);
-                    acc = make_float4(acc.x * s.x, acc.y * s.y, acc.z * s.z, acc.w * s.w);
+                    float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)col, p.drop_thr, p.inv_keep);
+                    acc = make_float4(acc.x * sc.x, acc.y * sc.y, acc.z * sc.z, acc.w * sc.w);
                   }
-                  if (p.resid) {
-                    float4 hv = ldg4_stream(p.resid + e * d + col);
-                    acc = make_float4(hv.x + acc.x, hv.y + acc.y, hv.z + acc.z, hv.w + acc.w);
-                  }
+                  if (has_resid) acc = make_float4(cur[it].x + acc.x, cur[it].y + acc.y, cur[it].z + acc.z, cur[it].w + acc.w);
                 }
                 stg4(p.out + e * d + col, acc);
               }
@@ -254,6 +274,17 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
     int s = 0;
     uint32_t ph = 0;
     for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      {  // pull the NEXT tile's operand rows into L2 (one row per producer thread) while this tile is processed
+        const int64_t en = (tile + gridDim.x) * TILE_M + (pt & (TILE_M - 1));
+        if (en < p.E) {
+          if (MODE == 0) {
+            if (pt < TILE_M) l2_prefetch_bulk(p.a0 + (int64_t)__ldg(p.src + en) * d, (uint32_t)d * 4u);
+            else l2_prefetch_bulk(p.a1 + (int64_t)__ldg(p.rev + en) * d, (uint32_t)d * 4u);
+          } else if (pt < TILE_M) {
+            l2_prefetch_bulk(p.a0 + en * d, (uint32_t)d * 4u);
+          }
+        }
+      }
       int64_t rowA[4], rowB[4];
       bool valid[4];
 #pragma unroll
@@ -295,6 +326,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
             if (MODE == 0) {
               float4 a = act_fwd4(vb[i], p.act, p.act_param);
               m = make_float4(va[i].x - a.x, va[i].y - a.y, va[i].z - a.z, va[i].w - a.w);
+              if (p.m_out != nullptr && nt == 0 && valid[i] && kvalid) stg4(p.m_out + (tile * TILE_M + r0 + 32 * i) * d + k0, m);
             } else {
               m = va[i];
               if (p.drop_p > 0.f && valid[i] && kvalid) {
@@ -382,8 +414,10 @@ int tc_weight_prepare(const float* W, int64_t d, int transpose, void* image, cud
 }
 
 int tc_layer_forward(const float* h, const float* n, const int32_t* src, const int32_t* rev, const void* wimg, const float* bias, int64_t E, int64_t d,
-                     int act, float act_param, int residual, float drop_p, uint64_t seed, uint64_t offset, float* out, int products, cudaStream_t st) {
+                     int act, float act_param, int residual, float drop_p, uint64_t seed, uint64_t offset, float* out, float* m_out, int products,
+                     cudaStream_t st) {
   tc::Params p{};
+  p.m_out = m_out;
   p.a0 = n; p.a1 = h; p.src = src; p.rev = rev; p.wimg = static_cast<const uint8_t*>(wimg); p.bias = bias;
   p.resid = residual ? h : nullptr; p.out = out; p.E = E; p.geo = tc::make_geometry((int)d);
   p.act = act; p.act_param = act_param; p.products = products;

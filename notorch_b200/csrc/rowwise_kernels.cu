@@ -18,46 +18,65 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(
 // ------------------------------------------------------------------------------------------------
 // seg_reduce, vectorised: one thread per (segment, float4 chunk)
 // ------------------------------------------------------------------------------------------------
+// Each thread owns SEG_ITEMS (segment, chunk) work items and walks their segments in lock step, two rows per
+// item per trip: the rowptr -> perm -> row dependency chain is three DRAM latencies long and segments are short
+// (in-degree ~2), so the independent chains of several items are what keeps enough bytes in flight.
+constexpr int SEG_ITEMS = 2;
+
 template <bool HAS_PERM>
-__global__ void __launch_bounds__(ROW_THREADS) seg_reduce_v4(const float* __restrict__ x, int d, int chunks, const int32_t* __restrict__ rowptr,
+__global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __restrict__ x, int d, int chunks, const int32_t* __restrict__ rowptr,
                                                               const int32_t* __restrict__ perm, int64_t total, int act, float act_param,
                                                               int mean, float scale, float* __restrict__ out) {
-  int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
-  if (t >= total) return;
-  int s = (int)(t / chunks);
-  int c = (int)(t - (int64_t)s * chunks) * 4;
-  int lo = __ldg(rowptr + s), hi = __ldg(rowptr + s + 1);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int j = lo;
-  // 4 independent row loads in flight, added in ascending order
-  for (; j + 4 <= hi; j += 4) {
-    int r0, r1, r2, r3;
-    if (HAS_PERM) { r0 = __ldg(perm + j); r1 = __ldg(perm + j + 1); r2 = __ldg(perm + j + 2); r3 = __ldg(perm + j + 3); }
-    else { r0 = j; r1 = j + 1; r2 = j + 2; r3 = j + 3; }
-    float4 v0 = ldg4(x + (int64_t)r0 * d + c), v1 = ldg4(x + (int64_t)r1 * d + c);
-    float4 v2 = ldg4(x + (int64_t)r2 * d + c), v3 = ldg4(x + (int64_t)r3 * d + c);
-    if (act != NT_ACT_IDENTITY) { v0 = act_fwd4(v0, act, act_param); v1 = act_fwd4(v1, act, act_param); v2 = act_fwd4(v2, act, act_param); v3 = act_fwd4(v3, act, act_param); }
-    acc = add4(acc, v0); acc = add4(acc, v1); acc = add4(acc, v2); acc = add4(acc, v3);
+  const int64_t t0 = (int64_t)blockIdx.x * (ROW_THREADS * SEG_ITEMS) + threadIdx.x;
+  int s[SEG_ITEMS], c[SEG_ITEMS], lo[SEG_ITEMS], hi[SEG_ITEMS];
+  float4 acc[SEG_ITEMS];
+  int maxlen = 0;
+#pragma unroll
+  for (int k = 0; k < SEG_ITEMS; ++k) {
+    const int64_t t = t0 + (int64_t)k * ROW_THREADS;
+    const bool live = t < total;
+    s[k] = live ? (int)(t / chunks) : 0;
+    c[k] = live ? (int)(t - (int64_t)s[k] * chunks) * 4 : 0;
+    lo[k] = live ? __ldg(rowptr + s[k]) : 0;
+    hi[k] = live ? __ldg(rowptr + s[k] + 1) : 0;
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    maxlen = max(maxlen, hi[k] - lo[k]);
   }
-  if (j + 2 <= hi) {
-    int r0 = HAS_PERM ? __ldg(perm + j) : j, r1 = HAS_PERM ? __ldg(perm + j + 1) : j + 1;
-    float4 v0 = ldg4(x + (int64_t)r0 * d + c), v1 = ldg4(x + (int64_t)r1 * d + c);
-    if (act != NT_ACT_IDENTITY) { v0 = act_fwd4(v0, act, act_param); v1 = act_fwd4(v1, act, act_param); }
-    acc = add4(acc, v0); acc = add4(acc, v1);
-    j += 2;
+  for (int j = 0; j < maxlen; j += 2) {
+    int r[SEG_ITEMS][2];
+    bool ok[SEG_ITEMS][2];
+    float4 v[SEG_ITEMS][2];
+#pragma unroll
+    for (int k = 0; k < SEG_ITEMS; ++k)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int idx = lo[k] + j + u;
+        ok[k][u] = idx < hi[k];
+        r[k][u] = ok[k][u] ? (HAS_PERM ? __ldg(perm + idx) : idx) : 0;
+      }
+#pragma unroll
+    for (int k = 0; k < SEG_ITEMS; ++k)
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (ok[k][u]) v[k][u] = ldg4(x + (int64_t)r[k][u] * d + c[k]);
+#pragma unroll
+    for (int k = 0; k < SEG_ITEMS; ++k)
+#pragma unroll
+      for (int u = 0; u < 2; ++u)  // ascending item order within the segment: bit-identical to a sequential scatter_add_
+        if (ok[k][u]) acc[k] = add4(acc[k], act != NT_ACT_IDENTITY ? act_fwd4(v[k][u], act, act_param) : v[k][u]);
   }
-  if (j < hi) {
-    int r0 = HAS_PERM ? __ldg(perm + j) : j;
-    float4 v0 = ldg4(x + (int64_t)r0 * d + c);
-    if (act != NT_ACT_IDENTITY) v0 = act_fwd4(v0, act, act_param);
-    acc = add4(acc, v0);
+#pragma unroll
+  for (int k = 0; k < SEG_ITEMS; ++k) {
+    const int64_t t = t0 + (int64_t)k * ROW_THREADS;
+    if (t >= total) continue;
+    float4 a = acc[k];
+    if (mean) {
+      const float cnt = (float)max(hi[k] - lo[k], 1);  // torch_scatter.scatter_mean: count.clamp(min=1), true division
+      a = make_float4(a.x / cnt, a.y / cnt, a.z / cnt, a.w / cnt);
+    }
+    if (scale != 1.f) a = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+    stg4(out + (int64_t)s[k] * d + c[k], a);
   }
-  if (mean) {
-    float cnt = (float)max(hi - lo, 1);  // torch_scatter.scatter_mean: count.clamp(min=1), true division
-    acc = make_float4(acc.x / cnt, acc.y / cnt, acc.z / cnt, acc.w / cnt);
-  }
-  if (scale != 1.f) acc = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
-  stg4(out + (int64_t)s * d + c, acc);
 }
 
 // scalar fallback for d % 4 != 0 (or unaligned bases): one thread per (segment, element)
@@ -181,7 +200,7 @@ extern "C" int nt_seg_reduce(const void* x, int64_t d, const int32_t* rowptr, co
   if (vec_ok(d, x, out)) {
     int chunks = (int)(d / 4);
     int64_t total = num_segments * chunks;
-    unsigned grid = (unsigned)cdiv(total, ROW_THREADS);
+    unsigned grid = (unsigned)cdiv(total, ROW_THREADS * SEG_ITEMS);
     if (perm) seg_reduce_v4<true><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, of);
     else seg_reduce_v4<false><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, of);
   } else {

@@ -319,6 +319,26 @@ __global__ void __launch_bounds__(256) colsum_final(const float* __restrict__ pa
 
 }  // namespace wg
 
+// gb[o] = sum_e g_u[e, o] — stand-alone, for hidden sizes where no spare ones row/column exists. Uses `workspace` as scratch
+// AFTER the caller's kernels (same stream), so it may alias the partial buffers that have already been reduced.
+int tc_bias_grad(const float* g, int64_t E, int64_t d, float drop_p, uint64_t seed, uint64_t offset, float* gb, void* workspace, size_t workspace_bytes,
+                 cudaStream_t st) {
+  const int64_t nblk = cdiv(E, wg::CS_ROWS);
+  if ((size_t)nblk * d * sizeof(float) > workspace_bytes) {
+    set_error("tc_bias_grad: workspace too small");
+    return NT_ERR_WORKSPACE;
+  }
+  float* part = static_cast<float*>(workspace);
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  double t = (double)drop_p * 4294967296.0;
+  const uint32_t thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  dim3 grid_cs((unsigned)cdiv(d, 256), (unsigned)nblk);
+  wg::colsum_partial<<<grid_cs, 256, 0, st>>>(g, E, (int)d, drop_p, inv_keep, thr, seed, offset, part);
+  wg::colsum_final<<<(unsigned)cdiv(d, 256), 256, 0, st>>>(part, nblk, (int)d, gb);
+  NT_LAUNCH_CHECK("tc_bias_grad", 2);
+  return NT_OK;
+}
+
 size_t tc_wgrad_workspace_bytes(int64_t E, int64_t d) {
   if (d % 4 != 0 || E <= 0) return 0;
   int sms = num_sms();

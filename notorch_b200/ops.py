@@ -419,19 +419,23 @@ class _Layer(torch.autograd.Function):
         if b is not None:
             b = _require(b, "bias", torch.float32, 1)
         L = _lib.lib()
+        # tensor-core path: K2 also writes the message tensor m, which K4b then streams with TMA
+        save_m = mode != GEMM_FP32 and d % 4 == 0 and (ctx.needs_input_grad[1] or (b is not None and ctx.needs_input_grad[2]))
         with torch.cuda.device(h.device):
             n = _seg_reduce_raw(h, csr.by_dst, act, act_param, mean, tag="K1")
             img = _weight_image(W, False) if mode != GEMM_FP32 else None
             out = torch.empty_like(h)
+            m = torch.empty_like(h) if save_m else None
             _run("K2:nt_layer_forward", L.nt_layer_forward, _p(h), _p(n), _p(csr.src), _p(csr.rev), _p(W), _p(img), _p(b), E, csr.V, d, act,
-                 act_param, int(residual), p, seed, offset, _p(out), NT_F32, mode, _stream())
-        ctx.save_for_backward(h, n, W)
-        ctx.csr, ctx.cfg, ctx.has_bias = csr, (act, act_param, mean, residual, p, seed, offset, mode), b is not None
+                 act_param, int(residual), p, seed, offset, _p(out), _p(m), NT_F32, mode, _stream())
+        ctx.save_for_backward(h, m if save_m else n, W)
+        ctx.csr, ctx.cfg, ctx.has_bias, ctx.has_m = csr, (act, act_param, mean, residual, p, seed, offset, mode), b is not None, save_m
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
-        h, n, W = ctx.saved_tensors
+        h, n_or_m, W = ctx.saved_tensors
+        m, n = (n_or_m, None) if ctx.has_m else (None, n_or_m)
         csr = ctx.csr
         act, act_param, mean, residual, p, seed, offset, mode = ctx.cfg
         E, d = h.shape
@@ -444,8 +448,8 @@ class _Layer(torch.autograd.Function):
                 gb = torch.empty(d, dtype=W.dtype, device=W.device) if ctx.has_bias else None
                 nbytes = L.nt_layer_backward_wgrad_workspace_bytes(E, d)
                 ws = _workspace(g.device, nbytes, slot=1)
-                _run("K4b:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(g), _p(h), _p(n), _p(csr.src), _p(csr.rev), E, csr.V, d, act,
-                     act_param, p, seed, offset, _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream())
+                _run("K4b:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(g), _p(m), _p(h), _p(n), _p(csr.src), _p(csr.rev), E, csr.V, d,
+                     act, act_param, p, seed, offset, _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream())
             if ctx.needs_input_grad[0]:
                 img_t = _weight_image(W, True) if mode != GEMM_FP32 else None
                 g_m = torch.empty_like(h)

@@ -43,7 +43,7 @@ def test_argument_errors_are_status_codes_not_crashes():
     assert rc == 1 and b"dtype" in lib.nt_last_error_string()
     rc = lib.nt_seg_reduce(None, 300, None, None, 10, 1, 0.0, 0, 1.0, None, _lib.NT_BF16, None)
     assert rc == 3
-    rc = lib.nt_layer_forward(None, None, None, None, None, None, None, 5, 5, 300, 1, 0.0, 1, 1.5, 0, 0, None, 0, 0, None)
+    rc = lib.nt_layer_forward(None, None, None, None, None, None, None, 5, 5, 300, 1, 0.0, 1, 1.5, 0, 0, None, None, 0, 0, None)
     assert rc == 1 and b"dropout_p" in lib.nt_last_error_string()
     rc = lib.nt_build_csr(None, -1, 4, None, None, None, None, None, 0, None)
     assert rc == 1

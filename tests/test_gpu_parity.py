@@ -394,3 +394,29 @@ def test_full_size_properties_config2():
     total_H, total_nodes = Hs[0][0].double().sum(0), Hs[0][1].double().sum(0)
     assert float((total_H - total_nodes).abs().max()) <= 1e-6 * float(total_nodes.abs().max())
     assert torch.isfinite(Hs[0][0]).all()
+
+
+@pytest.mark.parametrize("E,d", [(300, 64), (2000, 300), (500, 256)])
+def test_wgrad_gather_kernel_without_saved_messages(E, d):
+    """K4b has two tensor-core kernels: TMA-streamed (m saved by K2; what autograd uses) and gather-based (m == NULL,
+    recomputed from n / h / src / rev). This drives the second one through the C ABI directly."""
+    from notorch_b200 import _lib, ops
+
+    gen = torch.Generator().manual_seed(E + d)
+    V = max(1, E // 2)
+    src, dst, rev = torch.randint(0, V, (E,), generator=gen), torch.randint(0, V, (E,), generator=gen), torch.randint(0, E, (E,), generator=gen)
+    h, g = torch.randn(E, d, generator=gen), torch.randn(E, d, generator=gen)
+    a = torch.relu(h.double())
+    n64 = torch.zeros(V, d, dtype=torch.float64).index_add_(0, dst, a)
+    m64 = n64[src] - a[rev]
+    csr = ops.build_graph_csr(torch.stack([src, dst]).cuda(), rev.cuda(), V)
+    hc, gc = h.cuda(), g.cuda()
+    n = ops._seg_reduce_raw(hc, csr.by_dst, _lib.ACT_RELU, 0.0, False)
+    L = _lib.lib()
+    gW, gb = torch.empty(d, d, device="cuda"), torch.empty(d, device="cuda")
+    ws = torch.empty(L.nt_layer_backward_wgrad_workspace_bytes(E, d), dtype=torch.uint8, device="cuda")
+    p = lambda t: t.data_ptr()
+    _lib.check(L.nt_layer_backward_wgrad(p(gc), None, p(hc), p(n), p(csr.src), p(csr.rev), E, V, d, _lib.ACT_RELU, 0.0, 0.0, 0, 0, p(gW), p(gb),
+                                         p(ws), ws.numel(), _lib.NT_F32, _lib.GEMM_TF32X3, torch.cuda.current_stream().cuda_stream), "wgrad")
+    assert_close(gW, g.double().t() @ m64, "gW (gather kernel)")
+    assert_close(gb, g.double().sum(0), "gb (gather kernel)")
