@@ -420,3 +420,37 @@ def test_wgrad_gather_kernel_without_saved_messages(E, d):
                                          p(ws), ws.numel(), _lib.NT_F32, _lib.GEMM_TF32X3, torch.cuda.current_stream().cuda_stream), "wgrad")
     assert_close(gW, g.double().t() @ m64, "gW (gather kernel)")
     assert_close(gb, g.double().sum(0), "gb (gather kernel)")
+
+
+def test_foreign_graph_object_duck_typing():
+    """the modules only need node_feats / edge_feats / edge_index / rev_index /
+    batch_node_index / update() / len() — i.e. the reference's own BatchedGraph works unchanged."""
+    import copy
+
+    from notorch_b200.nn import ChempropBlock, Sum
+
+    class ForeignGraph:  # mimics notorch.data.models.graph.BatchedGraph's surface (graph.py:167-227, utils.py:34-40)
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+        def update(self, in_place=False, **kw):
+            other = self if in_place else copy.copy(self)
+            for k, v in kw.items():
+                setattr(other, k, v)
+            return other
+
+        def __len__(self):
+            return self._size
+
+    p = oracle_inputs(8, 32, 2, seed=12)
+    G = ForeignGraph(node_feats=p["x_v"].cuda(), edge_feats=p["x_e"].cuda(), edge_index=p["edge_index"].cuda(), rev_index=p["rev_index"].cuda(),
+                     batch_node_index=p["batch_node_index"].cuda(), batch_edge_index=p["batch_edge_index"].cuda(), _size=8)
+    blk = ChempropBlock(hidden_dim=32, depth=2).cuda()
+    G1 = blk(G)
+    H = Sum()(G1)
+    Ws = [l.module.update[0].weight.detach().cpu() for l in blk.layers]
+    bs = [l.module.update[0].bias.detach().cpu() for l in blk.layers]
+    node, edge, _ = O.block_forward(p["x_v"], p["x_e"], p["edge_index"], p["rev_index"], Ws, bs)
+    assert isinstance(G1, ForeignGraph) and G1.edge_index is G.edge_index
+    assert_close(G1.edge_feats, edge, "edge_out (foreign graph)")
+    assert_close(H, O.readout(node, p["batch_node_index"], 8, "sum"), "H (foreign graph)")
