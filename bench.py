@@ -194,7 +194,7 @@ def run_reference_arm(args, wl, batch):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -267,7 +267,7 @@ def run_ours(args, wl, batch):
         for _ in range(nsteps):
             loss = step(src, from_host)
             if from_host:
-                last = float(loss)  # D2H read of the step's result inside the timed region
+                last = float(loss.detach())  # D2H read of the step's result inside the timed region
         ev1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -302,6 +302,11 @@ def run_ours(args, wl, batch):
 
     # ---- per-kernel CUDA-event timing (a separate instrumented pass over the same steps) ----
     roof = kernels = None
+    nprof = min(args.steps, 10)
+    with ops.KernelTimer() as kt:  # every rank runs it (the step contains the collective); rank 0 reports
+        for _ in range(nprof):
+            step(resident, False)
+    summ = kt.summary()
     if rank == 0:
         peaks = {}
         try:
@@ -310,11 +315,6 @@ def run_ours(args, wl, batch):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        nprof = min(args.steps, 10)
-        with ops.KernelTimer() as kt:
-            for _ in range(nprof):
-                step(resident, False)
-        summ = kt.summary()
         alg = algorithmic_bytes(V, E, batch, d, L)
         kernels = []
         for tag, rec in sorted(summ.items(), key=lambda kv: -kv[1]["total_ms"]):
@@ -353,13 +353,25 @@ def run_ours(args, wl, batch):
                        "l2": "working set per step (>1.5 GB) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) went to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # libraries that print to fd 1 (e.g. the NCCL version banner) must not pollute the JSON line
     args = parse_args()
     wl = WORKLOADS[args.workload]
     batch = args.batch or wl["batch"]
