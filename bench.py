@@ -6,8 +6,8 @@
 
 metric   : molecules/sec, forward + backward, D-MPNN depth 3 hidden 300 (configs[1]: batch 4096
            ZINC-size synthetic graphs per GPU, fp32, Sum read-out)
-a step   : collation + CSR build of one batch -> ChempropBlock -> Sum -> loss = H.square().mean()
-           -> backward -> (N > 1: NCCL all-reduce of the flat gradient) -> fused Adam step
+a step   : collation + CSR build of one batch -> GraphEmbedding (type ids -> [V,d],[E,d]) -> ChempropBlock -> Sum
+           -> loss = H.square().mean() -> backward -> (N > 1: NCCL all-reduce of the flat gradient) -> fused Adam step
 value    : whole-job molecules/s with the batch already resident in HBM (CUDA events, max over ranks)
 e2e      : same step through the public API starting from pinned HOST buffers (H2D of the step's inputs
            and a D2H read of the loss inside the timed region)
@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "molecules/sec fwd+bwd, D-MPNN d=3 h=300"
+NUM_ATOM_TYPES, NUM_BOND_TYPES = 45, 13
 UNIT = "molecules/s"
 
 WORKLOADS = {
@@ -69,10 +70,12 @@ def make_workload(wl: dict, rank: int, batch: int):
     seed = config_seed(wl["config"], rank)
     mols = make_molecules(batch, wl["config"], seed=seed)
     gen = torch.Generator().manual_seed(seed)
-    V, E, d = mols.total_atoms, mols.total_edges, wl["d"]
-    x_v = torch.randn(V, d, generator=gen)
-    x_e = torch.randn(E, d, generator=gen)
-    return mols, x_v, x_e
+    V, E = mols.total_atoms, mols.total_edges
+    # integer type features, the reference's on-the-wire input (transforms/atom.py, transforms/bond.py): 7 ids per atom
+    # into a 45-entry table, 2 ids per bond into a 13-entry table
+    node_types = torch.randint(0, NUM_ATOM_TYPES, (V, 7), generator=gen)
+    edge_types = torch.randint(0, NUM_BOND_TYPES, (E, 2), generator=gen)
+    return mols, node_types, edge_types
 
 
 def algorithmic_bytes(V: int, E: int, B: int, d: int, L: int, s: int = 4) -> dict[str, float]:
@@ -88,6 +91,8 @@ def algorithmic_bytes(V: int, E: int, B: int, d: int, L: int, s: int = 4) -> dic
         "K6": (V + 4 * E) * d * s + 12 * E,
         "K1bwd": (V + 2 * E) * d * s + 4 * E,  # g_hL = gE + g_node[dst]
         "K3bwd": (V + B) * d * s + 4 * V,
+        "emb": 0.5 * ((V * 7 + E * 2) * 8 + (V + E) * d * s),  # two launches (atoms, bonds): average per launch
+        "embbwd": 0.5 * ((V * 7 + E * 2) * 8 + (V + E) * d * s),
         "step": d * s * (6 * E + 5 * V + B + L * (12 * E + 5 * V)),
     }
 
@@ -144,16 +149,16 @@ def cpu_reference_run(wl: dict, batch: int, steps: int, warmup: int, budget_s: f
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    mols, x_v, x_e = make_workload(wl, 0, batch)
+    mols, node_types, edge_types = make_workload(wl, 0, batch)
     # bounded sample: shrink the per-step batch until (warmup + steps) fits the budget
     sample = batch
-    model = O.CpuPort(hidden_dim=wl["d"], depth=wl["depth"], agg=wl["agg"])
+    model = O.CpuPort(hidden_dim=wl["d"], depth=wl["depth"], agg=wl["agg"], embed=(NUM_ATOM_TYPES, NUM_BOND_TYPES))
 
     def prep(nmol):
         sub = mols.shard(0, batch // nmol) if nmol < batch else mols
         c = O.collate(sub.split())
         V, E = sub.total_atoms, sub.total_edges
-        return (x_v[:V].clone().requires_grad_(True), x_e[:E].clone().requires_grad_(True), torch.from_numpy(c["edge_index"]),
+        return (node_types[:V], edge_types[:E], torch.from_numpy(c["edge_index"]),
                 torch.from_numpy(c["rev_index"]), torch.from_numpy(c["batch_node_index"]), len(sub))
 
     args = prep(sample)
@@ -175,8 +180,8 @@ def cpu_reference_run(wl: dict, batch: int, steps: int, warmup: int, budget_s: f
         times.append(time.perf_counter() - t0)
     total = sum(times)
     return {"value": sample * steps / total, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{steps} timed steps (after {warmup} warm-up) of zero_grad+forward+backward on {sample} of the {batch} molecules of the "
-                      f"workload batch, torch CPU fp32, {threads} threads",
+            "sample": f"{steps} timed steps (after {warmup} warm-up) of zero_grad+forward+backward (2 EmbeddingBag + block + readout) on {sample} "
+                      f"of the {batch} molecules of the workload batch, torch CPU fp32, {threads} threads",
             "ms_per_step": 1e3 * total / steps, "sample_molecules": sample}
 
 
@@ -205,7 +210,7 @@ def run_ours(args, wl, batch):
     import torch.distributed as dist
 
     from notorch_b200 import BatchedGraph, _lib, ops
-    from notorch_b200.nn import ChempropBlock, Mean, Sum
+    from notorch_b200.nn import ChempropBlock, GraphEmbedding, Mean, Sum
     from notorch_b200.parallel import FlatGradients
 
     rank = int(os.environ.get("RANK", "0"))
@@ -221,17 +226,18 @@ def run_ours(args, wl, batch):
         ops.set_gemm_mode(args.gemm)
     ops.set_index_validation("deferred")  # no per-batch device sync; an out-of-range index still raises (one batch late)
 
-    mols, x_v, x_e = make_workload(wl, rank, batch)
+    mols, node_types, edge_types = make_workload(wl, rank, batch)
     V, E, d, L = mols.total_atoms, mols.total_edges, wl["d"], wl["depth"]
     torch.manual_seed(0)
+    embed = GraphEmbedding(NUM_ATOM_TYPES, NUM_BOND_TYPES, hidden_dim=d).to(dev)
     block = ChempropBlock(hidden_dim=d, depth=L).to(dev)
     agg = (Sum if wl["agg"] == "sum" else Mean)()
-    params = list(block.parameters())
+    params = list(embed.parameters()) + list(block.parameters())
     flat = FlatGradients(params)
     opt = torch.optim.Adam(params, lr=1e-4, fused=True)
 
     # pinned host copies (e2e leg) and device-resident copies (value leg)
-    host = {"x_v": x_v.pin_memory(), "x_e": x_e.pin_memory(),
+    host = {"node_types": node_types.pin_memory(), "edge_types": edge_types.pin_memory(),
             "num_atoms": torch.from_numpy(mols.num_atoms).pin_memory(), "num_edges": torch.from_numpy(mols.num_edges).pin_memory(),
             "edge_index": torch.from_numpy(mols.edge_index).pin_memory(), "rev_index": torch.from_numpy(mols.rev_index).pin_memory()}
     resident = {k: v.to(dev) for k, v in host.items()}
@@ -246,9 +252,8 @@ def run_ours(args, wl, batch):
             t = {k: v.to(dev, non_blocking=True) for k, v in src.items()}
         else:
             t = src
-        xv, xe = t["x_v"].detach().requires_grad_(True), t["x_e"].detach().requires_grad_(True)
-        G = BatchedGraph.from_packed(Packed(t), xv, xe, device=dev)  # collation kernel (K-l)
-        H = agg(block(G))  # CSR build + K0 + L x (K1, K2) + K1 + K3
+        G = BatchedGraph.from_packed(Packed(t), t["node_types"], t["edge_types"], device=dev)  # collation kernel (K-l)
+        H = agg(block(embed(G)))  # embedding + CSR build + K0 + L x (K1, K2) + K1 + K3
         loss = H.square().mean()
         flat.zero()
         loss.backward()  # K3bwd, K1bwd, L x (K4b, K4a, K5, K6), K5
@@ -298,7 +303,7 @@ def run_ours(args, wl, batch):
         e2e_ms, _ = timed(args.steps, host, True)
         e2e = {"value": world * batch * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": e2e_ms / args.steps,
-               "inputs": "float node/edge features [V,d],[E,d] fp32 + packed int32 topology, from pinned host memory"}
+               "inputs": "int64 atom/bond type ids [V,7],[E,2] + packed int32 topology (counts, local edge_index, local rev_index), pinned host memory"}
 
     # ---- per-kernel CUDA-event timing (a separate instrumented pass over the same steps) ----
     roof = kernels = None
@@ -349,7 +354,7 @@ def run_ours(args, wl, batch):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "hidden": d, "depth": L, "readout": wl["agg"], "batch_per_gpu": batch, "atoms_per_gpu": V,
                        "edges_per_gpu": E, "gemm": ops.get_gemm_mode(), "parallelism": f"dp{world}",
-                       "step": "collate+CSR, forward, loss, backward, grad all-reduce (N>1), fused Adam",
+                       "step": "collate+CSR, GraphEmbedding, ChempropBlock, readout, loss, backward, grad all-reduce (N>1), fused Adam",
                        "l2": "working set per step (>1.5 GB) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
         }

@@ -181,6 +181,18 @@ int nt_layer_backward_epilogue(const void* g, const void* h, const void* g_n, co
                                int act, float act_param, int residual, int mean,
                                void* g_h, int dtype, nt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GraphEmbedding (row N1, the step before the block) — replaces the two nn.EmbeddingBag(mode="sum") of
+ * notorch/nn/gnn/embed.py:20-24 on 2-D index input: out[i,:] = sum_{j<bag} table[idx[i,j],:]  (idx int64 [n,bag]).
+ * *status bit 0 is set if an index is outside [0, num_types). Backward: g_table[t,:] = sum over all (i,j) with
+ * idx[i,j] == t of g[i,:], deterministic (per-CTA partial tables + fixed-order sum, no atomics).
+ * ---------------------------------------------------------------------------------------------- */
+int nt_embedding_bag_sum(const void* table, int64_t num_types, const int64_t* idx, int64_t n, int64_t bag, int64_t d,
+                         void* out, int32_t* status, int dtype, nt_stream_t stream);
+size_t nt_embedding_bag_backward_workspace_bytes(int64_t n, int64_t num_types, int64_t d);
+int nt_embedding_bag_backward(const void* g, const int64_t* idx, int64_t n, int64_t bag, int64_t num_types, int64_t d,
+                              void* g_table, void* workspace, size_t workspace_bytes, int dtype, nt_stream_t stream);
+
 /* Dropout keep-mask exactly as K2/K4 compute it (1.0f keep / 0.0f drop), for tests. */
 int nt_dropout_mask(int64_t n_rows, int64_t d, float dropout_p, uint64_t seed, uint64_t offset,
                     float* mask, nt_stream_t stream);

@@ -1,0 +1,77 @@
+"""``GraphEmbedding`` — drop-in for ``notorch/nn/gnn/embed.py:11-36`` (row N1 of SURVEY.md §8f, the step
+immediately before the message-passing block): two ``nn.EmbeddingBag(mode="sum")`` tables
+(``node.weight`` / ``edge.weight``, same state-dict keys) looked up with the graph's integer type
+features ``[V, t_v]`` / ``[E, t_e]``; computed by ``nt_embedding_bag_sum`` with a deterministic
+hand-written backward. With it the on-the-wire input of a training step is the integer type ids, not
+``[V, d]`` / ``[E, d]`` floats.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from ... import _lib, ops
+from ...data.models.graph import Graph
+
+# notorch/transforms/conf.py:35-44 (needs RDKit to import, so restated): 45 atom types, 13 bond types
+DEFAULT_NUM_ATOM_TYPES = 45
+DEFAULT_NUM_BOND_TYPES = 13
+DEFAULT_HIDDEN_DIM = 256  # notorch/conf.py:11
+
+
+class _EmbeddingBagSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table: Tensor, idx: Tensor):
+        table = ops._require_float(table, "embedding table")
+        idx = ops._require(idx, "type indices", torch.int64, 2)
+        n, bag = idx.shape
+        T, d = table.shape
+        L = _lib.lib()
+        with torch.cuda.device(table.device):
+            out = torch.empty((n, d), dtype=table.dtype, device=table.device)
+            status = torch.zeros(1, dtype=torch.int32, device=table.device)
+            ops._run("emb:nt_embedding_bag_sum", L.nt_embedding_bag_sum, ops._p(table), T, ops._p(idx), n, bag, d, ops._p(out), ops._p(status),
+                     _lib.NT_F32, ops._stream())
+        ops._check_status(status, "GraphEmbedding type indices")
+        ctx.save_for_backward(idx)
+        ctx.shape = (T, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (idx,) = ctx.saved_tensors
+        T, d = ctx.shape
+        n, bag = idx.shape
+        g = g.contiguous()
+        L = _lib.lib()
+        with torch.cuda.device(g.device):
+            gt = torch.empty((T, d), dtype=g.dtype, device=g.device)
+            ws = ops._workspace(g.device, L.nt_embedding_bag_backward_workspace_bytes(n, T, d), slot=2)
+            ops._run("embbwd:nt_embedding_bag_backward", L.nt_embedding_bag_backward, ops._p(g), ops._p(idx), n, bag, T, d, ops._p(gt), ops._p(ws),
+                     ws.numel(), _lib.NT_F32, ops._stream())
+        return gt, None
+
+
+class GraphEmbedding(nn.Module):
+    def __init__(self, num_node_types: int = DEFAULT_NUM_ATOM_TYPES, num_edge_types: int = DEFAULT_NUM_BOND_TYPES,
+                 hidden_dim: int = DEFAULT_HIDDEN_DIM):
+        super().__init__()
+        self.node = nn.EmbeddingBag(num_node_types, hidden_dim, mode="sum")
+        self.edge = nn.EmbeddingBag(num_edge_types, hidden_dim, mode="sum")
+
+    def forward(self, G: Graph) -> Graph:
+        return G.update(node_feats=_EmbeddingBagSum.apply(self.node.weight, G.node_feats),
+                        edge_feats=_EmbeddingBagSum.apply(self.edge.weight, G.edge_feats))
+
+    @property
+    def num_node_types(self) -> int:
+        return self.node.num_embeddings
+
+    @property
+    def num_edge_types(self) -> int:
+        return self.edge.num_embeddings
+
+    @classmethod
+    def from_transform(cls, transform, **kwargs) -> "GraphEmbedding":
+        return cls(transform.num_node_types, transform.num_edge_types, **kwargs)

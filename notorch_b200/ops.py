@@ -177,26 +177,48 @@ class SegmentCSR:
     status: Tensor | None = None  # [1] int32 device flag, bit 0 = key out of range
 
 
-_pending_checks: list[tuple[Tensor, torch.cuda.Event, str]] = []
+_STATUS_SLOTS = 256
+_status_ring: Tensor | None = None  # pinned int32 ring: no per-batch pinned allocation (cudaHostAlloc synchronises)
+_status_events: list = [None] * _STATUS_SLOTS
+_status_what: list = [""] * _STATUS_SLOTS
+_status_head = 0  # next slot to write
+_status_tail = 0  # oldest slot not yet examined
+
+
+def _drain_status(block_slot: int | None = None) -> None:
+    global _status_tail
+    while _status_tail < _status_head:
+        slot = _status_tail % _STATUS_SLOTS
+        ev = _status_events[slot]
+        if block_slot is not None and slot == block_slot:
+            ev.synchronize()
+        elif not ev.query():
+            return
+        _status_tail += 1
+        if int(_status_ring[slot]) != 0:
+            raise IndexError(f"notorch_b200: {_status_what[slot]}: index out of range (detected on a later batch)")
 
 
 def _check_status(status: Tensor, what: str) -> None:
+    global _status_ring, _status_head
     if _validate_mode == "off":
         return
     if _validate_mode == "sync":
         if int(status.item()) != 0:
             raise IndexError(f"notorch_b200: {what}: index out of range")
         return
-    # deferred: look at the verdicts of earlier batches that have completed by now
-    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
-    host.copy_(status, non_blocking=True)
+    # deferred: copy the verdict into a pinned ring slot and look at the verdicts that have landed by now
+    if _status_ring is None:
+        _status_ring = torch.zeros(_STATUS_SLOTS, dtype=torch.int32).pin_memory()
+    slot = _status_head % _STATUS_SLOTS
+    if _status_head - _status_tail >= _STATUS_SLOTS:
+        _drain_status(block_slot=slot)  # ring full: wait for the oldest verdict
+    _status_ring[slot:slot + 1].copy_(status, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
-    _pending_checks.append((host, ev, what))
-    while _pending_checks and _pending_checks[0][1].query():
-        h, _, w = _pending_checks.pop(0)
-        if int(h[0]) != 0:
-            raise IndexError(f"notorch_b200: {w}: index out of range (detected on a later batch)")
+    _status_events[slot], _status_what[slot] = ev, what
+    _status_head += 1
+    _drain_status()
 
 
 def build_segment_csr(keys: Tensor, num_segments: int, what: str = "index", status: Tensor | None = None,

@@ -291,8 +291,11 @@ class CpuPort(torch.nn.Module):
     reference's parameter names (``layers.{i}.module.update.0.{weight,bias}``), CPU only."""
 
     def __init__(self, hidden_dim: int = 300, depth: int = 3, bias: bool = True, residual: bool = True,
-                 reduce: str = "sum", agg: str = "sum", act: str = "relu"):
+                 reduce: str = "sum", agg: str = "sum", act: str = "relu", embed: tuple[int, int] | None = None):
         super().__init__()
+        # optional GraphEmbedding in front (notorch/nn/gnn/embed.py:20-24): then x_v / x_e are int64 type ids
+        self.node = torch.nn.EmbeddingBag(embed[0], hidden_dim, mode="sum") if embed else None
+        self.edge = torch.nn.EmbeddingBag(embed[1], hidden_dim, mode="sum") if embed else None
         self.hidden_dim, self.depth, self.residual, self.reduce, self.agg, self.act = (
             hidden_dim, depth, residual, reduce, agg, act)
         self.linears = torch.nn.ModuleList(torch.nn.Linear(hidden_dim, hidden_dim, bias) for _ in range(depth))
@@ -307,6 +310,8 @@ class CpuPort(torch.nn.Module):
         return out
 
     def forward(self, x_v, x_e, edge_index, rev_index, batch_node_index, size):
+        if self.node is not None:
+            x_v, x_e = self.node(x_v), self.edge(x_e)  # embed.py:24
         node_out, edge_out, _ = block_forward(
             x_v, x_e, edge_index, rev_index,
             [l.weight for l in self.linears], [l.bias for l in self.linears],

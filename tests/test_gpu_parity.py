@@ -454,3 +454,37 @@ def test_foreign_graph_object_duck_typing():
     assert isinstance(G1, ForeignGraph) and G1.edge_index is G.edge_index
     assert_close(G1.edge_feats, edge, "edge_out (foreign graph)")
     assert_close(H, O.readout(node, p["batch_node_index"], 8, "sum"), "H (foreign graph)")
+
+
+@pytest.mark.parametrize("d", [300, 37, 64])
+def test_graph_embedding_matches_torch_embedding_bag(d):
+    """Row N1: GraphEmbedding (embed.py:20-24 = two nn.EmbeddingBag(mode='sum')) forward and table gradients."""
+    from notorch_b200 import BatchedGraph
+    from notorch_b200.nn import GraphEmbedding
+
+    p = oracle_inputs(64, 8, 0, seed=21)
+    gen = torch.Generator().manual_seed(3)
+    V, E = p["V"], p["E"]
+    nv = torch.randint(0, 45, (V, 7), generator=gen)
+    ne = torch.randint(0, 13, (E, 2), generator=gen)
+    gv, ge = torch.randn(V, d, generator=gen), torch.randn(E, d, generator=gen)
+    torch.manual_seed(0)
+    emb = GraphEmbedding(hidden_dim=d)
+    ref_v = torch.nn.functional.embedding_bag(nv, emb.node.weight.detach().double().requires_grad_(True), mode="sum")
+    wv64 = emb.node.weight.detach().double().requires_grad_(True)
+    we64 = emb.edge.weight.detach().double().requires_grad_(True)
+    ref_v = torch.nn.functional.embedding_bag(nv, wv64, mode="sum")
+    ref_e = torch.nn.functional.embedding_bag(ne, we64, mode="sum")
+    ((ref_v * gv.double()).sum() + (ref_e * ge.double()).sum()).backward()
+    emb = emb.cuda()
+    G = BatchedGraph(nv.cuda(), ne.cuda(), p["edge_index"].cuda(), p["rev_index"].cuda(), batch_node_index=p["batch_node_index"].cuda(),
+                     batch_edge_index=p["batch_edge_index"].cuda(), size=64)
+    G1 = emb(G)
+    ((G1.node_feats * gv.cuda()).sum() + (G1.edge_feats * ge.cuda()).sum()).backward()
+    assert_close(G1.node_feats, ref_v.detach(), "node embedding", 1e-6)
+    assert_close(G1.edge_feats, ref_e.detach(), "edge embedding", 1e-6)
+    assert_close(emb.node.weight.grad, wv64.grad, "grad node table")
+    assert_close(emb.edge.weight.grad, we64.grad, "grad edge table")
+    assert list(emb.state_dict()) == ["node.weight", "edge.weight"]
+    with pytest.raises(IndexError):
+        emb(G.update(node_feats=nv.cuda() + 45))
