@@ -65,6 +65,9 @@ const char* nt_last_error_string(void);
 int nt_version(void);
 /* Number of kernels this library has launched in this process so far (all threads). */
 long long nt_kernel_launch_count(void);
+/* Debug only: device buffer of >= 65001 uint64 (word 0 = counter, zeroed by the caller) into which CTA 0 of the fused
+ * tensor-core kernel appends role/time records; NULL switches tracing off. Not part of the data path. */
+void nt_debug_set_trace_buffer(void* device_u64_buffer);
 /* 1 if the current device is compute capability 10.x (tcgen05 available), else 0; <0 on error. */
 int nt_device_supported(void);
 

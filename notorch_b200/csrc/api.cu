@@ -46,6 +46,7 @@ int simt_layer_dgrad(const float*, const float*, int64_t, int64_t, float, uint64
 int simt_layer_wgrad(const float*, const float*, const float*, const int32_t*, const int32_t*, int64_t, int64_t, int, float, float, uint64_t, uint64_t,
                      float*, float*, float*, cudaStream_t);
 // gemm_tc.cu
+void tc_set_trace_buffer(void* ptr);
 size_t tc_weight_image_bytes(int64_t d);
 int tc_weight_prepare(const float*, int64_t, int, void*, cudaStream_t);
 int tc_layer_forward(const float*, const float*, const int32_t*, const int32_t*, const void*, const float*, int64_t, int64_t, int, float, int, float,
@@ -71,6 +72,8 @@ using namespace nt;
 extern "C" const char* nt_last_error_string(void) { return g_err; }
 extern "C" int nt_version(void) { return 100; }
 extern "C" long long nt_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" void nt_debug_set_trace_buffer(void* device_u64_buffer) { tc_set_trace_buffer(device_u64_buffer); }
 
 extern "C" int nt_device_supported(void) {
   int dev = 0;

@@ -17,6 +17,8 @@
 // The A operand cannot come from TMA (it is a gather-and-subtract), which is why only W is staged
 // by the copy engine; W is pre-split and pre-swizzled once per step by nt_weight_prepare so that
 // each (N-tile, K-block) is one contiguous bulk copy.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -81,7 +83,19 @@ struct Params {
   uint32_t drop_thr;
   uint64_t seed, offset;
   int products;  // 3 = 3xTF32, 1 = single-pass TF32
+  unsigned long long* trace;  // timing experiments only: CTA 0 appends (event << 56 | tile << 40 | clock) records
+  int ablate;    // timing experiments only (NOTORCH_B200_ABLATE): 1 no epilogue stores, 2 no producer loads, 4 W only once, 8 no MMAs
 };
+
+// Debug trace: each tracing thread owns a region of the buffer and a private cursor (plain stores, no atomics, so the
+// probe costs a few cycles). Regions: 0 = epilogue thread 0, 1 = MMA issuer, 2 = producer thread 0; 16384 records each.
+__device__ __forceinline__ void trace_event(const Params& p, int region, uint32_t& cursor, int ev, int64_t tile, int aux = 0) {
+  if (p.trace != nullptr && blockIdx.x == 0 && cursor < 16384u) {
+    p.trace[1 + region * 16384 + cursor] = ((unsigned long long)ev << 56) | ((unsigned long long)(tile & 0xFFFF) << 40) |
+                                             ((unsigned long long)(aux & 0xFF) << 32) | (unsigned long long)(clock64() & 0xFFFFFFFFull);
+    ++cursor;
+  }
+}
 
 template <int MODE>  // 0 = K2 forward, 1 = K4a dgrad
 __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
@@ -106,12 +120,12 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_a_full + 8 * s, NUM_A_THREADS);
+      mbar_init(bar_a_full + 8 * s, NUM_A_WARPS);  // one elected arrive per producer warp
       mbar_init(bar_w_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tmem_full, 1);
-    mbar_init(bar_tmem_empty, NUM_EPI_WARPS * 32);
+    mbar_init(bar_tmem_empty, NUM_EPI_WARPS);  // one elected arrive per epilogue warp
     fence_barrier_init();
   }
   if (warp == MMA_WARP) {
@@ -122,6 +136,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  uint32_t tcur = 0;  // debug-trace cursor of this thread
 
   if (warp < NUM_EPI_WARPS) {
     // ===================================== EPILOGUE =====================================
@@ -133,6 +148,8 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
     const int chunks = geo.n_tile / EPI_COLS;
     const int sub = lane & 3, rsub = lane >> 2;
     const bool has_resid = MODE == 0 && p.resid != nullptr;
+    const int shared_chunks = 2 * geo.n_tile > 512 ? (2 * geo.n_tile - 512) / EPI_COLS : 0;
+    int tw = 0;
     for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
       const int64_t row0 = tile * TILE_M + warp * 32;
       if (has_resid && row0 + lane < p.E) l2_prefetch_bulk(p.resid + (row0 + lane) * d, (uint32_t)d * 4u);
@@ -146,23 +163,35 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
             if (has_resid && cc < chunks && col < d && e < p.E) dst[it] = ldg4_stream(p.resid + e * d + col);
           }
         };
+        // TMEM windows: successive (tile, N tile) passes alternate between columns [0, n_tile) and [512 - n_tile, 512).
+        // They overlap in `shared_chunks` 16-column chunks (6 at n_tile = 304, none for n_tile <= 256); this pass drains
+        // the overlap FIRST and then hands TMEM back, so the next pass's MMAs run under the rest of this epilogue.
+        const int col_base = tw ? 512 - geo.n_tile : 0;
+        const int first = (tw == 0 && shared_chunks > 0) ? chunks - shared_chunks : 0;  // rotation of the chunk order
+        auto chunk_at = [&](int k) { int c = k + first; return c >= chunks ? c - chunks : c; };
         float4 r0[4], r1[4], r2[4];
-        load_resid(0, r0);
-        load_resid(1, r1);
-        load_resid(2, r2);
+        load_resid(chunk_at(0), r0);
+        load_resid(chunks > 1 ? chunk_at(1) : chunks, r1);
+        load_resid(chunks > 2 ? chunk_at(2) : chunks, r2);
+        if (threadIdx.x == 0) trace_event(p, 0, tcur, 1, tile);  // epilogue: waiting for the accumulator
         mbar_wait(bar_tmem_full, tphase);
         tc_fence_after();
-        for (int cc = 0; cc < chunks; ++cc) {
+        if (threadIdx.x == 0) trace_event(p, 0, tcur, 2, tile);  // epilogue: accumulator ready
+        if (shared_chunks == 0 && lane == 0) mbar_arrive(bar_tmem_empty);  // the other window is free as soon as this pass has begun
+        for (int k = 0; k < chunks; ++k) {
+          const int cc = chunk_at(k);
           uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * EPI_COLS), v);
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(col_base + cc * EPI_COLS), v);
           float4 cur[4];
 #pragma unroll
           for (int it = 0; it < 4; ++it) { cur[it] = r0[it]; r0[it] = r1[it]; r1[it] = r2[it]; }
-          load_resid(cc + 3, r2);
+          load_resid(k + 3 < chunks ? chunk_at(k + 3) : chunks, r2);
           tmem_ld_wait();
-          if (cc == chunks - 1) {  // accumulator fully read: hand TMEM back to the MMA warp
+          if (shared_chunks > 0 && k == shared_chunks - 1) {  // overlap drained: the next pass may start its MMAs
             tc_fence_before();
-            mbar_arrive(bar_tmem_empty);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tmem_empty);
+            if (threadIdx.x == 0) trace_event(p, 0, tcur, 3, tile);  // epilogue: overlap drained, TMEM handed back
           }
           // thread = accumulator row: 16 columns into the XOR-swizzled staging tile (conflict-free both ways)
 #pragma unroll
@@ -188,51 +217,61 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
                   }
                   if (has_resid) acc = make_float4(cur[it].x + acc.x, cur[it].y + acc.y, cur[it].z + acc.z, cur[it].w + acc.w);
                 }
-                stg4(p.out + e * d + col, acc);
+                if (!(p.ablate & 1)) stg4(p.out + e * d + col, acc);
               }
             }
           }
           __syncwarp();
         }
+        tc_fence_before();
+        if (threadIdx.x == 0) trace_event(p, 0, tcur, 4, tile);  // epilogue: done
         tphase ^= 1;
+        tw ^= 1;
       }
     }
   } else if (warp == MMA_WARP) {
     // ===================================== MMA ISSUER =====================================
     const uint32_t idesc_a = make_idesc_tf32(geo.n_a);
     const uint32_t idesc_b = make_idesc_tf32(geo.n_b > 0 ? geo.n_b : 16);
-    int s = 0;
+    int s = 0, tw = 0;
     uint32_t ph = 0, tphase = 0;
     for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
+        const uint32_t col_base = tw ? (uint32_t)(512 - geo.n_tile) : 0u;  // alternate TMEM windows (see the epilogue)
+        if (lane == 0) trace_event(p, 1, tcur, 10, tile);  // MMA: waiting for TMEM
         mbar_wait(bar_tmem_empty, tphase ^ 1);
         tc_fence_after();
+        if (lane == 0) trace_event(p, 1, tcur, 11, tile);  // MMA: TMEM granted
         for (int kb = 0; kb < geo.k_blocks; ++kb) {
           mbar_wait(bar_a_full + 8 * s, ph);
+          if (lane == 0) trace_event(p, 1, tcur, 12, tile, kb);  // MMA: A stage ready
           mbar_wait(bar_w_full + 8 * s, ph);
           tc_fence_after();
-          if (lane == 0) {
+          if (lane == 0) trace_event(p, 1, tcur, 13, tile, kb);  // MMA: W stage ready
+          if (elect_one()) {
             const int rem = d - kb * BLOCK_K;
-            const int ksteps = rem >= BLOCK_K ? BLOCK_K / 8 : (rem + 7) / 8;
-            const uint32_t a_hi = sbase + OFF_A_HI + s * A_STAGE_BYTES, a_lo = sbase + OFF_A_LO + s * A_STAGE_BYTES;
-            const uint32_t w_hi = sbase + OFF_W_HI + s * W_STAGE_BYTES, w_lo = sbase + OFF_W_LO + s * W_STAGE_BYTES;
-            for (int j = 0; j < ksteps; ++j) {
-              const uint32_t koff = j * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
-              const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff), da_lo = make_kmajor_sw128_desc(a_lo + koff);
-              const uint32_t first = (kb | j) != 0 ? 1u : 0u;
+            const int ksteps = (p.ablate & 8) ? 0 : (rem >= BLOCK_K ? BLOCK_K / 8 : (rem + 7) / 8);
+            const uint32_t a_hi = kmajor_desc_lo(sbase + OFF_A_HI + s * A_STAGE_BYTES), a_lo = kmajor_desc_lo(sbase + OFF_A_LO + s * A_STAGE_BYTES);
+            const uint32_t w_hi = kmajor_desc_lo(sbase + OFF_W_HI + s * W_STAGE_BYTES), w_lo = kmajor_desc_lo(sbase + OFF_W_LO + s * W_STAGE_BYTES);
+            const uint32_t d0 = tmem_base + col_base, d1 = d0 + (uint32_t)geo.n_a;
+            const uint32_t woff = (uint32_t)geo.n_a * (128u >> 4);  // second N half: n_a rows further down the W tile
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                if (half == 1 && geo.n_b == 0) break;
-                const uint32_t woff = half ? (uint32_t)geo.n_a * 128u : 0u;
-                const uint32_t dcol = tmem_base + (half ? (uint32_t)geo.n_a : 0u);
-                const uint32_t idesc = half ? idesc_b : idesc_a;
-                const uint64_t db_hi = make_kmajor_sw128_desc(w_hi + woff + koff), db_lo = make_kmajor_sw128_desc(w_lo + woff + koff);
+            for (int j = 0; j < BLOCK_K / 8; ++j) {
+              if (j < ksteps) {
+                const uint32_t k16 = j * 2;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row, in 16-byte units
+                const uint32_t acc = (kb | j) != 0 ? 1u : 0u;
                 if (p.products == 3) {
-                  umma_tf32(dcol, da_lo, db_hi, idesc, first);  // small terms first
-                  umma_tf32(dcol, da_hi, db_lo, idesc, 1u);
-                  umma_tf32(dcol, da_hi, db_hi, idesc, 1u);
+                  umma_tf32_lo(d0, a_lo + k16, w_hi + k16, KMAJOR_SW128_DESC_HI, idesc_a, acc);  // small terms first
+                  umma_tf32_lo(d0, a_hi + k16, w_lo + k16, KMAJOR_SW128_DESC_HI, idesc_a, 1u);
+                  umma_tf32_lo(d0, a_hi + k16, w_hi + k16, KMAJOR_SW128_DESC_HI, idesc_a, 1u);
+                  if (geo.n_b > 0) {
+                    umma_tf32_lo(d1, a_lo + k16, w_hi + woff + k16, KMAJOR_SW128_DESC_HI, idesc_b, acc);
+                    umma_tf32_lo(d1, a_hi + k16, w_lo + woff + k16, KMAJOR_SW128_DESC_HI, idesc_b, 1u);
+                    umma_tf32_lo(d1, a_hi + k16, w_hi + woff + k16, KMAJOR_SW128_DESC_HI, idesc_b, 1u);
+                  }
                 } else {
-                  umma_tf32(dcol, da_hi, db_hi, idesc, first);
+                  umma_tf32_lo(d0, a_hi + k16, w_hi + k16, KMAJOR_SW128_DESC_HI, idesc_a, acc);
+                  if (geo.n_b > 0) umma_tf32_lo(d1, a_hi + k16, w_hi + woff + k16, KMAJOR_SW128_DESC_HI, idesc_b, acc);
                 }
               }
             }
@@ -240,9 +279,11 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
             if (kb == geo.k_blocks - 1) umma_commit(bar_tmem_full);       // accumulator complete
           }
           __syncwarp();
+          if (lane == 0) trace_event(p, 1, tcur, 14, tile, kb);  // MMA: K-block issued
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         tphase ^= 1;
+        tw ^= 1;
       }
     }
   } else if (warp == W_WARP) {
@@ -254,12 +295,16 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
         for (int kb = 0; kb < geo.k_blocks; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          if (lane == 0) {
+          if (elect_one()) {
             const size_t off = ((size_t)nt * geo.k_blocks + kb) * tile_bytes;
             const bool need_lo = p.products == 3;
-            mbar_arrive_expect_tx(bar_w_full + 8 * s, need_lo ? 2 * tile_bytes : tile_bytes);
-            bulk_copy_g2s(sbase + OFF_W_HI + s * W_STAGE_BYTES, p.wimg + off, tile_bytes, bar_w_full + 8 * s);
-            if (need_lo) bulk_copy_g2s(sbase + OFF_W_LO + s * W_STAGE_BYTES, p.wimg + geo.part_bytes + off, tile_bytes, bar_w_full + 8 * s);
+            if ((p.ablate & 4) && !(tile == blockIdx.x && kb < STAGES)) {
+              mbar_arrive(bar_w_full + 8 * s);  // experiment: reuse whatever W the stage holds
+            } else {
+              mbar_arrive_expect_tx(bar_w_full + 8 * s, need_lo ? 2 * tile_bytes : tile_bytes);
+              bulk_copy_g2s(sbase + OFF_W_HI + s * W_STAGE_BYTES, p.wimg + off, tile_bytes, bar_w_full + 8 * s);
+              if (need_lo) bulk_copy_g2s(sbase + OFF_W_LO + s * W_STAGE_BYTES, p.wimg + geo.part_bytes + off, tile_bytes, bar_w_full + 8 * s);
+            }
           }
           __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -308,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
           for (int i = 0; i < 4; ++i) {  // all loads first: 8 x 16 B in flight per thread
             va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             vb[i] = va[i];
-            if (valid[i] && kvalid) {
+            if (valid[i] && kvalid && !(p.ablate & 2)) {
               if (MODE == 0) {
                 va[i] = ldg4(p.a0 + rowA[i] + k0);
                 vb[i] = ldg4_stream(p.a1 + rowB[i] + k0);
@@ -317,7 +362,9 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
               }
             }
           }
+          if (pt == 0) trace_event(p, 2, tcur, 20, tile, kb);  // producer: loads issued, waiting for the stage
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          if (pt == 0) trace_event(p, 2, tcur, 21, tile, kb);  // producer: stage free
           uint8_t* a_hi = smem + OFF_A_HI + s * A_STAGE_BYTES;
           uint8_t* a_lo = smem + OFF_A_LO + s * A_STAGE_BYTES;
 #pragma unroll
@@ -340,8 +387,10 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
             *reinterpret_cast<float4*>(a_hi + off) = hi;
             *reinterpret_cast<float4*>(a_lo + off) = lo;
           }
-          fence_proxy_async();  // make the generic-proxy writes visible to the tensor core (async proxy)
-          mbar_arrive(bar_a_full + 8 * s);
+          fence_proxy_async();  // make this thread's generic-proxy writes visible to the tensor core (async proxy)
+          __syncwarp();         // ... for every lane of the warp, then ONE arrive per warp (256 arrives per stage serialise)
+          if (lane == 0) mbar_arrive(bar_a_full + 8 * s);
+          if (pt == 0) trace_event(p, 2, tcur, 22, tile, kb);  // producer: stage written
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -392,7 +441,12 @@ static int launch(const Params& p, cudaStream_t st) {
   return NT_OK;
 }
 
+unsigned long long* g_trace_buffer = nullptr;
+
 static void fill_dropout(Params& p, float drop_p, uint64_t seed, uint64_t offset) {
+  static const int ablate = getenv("NOTORCH_B200_ABLATE") ? atoi(getenv("NOTORCH_B200_ABLATE")) : 0;
+  p.ablate = ablate;
+  p.trace = g_trace_buffer;
   p.drop_p = drop_p;
   p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   double t = (double)drop_p * 4294967296.0;
@@ -402,6 +456,8 @@ static void fill_dropout(Params& p, float drop_p, uint64_t seed, uint64_t offset
 }
 
 }  // namespace tc
+
+void tc_set_trace_buffer(void* ptr) { tc::g_trace_buffer = static_cast<unsigned long long*>(ptr); }
 
 size_t tc_weight_image_bytes(int64_t d) { return 2 * tc::make_geometry((int)d).part_bytes; }
 

@@ -72,6 +72,30 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One lane of a converged warp. ptxas recognises the ELECT-derived predicate, so code under `if (elect_one())` may feed
+// tcgen05 / bulk-copy instructions from uniform registers directly; with `if (lane == 0)` it wraps every such instruction
+// in a vote/elect loop (~100+ cycles each, which made the MMA issuer the bottleneck of the fused kernels).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+// tcgen05.mma.kind::tf32 with both shared-memory descriptors given as (low word, shared high word): the high words of
+// all descriptors of one layout are identical, the low word is base + (byte offset >> 4).
+__device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+constexpr uint32_t KMAJOR_SW128_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1 KiB, version 1, SWIZZLE_128B
+constexpr uint32_t MNMAJOR_SW128B32_DESC_HI = (512u >> 4) | (1u << 14) | (1u << 29);  // SBO = 512 B, version 1, SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t mnmajor_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) { return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_raw + 8 * s, 1);
-      mbar_init(bar_ready + 8 * s, NUM_X_THREADS);
+      mbar_init(bar_ready + 8 * s, NUM_X_WARPS);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tmem_full, 1);
@@ -158,29 +158,28 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
     for (int64_t kb = 0; kb < nkb; ++kb) {
       mbar_wait(bar_ready + 8 * s, ph);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_hi = sbase + s * STAGE_BYTES, b_hi = a_hi + A_CHUNKS * CHUNK_BYTES;
-        const uint32_t a_lo = a_hi + PART_BYTES, b_lo = b_hi + PART_BYTES;
+      if (elect_one()) {
+        const uint32_t st0 = sbase + s * STAGE_BYTES;
+        const uint32_t a_hi = mnmajor_desc_lo(st0, CHUNK_BYTES), b_hi = mnmajor_desc_lo(st0 + A_CHUNKS * CHUNK_BYTES, CHUNK_BYTES);
+        const uint32_t a_lo = mnmajor_desc_lo(st0 + PART_BYTES, CHUNK_BYTES), b_lo = mnmajor_desc_lo(st0 + PART_BYTES + A_CHUNKS * CHUNK_BYTES, CHUNK_BYTES);
+        const uint32_t d1 = tmem_base + (uint32_t)geo.n_a;
+        const uint32_t boff = (uint32_t)(geo.n_a / 32) * (CHUNK_BYTES >> 4);  // second N half: n_a / 32 chunks further
 #pragma unroll
         for (int j = 0; j < BLOCK_E / 8; ++j) {
-          const uint32_t koff = j * 1024;  // 8 edges = two 4-row swizzle atoms
-          const uint64_t da_hi = make_mnmajor_sw128b32_desc(a_hi + koff, CHUNK_BYTES, 512), da_lo = make_mnmajor_sw128b32_desc(a_lo + koff, CHUNK_BYTES, 512);
+          const uint32_t k16 = j * (1024u >> 4);  // next 8 edges = the next two 4-row swizzle atoms of every chunk
           const uint32_t acc = (kb | j) != 0 ? 1u : 0u;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (half == 1 && geo.n_b == 0) break;
-            const uint32_t boff = half ? (uint32_t)(geo.n_a / 32) * CHUNK_BYTES : 0u;
-            const uint32_t dcol = tmem_base + (half ? (uint32_t)geo.n_a : 0u);
-            const uint32_t idesc = half ? idesc_b : idesc_a;
-            const uint64_t db_hi = make_mnmajor_sw128b32_desc(b_hi + boff + koff, CHUNK_BYTES, 512);
-            const uint64_t db_lo = make_mnmajor_sw128b32_desc(b_lo + boff + koff, CHUNK_BYTES, 512);
-            if (p.products == 3) {
-              umma_tf32(dcol, da_lo, db_hi, idesc, acc);
-              umma_tf32(dcol, da_hi, db_lo, idesc, 1u);
-              umma_tf32(dcol, da_hi, db_hi, idesc, 1u);
-            } else {
-              umma_tf32(dcol, da_hi, db_hi, idesc, acc);
+          if (p.products == 3) {
+            umma_tf32_lo(tmem_base, a_lo + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, acc);
+            umma_tf32_lo(tmem_base, a_hi + k16, b_lo + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, 1u);
+            umma_tf32_lo(tmem_base, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, 1u);
+            if (geo.n_b > 0) {
+              umma_tf32_lo(d1, a_lo + k16, b_hi + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, acc);
+              umma_tf32_lo(d1, a_hi + k16, b_lo + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, 1u);
+              umma_tf32_lo(d1, a_hi + k16, b_hi + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, 1u);
             }
+          } else {
+            umma_tf32_lo(tmem_base, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, acc);
+            if (geo.n_b > 0) umma_tf32_lo(d1, a_hi + k16, b_hi + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, acc);
           }
         }
         umma_commit(bar_empty + 8 * s);
@@ -191,7 +190,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
     }
   } else if (warp == TMA_WARP) {
     // ===================================== TMA PRODUCER =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t bytes = (uint32_t)(A_CHUNKS + b_chunks) * CHUNK_BYTES;
@@ -247,7 +246,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
         *reinterpret_cast<float4*>(lo + u * 16) = l4;
       }
       fence_proxy_async();
-      mbar_arrive(bar_ready + 8 * s);
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(bar_ready + 8 * s);
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   }
