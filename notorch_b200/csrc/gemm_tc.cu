@@ -33,6 +33,7 @@ constexpr int A_STAGE_BYTES = TILE_M * 128;          // 16 KiB per part
 constexpr int W_STAGE_BYTES = MAX_N_TILE * 128;      // 38 KiB per part
 constexpr int EPI_COLS = 16;                         // accumulator columns per epilogue step
 constexpr int EPI_WARP_BYTES = 32 * EPI_COLS * 4;    // 2 KiB staging tile per epilogue warp (XOR-swizzled)
+constexpr int PF_DIST = 3;                           // producers prefetch this many K-blocks ahead into L2
 constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, W_WARP = 5, FIRST_A_WARP = 6, NUM_A_WARPS = 8;
 constexpr int NUM_A_THREADS = NUM_A_WARPS * 32;
 constexpr int THREADS = (FIRST_A_WARP + NUM_A_WARPS) * 32;  // 448
@@ -152,7 +153,6 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
     int tw = 0;
     for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
       const int64_t row0 = tile * TILE_M + warp * 32;
-      if (has_resid && row0 + lane < p.E) l2_prefetch_bulk(p.resid + (row0 + lane) * d, (uint32_t)d * 4u);
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
         auto load_resid = [&](int cc, float4 (&dst)[4]) {
           const int col = nt * geo.n_tile + cc * EPI_COLS + sub * 4;
@@ -169,24 +169,23 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
         const int col_base = tw ? 512 - geo.n_tile : 0;
         const int first = (tw == 0 && shared_chunks > 0) ? chunks - shared_chunks : 0;  // rotation of the chunk order
         auto chunk_at = [&](int k) { int c = k + first; return c >= chunks ? c - chunks : c; };
-        float4 r0[4], r1[4], r2[4];
-        load_resid(chunk_at(0), r0);
-        load_resid(chunks > 1 ? chunk_at(1) : chunks, r1);
-        load_resid(chunks > 2 ? chunk_at(2) : chunks, r2);
+        // residual rows are software-pipelined three chunks ahead in three statically named buffers (a rotating
+        // register array would make every iteration wait for the load issued by the previous one)
+        float4 rA[4], rB[4], rC[4];
+        load_resid(chunk_at(0), rA);
+        load_resid(chunks > 1 ? chunk_at(1) : chunks, rB);
+        load_resid(chunks > 2 ? chunk_at(2) : chunks, rC);
         if (threadIdx.x == 0) trace_event(p, 0, tcur, 1, tile);  // epilogue: waiting for the accumulator
         mbar_wait(bar_tmem_full, tphase);
         tc_fence_after();
         if (threadIdx.x == 0) trace_event(p, 0, tcur, 2, tile);  // epilogue: accumulator ready
         if (shared_chunks == 0 && lane == 0) mbar_arrive(bar_tmem_empty);  // the other window is free as soon as this pass has begun
-        for (int k = 0; k < chunks; ++k) {
+        auto do_chunk = [&](int k, float4 (&cur)[4]) {
           const int cc = chunk_at(k);
           uint32_t v[16];
           tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(col_base + cc * EPI_COLS), v);
-          float4 cur[4];
-#pragma unroll
-          for (int it = 0; it < 4; ++it) { cur[it] = r0[it]; r0[it] = r1[it]; r1[it] = r2[it]; }
-          load_resid(k + 3 < chunks ? chunk_at(k + 3) : chunks, r2);
           tmem_ld_wait();
+          if (threadIdx.x == 0) trace_event(p, 0, tcur, 5, tile, k);  // epilogue: chunk k loaded from TMEM
           if (shared_chunks > 0 && k == shared_chunks - 1) {  // overlap drained: the next pass may start its MMAs
             tc_fence_before();
             __syncwarp();
@@ -198,6 +197,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
           for (int q = 0; q < 4; ++q)
             *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           __syncwarp();
+          if (threadIdx.x == 0) trace_event(p, 0, tcur, 6, tile, k);  // epilogue: chunk k staged
           // 4 lanes per row (64 contiguous bytes), 8 rows per step: coalesced global traffic
           const int col = nt * geo.n_tile + cc * EPI_COLS + sub * 4;
           if (col < d) {
@@ -221,7 +221,15 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
               }
             }
           }
+          if (threadIdx.x == 0) trace_event(p, 0, tcur, 7, tile, k);  // epilogue: chunk k stored
           __syncwarp();
+          load_resid(k + 3 < chunks ? chunk_at(k + 3) : chunks, cur);  // refill this buffer for chunk k + 3
+          if (threadIdx.x == 0) trace_event(p, 0, tcur, 8, tile, k);  // epilogue: refill issued
+        };
+        for (int k = 0; k < chunks; k += 3) {
+          do_chunk(k, rA);
+          if (k + 1 < chunks) do_chunk(k + 1, rB);
+          if (k + 2 < chunks) do_chunk(k + 2, rC);
         }
         tc_fence_before();
         if (threadIdx.x == 0) trace_event(p, 0, tcur, 4, tile);  // epilogue: done
@@ -318,31 +326,34 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
     const int r0 = pt >> 3;                          // rows r0, r0+32, r0+64, r0+96
     int s = 0;
     uint32_t ph = 0;
-    for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-      {  // pull the NEXT tile's operand rows into L2 (one row per producer thread) while this tile is processed
-        const int64_t en = (tile + gridDim.x) * TILE_M + (pt & (TILE_M - 1));
-        if (en < p.E) {
-          if (MODE == 0) {
-            if (pt < TILE_M) l2_prefetch_bulk(p.a0 + (int64_t)__ldg(p.src + en) * d, (uint32_t)d * 4u);
-            else l2_prefetch_bulk(p.a1 + (int64_t)__ldg(p.rev + en) * d, (uint32_t)d * 4u);
-          } else if (pt < TILE_M) {
-            l2_prefetch_bulk(p.a0 + en * d, (uint32_t)d * 4u);
-          }
-        }
-      }
-      int64_t rowA[4], rowB[4];
-      bool valid[4];
+    // Row bases (element offsets) of this thread's four tile rows, for the current and the next tile. The next tile's
+    // indices are fetched a whole tile early so that the dependent src/rev -> row-address chain is never exposed.
+    int64_t rowA[4], rowB[4], nextA[4], nextB[4];
+    bool valid[4], next_valid[4];
+    auto fetch_rows = [&](int64_t t, int64_t (&ra)[4], int64_t (&rb)[4], bool (&ok)[4]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int64_t e = tile * TILE_M + r0 + 32 * i;
-        valid[i] = e < p.E;
+        const int64_t e = t * TILE_M + r0 + 32 * i;
+        ok[i] = t < m_tiles && e < p.E;
         if (MODE == 0) {
-          rowA[i] = valid[i] ? (int64_t)__ldg(p.src + e) * d : 0;
-          rowB[i] = valid[i] ? (int64_t)__ldg(p.rev + e) * d : 0;
+          ra[i] = ok[i] ? (int64_t)__ldg(p.src + e) * d : 0;
+          rb[i] = ok[i] ? (int64_t)__ldg(p.rev + e) * d : 0;
         } else {
-          rowA[i] = e * d;
-          rowB[i] = 0;
+          ra[i] = e * d;
+          rb[i] = 0;
         }
+      }
+    };
+    fetch_rows(blockIdx.x, nextA, nextB, next_valid);
+    for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { rowA[i] = nextA[i]; rowB[i] = nextB[i]; valid[i] = next_valid[i]; }
+      fetch_rows(tile + gridDim.x, nextA, nextB, next_valid);
+      if (MODE == 0 && p.resid != nullptr && warp == FIRST_A_WARP && elect_one()) {
+        // the epilogue of THIS tile (one main loop from now) adds the residual rows h[tile rows, :]: one contiguous block
+        const int64_t e0 = tile * TILE_M;
+        const int64_t rows = p.E - e0 < TILE_M ? p.E - e0 : TILE_M;
+        l2_prefetch_bulk(p.resid + e0 * d, (uint32_t)(rows * d * 4));
       }
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
         for (int kb = 0; kb < geo.k_blocks; ++kb) {
@@ -359,6 +370,21 @@ __global__ void __launch_bounds__(THREADS, 1) layer_gemm_tc(const Params p) {
                 vb[i] = ldg4_stream(p.a1 + rowB[i] + k0);
               } else {
                 va[i] = ldg4_stream(p.a0 + rowA[i] + k0);
+              }
+            }
+          }
+          {  // L2 prefetch PF_DIST K-blocks ahead (this thread's own 16-byte chunks; running into the next tile's rows at the end)
+            int kp = kb + PF_DIST;
+            const bool into_next = kp >= geo.k_blocks;
+            if (into_next) kp -= geo.k_blocks;
+            const int kp0 = kp * BLOCK_K + c * 4;
+            if (kp0 < d && (!into_next || nt == geo.n_tiles - 1)) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (into_next ? next_valid[i] : valid[i]) {
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(p.a0 + (into_next ? nextA[i] : rowA[i]) + kp0));
+                  if (MODE == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.a1 + (into_next ? nextB[i] : rowB[i]) + kp0));
+                }
               }
             }
           }

@@ -20,6 +20,8 @@ img = ops._weight_image(W, False); imgt = ops._weight_image(W, True)
 out = torch.empty_like(h); m = torch.empty_like(h)
 def fwd(): _lib.check(L.nt_layer_forward(p(h), p(n), p(csr.src), p(csr.rev), p(W), p(img), p(b), E, V, d, 1, 0.0, 1, 0.0, 0, 0, p(out), p(m), 0, mode, st), "fwd")
 def fwd_nom(): _lib.check(L.nt_layer_forward(p(h), p(n), p(csr.src), p(csr.rev), p(W), p(img), p(b), E, V, d, 1, 0.0, 1, 0.0, 0, 0, p(out), None, 0, mode, st), "fwd")
+def fwd_nores(): _lib.check(L.nt_layer_forward(p(h), p(n), p(csr.src), p(csr.rev), p(W), p(img), p(b), E, V, d, 1, 0.0, 0, 0.0, 0, 0, p(out), None, 0, mode, st), "fwd")
+def fwd_nores_nobias(): _lib.check(L.nt_layer_forward(p(h), p(n), p(csr.src), p(csr.rev), p(W), p(img), None, E, V, d, 1, 0.0, 0, 0.0, 0, 0, p(out), None, 0, mode, st), "fwd")
 def dgrad(): _lib.check(L.nt_layer_backward_dgrad(p(g), p(W), p(imgt), E, d, 0.0, 0, 0, p(out), 0, mode, st), "dgrad")
 def timeit(f, n=20):
     for _ in range(3): f()
@@ -27,4 +29,4 @@ def timeit(f, n=20):
     s.record()
     for _ in range(n): f()
     e.record(); torch.cuda.synchronize(); return s.elapsed_time(e) / n * 1e3
-print(f"ABLATE={os.environ.get('NOTORCH_B200_ABLATE','0'):>2s} GEMM={os.environ.get('GEMM','tf32x3'):7s} K2 {timeit(fwd):7.1f} us   K2(no m_out) {timeit(fwd_nom):7.1f} us   K4a {timeit(dgrad):7.1f} us")
+print(f"ABLATE={os.environ.get('NOTORCH_B200_ABLATE','0'):>2s} GEMM={os.environ.get('GEMM','tf32x3'):7s} K2 {timeit(fwd):7.1f} us   K2(no m_out) {timeit(fwd_nom):7.1f} us   K4a {timeit(dgrad):7.1f} us   K2(no m_out, no resid) {timeit(fwd_nores):7.1f}   K2(no m_out/resid/bias) {timeit(fwd_nores_nobias):7.1f}")

@@ -25,7 +25,7 @@ buf = torch.zeros(65001, dtype=torch.int64, device="cuda")
 L.nt_debug_set_trace_buffer(buf.data_ptr()); f(); torch.cuda.synchronize(); L.nt_debug_set_trace_buffer(None)
 rec = buf[1:].cpu().numpy().astype("uint64"); rec = rec[rec != 0]; n_rec = len(rec)
 ev = (rec >> 56) & 0xFF; tile = (rec >> 40) & 0xFFFF; aux = (rec >> 32) & 0xFF; clk = (rec & 0xFFFFFFFF).astype("int64")
-t0 = clk.min(); names = {1: "epi wait", 2: "epi ready", 3: "epi handback", 4: "epi done", 10: "mma wait tmem", 11: "mma tmem ok", 12: "mma A ready", 13: "mma W ready", 14: "mma issued", 20: "prod loads issued", 21: "prod stage free", 22: "prod stage written"}
+t0 = clk.min(); names = {7: "epi chunk stored", 8: "epi refill issued", 5: "epi chunk loaded", 6: "epi chunk staged", 1: "epi wait", 2: "epi ready", 3: "epi handback", 4: "epi done", 10: "mma wait tmem", 11: "mma tmem ok", 12: "mma A ready", 13: "mma W ready", 14: "mma issued", 20: "prod loads issued", 21: "prod stage free", 22: "prod stage written"}
 print(f"{which}: {n_rec} records; tiles seen {sorted(set(tile.tolist()))[:4]}...")
 tiles = sorted(set(tile.tolist()))
 order = sorted(range(len(rec)), key=lambda i: clk[i])
@@ -33,7 +33,7 @@ sel = tiles[2] if len(tiles) > 3 else tiles[0]
 print(f"--- timeline around tile {sel} (cycles since kernel start; only events of tiles {sel} and next)")
 nxt = tiles[tiles.index(sel) + 1] if tiles.index(sel) + 1 < len(tiles) else sel
 for i in order:
-    if tile[i] == sel and 2 <= aux[i] <= 5 and ev[i] >= 10:
+    if tile[i] == sel and ev[i] < 10 and aux[i] <= 7:
         print(f"{clk[i]-t0:9d}  tile {tile[i]:5d} kb {aux[i]:2d}  {names.get(int(ev[i]), ev[i])}")
 # per-tile summaries
 def first(evid, t, a=None):
