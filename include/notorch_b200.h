@@ -196,6 +196,35 @@ size_t nt_embedding_bag_backward_workspace_bytes(int64_t n, int64_t num_types, i
 int nt_embedding_bag_backward(const void* g, const int64_t* idx, int64_t n, int64_t bag, int64_t num_types, int64_t d,
                               void* g_table, void* workspace, size_t workspace_bytes, int dtype, nt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Remaining read-outs of notorch/nn/gnn/agg.py (row N2). Segments are given as a CSR (rowptr, perm; perm NULL =
+ * contiguous rows); every loop is sequential in ascending row order (deterministic).
+ *  nt_seg_max            agg.Max (agg.py:45, torch_scatter.scatter_max): out[s,c] = max, arg = first row attaining it
+ *                        (-1 and value 0 for an empty segment). Backward routes g to the arg row.
+ *  nt_row_dot            out[i] = scale * <x[i,:], y[row(i),:]> + bias, row(i) = y_index[i] | 0 (y_rows == 1) | i
+ *  nt_seg_softmax(_backward)  torch_scatter.scatter_softmax over a [n] score vector (agg.py:60,83)
+ *  nt_seg_weighted_sum   out[s,:] = scale * sum_j w[r_j] * x[r_j,:]          (agg.py:61,84: scatter_sum(alpha * x))
+ *  nt_row_scale_gather   out[i,:] = scale * w[i] * y[y_index ? y_index[i] : 0, :]   (backward of the two above)
+ *  nt_weighted_col_sum   out[c] = scale * sum_i w[i] * x[i,c]  (w NULL = 1), two fixed-order stages
+ * ---------------------------------------------------------------------------------------------- */
+int nt_seg_max(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments,
+               void* out, int32_t* arg, int dtype, nt_stream_t stream);
+int nt_seg_max_backward(const void* g, const int32_t* arg, const int32_t* seg_of_row, int64_t n, int64_t d,
+                        void* gx, int dtype, nt_stream_t stream);
+int nt_row_dot(const void* x, const void* y, const int32_t* y_index, int64_t y_rows, int64_t n, int64_t d,
+               float scale, float bias, void* out, int dtype, nt_stream_t stream);
+int nt_seg_softmax(const void* s, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, void* alpha,
+                   int dtype, nt_stream_t stream);
+int nt_seg_softmax_backward(const void* alpha, const void* g_alpha, const int32_t* rowptr, const int32_t* perm,
+                            int64_t num_segments, void* g_s, int dtype, nt_stream_t stream);
+int nt_seg_weighted_sum(const void* x, const void* w, int64_t d, const int32_t* rowptr, const int32_t* perm,
+                        int64_t num_segments, float scale, void* out, int dtype, nt_stream_t stream);
+int nt_row_scale_gather(const void* y, const void* w, const int32_t* y_index, int64_t n, int64_t d, float scale,
+                        void* out, int dtype, nt_stream_t stream);
+size_t nt_weighted_col_sum_workspace_bytes(int64_t n, int64_t d);
+int nt_weighted_col_sum(const void* x, const void* w, int64_t n, int64_t d, float scale, void* out,
+                        void* workspace, size_t workspace_bytes, int dtype, nt_stream_t stream);
+
 /* Dropout keep-mask exactly as K2/K4 compute it (1.0f keep / 0.0f drop), for tests. */
 int nt_dropout_mask(int64_t n_rows, int64_t d, float dropout_p, uint64_t seed, uint64_t offset,
                     float* mask, nt_stream_t stream);

@@ -44,6 +44,15 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "nt_embedding_bag_sum": (_int, [_vp, _i64, _i64p, _i64, _i64, _i64, _vp, _i32p, _int, _vp]),
     "nt_embedding_bag_backward_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "nt_embedding_bag_backward": (_int, [_vp, _i64p, _i64, _i64, _i64, _i64, _vp, _vp, _sz, _int, _vp]),
+    "nt_seg_max": (_int, [_vp, _i64, _i32p, _i32p, _i64, _vp, _i32p, _int, _vp]),
+    "nt_seg_max_backward": (_int, [_vp, _i32p, _i32p, _i64, _i64, _vp, _int, _vp]),
+    "nt_row_dot": (_int, [_vp, _vp, _i32p, _i64, _i64, _i64, _f32, _f32, _vp, _int, _vp]),
+    "nt_seg_softmax": (_int, [_vp, _i32p, _i32p, _i64, _vp, _int, _vp]),
+    "nt_seg_softmax_backward": (_int, [_vp, _vp, _i32p, _i32p, _i64, _vp, _int, _vp]),
+    "nt_seg_weighted_sum": (_int, [_vp, _vp, _i64, _i32p, _i32p, _i64, _f32, _vp, _int, _vp]),
+    "nt_row_scale_gather": (_int, [_vp, _vp, _i32p, _i64, _i64, _f32, _vp, _int, _vp]),
+    "nt_weighted_col_sum_workspace_bytes": (_sz, [_i64, _i64]),
+    "nt_weighted_col_sum": (_int, [_vp, _vp, _i64, _i64, _f32, _vp, _vp, _sz, _int, _vp]),
     "nt_dropout_mask": (_int, [_i64, _i64, _f32, _u64, _u64, _vp, _vp]),
 }
 

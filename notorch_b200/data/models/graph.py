@@ -59,6 +59,7 @@ class Graph(UpdateMixin):
         self.__dict__.pop("_nt_csr", None)
         self.__dict__.pop("_nt_seg_csr", None)
         self.__dict__.pop("_nt_mol_ptr", None)
+        self.__dict__.pop("_nt_mol_csr", None)
         return self
 
     def _field_lines(self) -> list[str]:

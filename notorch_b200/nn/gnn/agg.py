@@ -1,13 +1,14 @@
 """Atom -> molecule read-outs — drop-in for ``Sum`` / ``Mean`` of ``notorch/nn/gnn/agg.py:23-38``
 (K3: deterministic segmented reduction over the CSR of ``batch_node_index``, no atomics), plus the
 builder-defined ``Norm`` extension BASELINE config 4 names (not in the
-reference tree, parity unpinned). ``Max``, ``Gated`` and ``SDPAttention`` (agg.py:41-86) are the
-"next" row N2 and raise until their kernels exist — by design there is no fallback.
+reference tree, parity unpinned) and the row-N2 read-outs ``Max`` (pinned), ``Gated`` and ``SDPAttention``
+(agg.py:41-86; both are broken in the reference, see their docstrings).
 """
 from __future__ import annotations
 
 from abc import abstractmethod
 
+import torch
 import torch.nn as nn
 from torch import Tensor
 
@@ -16,6 +17,14 @@ from ...data.models.graph import BatchedGraph
 
 
 def _mol_csr(G: BatchedGraph) -> ops.SegmentCSR:
+    ptr = getattr(G, "_nt_mol_ptr", None)
+    if ptr is not None and ptr.device == G.batch_node_index.device:
+        # collated on the device (BatchedGraph.from_packed): molecules are contiguous atom ranges, no permutation needed
+        cached = getattr(G, "_nt_mol_csr", None)
+        if cached is None:
+            cached = ops.SegmentCSR(ptr, None, G.batch_node_index.to(torch.int32), len(G))
+            G._nt_mol_csr = cached
+        return cached
     return ops.segment_csr_for(G, "batch_node_index", len(G))
 
 
@@ -46,22 +55,50 @@ class Norm(Aggregation):
         return ops.readout(G.node_feats, _mol_csr(G), "norm", self.norm)
 
 
-class _NotYet(Aggregation):
+class Max(Aggregation):
+    """``scatter_max`` read-out (agg.py:41-47); pinned against the reference (``tests/golden/readout_max.npz``)."""
+
     def forward(self, G: BatchedGraph, **kwargs) -> Tensor:
-        raise NotImplementedError(f"notorch_b200: {type(self).__name__} read-out has no sm_100a kernel yet (SURVEY.md §8f N2); no fallback")
+        from ... import readouts
+
+        hiddens, _ = readouts.seg_max(G.node_feats, _mol_csr(G))
+        return hiddens
 
 
-class Max(_NotYet):
-    pass
+class Gated(Aggregation):
+    """Softmax-gated sum: ``alpha = softmax_b(Linear(x))``, ``H[b] = sum_v alpha[v] x[v]`` (agg.py:50-63).
 
+    DEVIATION, labelled: the reference's ``forward`` unsqueezes ``alpha`` ([V,1] -> [V,1,1]) before multiplying it with
+    ``node_feats`` [V,d], which broadcasts to [V,V,d] and returns a ``[b, V, d]`` tensor (agg.py:60-61, checked by
+    running it). This implements the evident intent (``alpha`` of shape [V,1]); parity is pinned to the builder's
+    restatement only (``oracle.dmpnn_oracle.readout_gated``). Parameter names match (``a.weight`` [1,d], ``a.bias`` [1])."""
 
-class Gated(_NotYet):
     def __init__(self, input_dim: int = 256):
         super().__init__()
         self.a = nn.Linear(input_dim, 1)
 
+    def forward(self, G: BatchedGraph, **kwargs) -> Tensor:
+        from ... import readouts
 
-class SDPAttention(_NotYet):
+        csr = _mol_csr(G)
+        scores = readouts._RowDotVector.apply(G.node_feats, self.a.weight, self.a.bias)
+        return readouts.attention_readout(G.node_feats, scores, csr)
+
+
+class SDPAttention(Aggregation):
+    """Scaled dot-product attention read-out against a per-molecule query ``Q`` [b,d] (agg.py:66-86).
+
+    DEVIATION, labelled: the reference's ``forward`` raises — its einsum string ``"V d_v, V d_v -> V"`` is not a
+    valid equation (agg.py:80, checked by running it). This implements what the string means:
+    ``scores[v] = <Q[batch[v]], x[v]> / sqrt(key_dim)``; parity is pinned to the builder's restatement only."""
+
     def __init__(self, key_dim: int = 256):
         super().__init__()
         self.sqrt_key_dim = key_dim ** 0.5
+
+    def forward(self, G: BatchedGraph, *, Q: Tensor, **kwargs) -> Tensor:
+        from ... import readouts
+
+        csr = _mol_csr(G)
+        scores = readouts._RowDotSegment.apply(G.node_feats, Q, csr, 1.0 / self.sqrt_key_dim)
+        return readouts.attention_readout(G.node_feats, scores, csr)

@@ -199,6 +199,36 @@ def readout(x: Tensor, batch_node_index: Tensor, size: int, kind: str = "sum", n
     raise NotImplementedError(kind)
 
 
+def readout_max(x: Tensor, batch_node_index: Tensor, size: int) -> Tensor:
+    """``agg.Max`` (agg.py:41-47): ``torch_scatter.scatter_max`` values; empty molecules give 0."""
+    idx = batch_node_index.view(-1, 1).expand_as(x)
+    out = torch.full((size, x.shape[1]), float("-inf"), dtype=x.dtype).scatter_reduce(0, idx, x, reduce="amax", include_self=True)
+    return torch.where(torch.isinf(out) & (out < 0), torch.zeros_like(out), out)
+
+
+def _seg_softmax(scores: Tensor, index: Tensor, size: int) -> Tensor:
+    """``torch_scatter.scatter_softmax`` over a vector (composite/softmax.py): max -> exp -> sum -> divide."""
+    mx = torch.full((size,), float("-inf"), dtype=scores.dtype).scatter_reduce(0, index, scores, reduce="amax", include_self=True)
+    ex = (scores - mx[index]).exp()
+    return ex / torch.zeros(size, dtype=scores.dtype).scatter_add_(0, index, ex)[index]
+
+
+def readout_gated(x: Tensor, weight: Tensor, bias: Tensor | None, batch_node_index: Tensor, size: int) -> Tensor:
+    """INTENDED semantics of ``agg.Gated`` (agg.py:50-63): ``alpha = softmax_b(x w^T + b)`` of shape [V], ``H[b] = sum alpha x``.
+    The reference itself mis-broadcasts (returns [b, V, d]); this restatement is the builder's, parity unpinned."""
+    scores = torch.nn.functional.linear(x, weight, bias).squeeze(1)
+    alpha = _seg_softmax(scores, batch_node_index, size)
+    return seg_reduce(alpha.unsqueeze(1) * x, batch_node_index, size, "sum")
+
+
+def readout_sdpa(x: Tensor, Q: Tensor, batch_node_index: Tensor, size: int, key_dim: int) -> Tensor:
+    """INTENDED semantics of ``agg.SDPAttention`` (agg.py:66-86): ``scores = <Q[batch], x> / sqrt(key_dim)``. The reference
+    raises on its einsum string; this restatement is the builder's, parity unpinned."""
+    scores = (Q[batch_node_index] * x).sum(1) / key_dim ** 0.5
+    alpha = _seg_softmax(scores, batch_node_index, size)
+    return seg_reduce(alpha.unsqueeze(1) * x, batch_node_index, size, "sum")
+
+
 def _act_grad(h: Tensor, act: str, act_param: float | None) -> Tensor:
     hh = h.detach().clone().requires_grad_(True)
     apply_act(hh, act, act_param).sum().backward()

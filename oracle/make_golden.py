@@ -139,6 +139,27 @@ def run_case(name: str, cfg: dict, seed: int) -> dict[str, np.ndarray]:
     return out
 
 
+def run_readout_max(seed: int) -> dict[str, np.ndarray]:
+    """``agg.Max`` of the reference (agg.py:41-47) incl. an empty molecule and tied maxima, forward + backward."""
+    ref = reference_loader.load()
+    g = torch.Generator().manual_seed(seed)
+    B, d = 7, 24
+    counts = [5, 1, 0, 9, 3, 0, 6]  # molecules 2 and 5 own no atom
+    batch = torch.repeat_interleave(torch.arange(B), torch.tensor(counts))
+    V = int(batch.numel())
+    x = torch.randn(V, d, generator=g)
+    x[0, :4] = x[1, :4] = 3.0  # ties: the first maximum wins
+    gH = torch.randn(B, d, generator=g)
+    xr = x.clone().requires_grad_(True)
+    G = ref.BatchedGraph(xr, torch.zeros(0, d), torch.zeros(2, 0, dtype=torch.long), torch.zeros(0, dtype=torch.long),
+                         batch_node_index=batch, batch_edge_index=torch.zeros(0, dtype=torch.long), size=B)
+    H = ref.agg.Max()(G)
+    (H * gH).sum().backward()
+    meta = dict(name="readout_max", seed=seed, B=B, d=d, V=V)
+    return {"meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), "x": x.numpy(), "batch_node_index": batch.numpy(),
+            "gH": gH.numpy(), "H": H.detach().numpy(), "g_x": xr.grad.numpy()}
+
+
 def main() -> None:
     if not reference_loader.available():
         raise SystemExit("reference tree not found; golden fixtures can only be made in the authoring container")
@@ -151,6 +172,10 @@ def main() -> None:
         total += os.path.getsize(path)
         print(f"{name:18s} V={int(data['num_atoms'].sum()):4d} E={int(data['num_edges'].sum()):4d} "
               f"{os.path.getsize(path) / 1024:.0f} KiB")
+    extra = run_readout_max(seed=9001)
+    path = os.path.join(OUT, "..", "golden_readouts", "readout_max.npz")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    np.savez_compressed(path, **extra)
     print(f"total {total / 1024:.0f} KiB -> {OUT}")
 
 

@@ -75,21 +75,25 @@ def scatter_mean(src: Tensor, index: Tensor, dim: int = -1, out: Tensor | None =
 
 def scatter_max(src: Tensor, index: Tensor, dim: int = -1, out: Tensor | None = None,
                 dim_size: int | None = None) -> tuple[Tensor, Tensor]:
+    """Upstream is a custom C++/CUDA op: values + ``arg`` (index of the maximum; ``src.size(dim)`` for an empty
+    segment, whose value is 0), and its backward routes the gradient to the ``arg`` element only. On CPU the reducer
+    updates on a strict ``>``, so the FIRST maximum wins on ties. Restated with that forward and that backward."""
     index_b = _broadcast(index, src, dim)
     size = _out_size(src, index_b, dim, dim_size)
-    vals = torch.full(size, float("-inf"), dtype=src.dtype, device=src.device)
-    vals = vals.scatter_reduce(dim, index_b, src, reduce="amax", include_self=True)
-    empty = torch.isinf(vals) & (vals < 0)
-    # argmax: first position attaining the max
     n = src.size(dim)
-    pos_shape = [1] * src.dim()
-    pos_shape[dim] = n
-    pos = torch.arange(n, device=src.device).view(pos_shape).expand(src.size())
-    hit = src == vals.gather(dim, index_b)
-    cand = torch.where(hit, pos, torch.full_like(pos, n))
-    arg = torch.full(size, n, dtype=torch.long, device=src.device)
-    arg = arg.scatter_reduce(dim, index_b, cand, reduce="amin", include_self=True)
-    vals = vals.masked_fill(empty, 0)
+    with torch.no_grad():
+        vals = torch.full(size, float("-inf"), dtype=src.dtype, device=src.device)
+        vals = vals.scatter_reduce(dim, index_b, src, reduce="amax", include_self=True)
+        pos_shape = [1] * src.dim()
+        pos_shape[dim] = n
+        pos = torch.arange(n, device=src.device).view(pos_shape).expand(src.size())
+        hit = src == vals.gather(dim, index_b)
+        cand = torch.where(hit, pos, torch.full_like(pos, n))
+        arg = torch.full(size, n, dtype=torch.long, device=src.device)
+        arg = arg.scatter_reduce(dim, index_b, cand, reduce="amin", include_self=True)
+    empty = arg == n
+    picked = src.gather(dim, arg.clamp(max=max(n - 1, 0))) if n > 0 else torch.zeros(size, dtype=src.dtype, device=src.device)
+    vals = torch.where(empty, torch.zeros_like(picked), picked)  # gradient flows to the arg element only
     return vals, arg
 
 

@@ -346,8 +346,6 @@ def test_unsupported_inputs_raise():
         ChempropBlock(hidden_dim=16, depth=1, reduce="max").cuda()(G)
     with pytest.raises(NotImplementedError):
         ChempropBlock(hidden_dim=16, depth=1, act=torch.nn.Softplus).cuda()(G)
-    with pytest.raises(NotImplementedError):
-        agg.Max()(G)
     with pytest.raises(RuntimeError, match="float32 only"):
         ChempropBlock(hidden_dim=16, depth=1).cuda().double()(G.update(node_feats=G.node_feats.double(), edge_feats=G.edge_feats.double()))
 
@@ -488,3 +486,65 @@ def test_graph_embedding_matches_torch_embedding_bag(d):
     assert list(emb.state_dict()) == ["node.weight", "edge.weight"]
     with pytest.raises(IndexError):
         emb(G.update(node_feats=nv.cuda() + 45))
+
+
+def _mol_graph(x, batch, B, Q=None):
+    from notorch_b200 import BatchedGraph
+
+    E0 = torch.zeros(0, x.shape[1], device="cuda")
+    return BatchedGraph(x, E0, torch.zeros(2, 0, dtype=torch.long, device="cuda"), torch.zeros(0, dtype=torch.long, device="cuda"),
+                        batch_node_index=batch.cuda(), batch_edge_index=torch.zeros(0, dtype=torch.long, device="cuda"), size=B)
+
+
+def test_max_readout_matches_reference_golden():
+    """Row N2: agg.Max (agg.py:41-47) vs the reference's own output, incl. empty molecules and tied maxima (bit-exact)."""
+    import os
+
+    from notorch_b200.nn import Max
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden_readouts", "readout_max.npz"))
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_(True)
+    H = Max()(_mol_graph(x, torch.from_numpy(z["batch_node_index"]), 7))
+    (H * torch.from_numpy(z["gH"]).cuda()).sum().backward()
+    assert torch.equal(H.cpu(), torch.from_numpy(z["H"]))
+    assert torch.equal(x.grad.cpu(), torch.from_numpy(z["g_x"]))
+
+
+@pytest.mark.parametrize("B,d", [(16, 300), (5, 37)])
+def test_gated_and_sdpa_readouts_vs_restatement(B, d):
+    """Row N2: Gated / SDPAttention with their intended semantics (both are broken in the reference, see agg.py docstrings
+    here) vs the builder's fp64 restatement, forward and all gradients."""
+    from notorch_b200.nn import Gated, SDPAttention
+
+    p = oracle_inputs(B, d, 0, seed=31)
+    V, batch = p["V"], p["batch_node_index"]
+    gen = torch.Generator().manual_seed(2)
+    gH, Q = torch.randn(B, d, generator=gen), torch.randn(B, d, generator=gen)
+    x = p["x_v"]
+
+    torch.manual_seed(0)
+    gate = Gated(d)
+    w64, b64 = gate.a.weight.detach().double().requires_grad_(True), gate.a.bias.detach().double().requires_grad_(True)
+    x64 = x.double().requires_grad_(True)
+    ref = O.readout_gated(x64, w64, b64, batch, B)
+    (ref * gH.double()).sum().backward()
+    gate = gate.cuda()
+    xc = x.cuda().requires_grad_(True)
+    H = gate(_mol_graph(xc, batch, B))
+    (H * gH.cuda()).sum().backward()
+    assert_close(H, ref.detach(), "Gated H")
+    assert_close(xc.grad, x64.grad, "Gated grad x")
+    assert_close(gate.a.weight.grad, w64.grad, "Gated grad weight")
+    # softmax is shift invariant: the bias gradient is exactly 0 in exact arithmetic
+    assert float(gate.a.bias.grad.abs().max()) <= 1e-5 * float(w64.grad.abs().max()) and float(b64.grad.abs().max()) < 1e-12
+
+    x64 = x.double().requires_grad_(True)
+    Q64 = Q.double().requires_grad_(True)
+    ref = O.readout_sdpa(x64, Q64, batch, B, d)
+    (ref * gH.double()).sum().backward()
+    xc, Qc = x.cuda().requires_grad_(True), Q.cuda().requires_grad_(True)
+    H = SDPAttention(d)(_mol_graph(xc, batch, B), Q=Qc)
+    (H * gH.cuda()).sum().backward()
+    assert_close(H, ref.detach(), "SDPA H")
+    assert_close(xc.grad, x64.grad, "SDPA grad x")
+    assert_close(Qc.grad, Q64.grad, "SDPA grad Q")

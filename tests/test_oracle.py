@@ -158,3 +158,12 @@ def test_oracle_matches_live_reference_fresh_seed():
     node_out, edge_out, _ = O.block_forward(xv, xe, G0.edge_index, G0.rev_index, Ws, bs)
     assert torch.equal(node_out, G1.node_feats) and torch.equal(edge_out, G1.edge_feats)
     assert torch.equal(O.readout(node_out, G0.batch_node_index, 16, "mean"), ref.Mean()(G1))
+
+
+def test_readout_max_matches_reference_golden():
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden_readouts", "readout_max.npz"))
+    H = O.readout_max(torch.from_numpy(z["x"]), torch.from_numpy(z["batch_node_index"]), 7)
+    assert torch.equal(H, torch.from_numpy(z["H"]))
+    assert (H[2] == 0).all() and (H[5] == 0).all()  # empty molecules give 0 (torch_scatter.scatter_max)
