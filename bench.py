@@ -110,8 +110,9 @@ class ClockSampler:
     def __init__(self, index: int):
         self.rows: list[list[str]] = []
         self.proc = None
+        self.t_start = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -120,7 +121,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            if self.t_start is not None:  # samples before mark_start() (nvidia-smi start-up, warm-up) are not of the timed region
+                self.rows.append([c.strip() for c in line.split(",")])
+
+    def mark_start(self):
+        """nvidia-smi is launched BEFORE the warm-up (its NVML start-up takes the driver lock and would stall the first timed
+        launches); only the samples that arrive after this call are kept."""
+        self.t_start = time.perf_counter()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -285,11 +292,12 @@ def run_ours(args, wl, batch):
             ms = float(tt)
         return ms, last
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step(resident, False)
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
     launches0 = _lib.lib().nt_kernel_launch_count()
     ms_total, _ = timed(args.steps, resident, False)
     launches = _lib.lib().nt_kernel_launch_count() - launches0

@@ -52,6 +52,12 @@ int tc_weight_prepare(const float*, int64_t, int, void*, cudaStream_t);
 int tc_layer_forward(const float*, const float*, const int32_t*, const int32_t*, const void*, const float*, int64_t, int64_t, int, float, int, float,
                      uint64_t, uint64_t, float*, float*, int, cudaStream_t);
 int tc_layer_dgrad(const float*, const void*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
+// gemm_pair.cu (second-generation K2 / K4a: CTA pairs, copy-engine gathers)
+void pair_set_trace_buffer(void* ptr);
+int pair_weight_prepare(const float*, int64_t, int, void*, cudaStream_t);
+int pair_layer_forward(const float*, const float*, const int32_t*, const int32_t*, const void*, const float*, int64_t, int64_t, int64_t, int, float, int,
+                       float, uint64_t, uint64_t, float*, float*, int, cudaStream_t);
+int pair_layer_dgrad(const float*, const void*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
 // wgrad_tma.cu
 size_t tma_wgrad_workspace_bytes(int64_t E, int64_t d);
 int tma_layer_wgrad(const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, float*, void*, size_t, int, cudaStream_t);
@@ -60,6 +66,19 @@ int tc_bias_grad(const float*, int64_t, int64_t, float, uint64_t, uint64_t, floa
 size_t tc_wgrad_workspace_bytes(int64_t E, int64_t d);
 int tc_layer_wgrad(const float*, const float*, const float*, const int32_t*, const int32_t*, int64_t, int64_t, int, float, float, uint64_t, uint64_t,
                    float*, float*, void*, size_t, int, cudaStream_t);
+
+// NOTORCH_B200_GEMM_V1=1 selects the first-generation single-CTA kernels of gemm_tc.cu (A/B timing only; the weight
+// image layouts differ, so the switch is process-wide and read once).
+static bool use_pair_kernels() {
+  static const bool v1 = getenv("NOTORCH_B200_GEMM_V1") != nullptr && atoi(getenv("NOTORCH_B200_GEMM_V1")) != 0;
+  return !v1;
+}
+
+// NOTORCH_B200_PAIR_DGRAD=1 routes K4a through gemm_pair.cu as well (timing experiments)
+static bool pair_dgrad_enabled() {
+  static const bool on = getenv("NOTORCH_B200_PAIR_DGRAD") != nullptr && atoi(getenv("NOTORCH_B200_PAIR_DGRAD")) != 0;
+  return on && use_pair_kernels();
+}
 
 static bool tc_shape_ok(int64_t d, const void* a, const void* b, const void* c, const void* e) {
   return d % 4 == 0 && d >= 4 && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(e);
@@ -73,7 +92,10 @@ extern "C" const char* nt_last_error_string(void) { return g_err; }
 extern "C" int nt_version(void) { return 100; }
 extern "C" long long nt_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-extern "C" void nt_debug_set_trace_buffer(void* device_u64_buffer) { tc_set_trace_buffer(device_u64_buffer); }
+extern "C" void nt_debug_set_trace_buffer(void* device_u64_buffer) {
+  tc_set_trace_buffer(device_u64_buffer);
+  pair_set_trace_buffer(device_u64_buffer);
+}
 
 extern "C" int nt_device_supported(void) {
   int dev = 0;
@@ -95,6 +117,8 @@ extern "C" int nt_weight_prepare(const void* W, int64_t d, int transpose, void* 
   if (dtype != NT_F32) { set_error("nt_weight_prepare: only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
   NT_CHECK_ARG(W && image && d > 0 && d < (1 << 20), "nt_weight_prepare: bad arguments");
   if (!aligned16(image)) { set_error("nt_weight_prepare: image must be 16-byte aligned"); return NT_ERR_ALIGN; }
+  // forward image (transpose = 0): CTA-pair layout of gemm_pair.cu; dgrad image (transpose = 1): single-CTA layout of gemm_tc.cu
+  if (use_pair_kernels() && (!transpose || pair_dgrad_enabled())) return pair_weight_prepare(static_cast<const float*>(W), d, transpose != 0, image, as_stream(stream));
   return tc_weight_prepare(static_cast<const float*>(W), d, transpose != 0, image, as_stream(stream));
 }
 
@@ -109,6 +133,10 @@ extern "C" int nt_layer_forward(const void* h, const void* n, const int32_t* src
   cudaStream_t st = as_stream(stream);
   if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, h, n, out, bias) && aligned16(m_out)) {
     NT_CHECK_ARG(weight_image, "nt_layer_forward: tensor-core path needs weight_image (nt_weight_prepare)");
+    if (use_pair_kernels())
+      return pair_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, weight_image, static_cast<const float*>(bias), E,
+                                V, d, act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), static_cast<float*>(m_out),
+                                gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
     return tc_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, weight_image, static_cast<const float*>(bias), E, d,
                             act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), static_cast<float*>(m_out),
                             gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
@@ -126,6 +154,11 @@ extern "C" int nt_layer_backward_dgrad(const void* g, const void* W, const void*
   cudaStream_t st = as_stream(stream);
   if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, g, g_m, nullptr, nullptr)) {
     NT_CHECK_ARG(weight_image, "nt_layer_backward_dgrad: tensor-core path needs weight_image (nt_weight_prepare, transpose=1)");
+    // K4a stays on the single-CTA kernel: measured 205 us vs 243 us for the pair kernel at BASELINE configs[1] (its A operand
+    // is a dense tile, so the pair kernel's cp.async producers buy nothing there)
+    if (pair_dgrad_enabled())
+      return pair_layer_dgrad(static_cast<const float*>(g), weight_image, E, d, dropout_p, seed, offset, static_cast<float*>(g_m),
+                              gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
     return tc_layer_dgrad(static_cast<const float*>(g), weight_image, E, d, dropout_p, seed, offset, static_cast<float*>(g_m),
                           gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
   }
