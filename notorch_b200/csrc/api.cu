@@ -1,5 +1,6 @@
 // extern "C" entry points that dispatch between the arithmetic paths, plus error plumbing.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <string.h>
@@ -74,10 +75,10 @@ static bool use_pair_kernels() {
   return !v1;
 }
 
-// NOTORCH_B200_PAIR_DGRAD=1 routes K4a through gemm_pair.cu as well (timing experiments)
+// NOTORCH_B200_PAIR_DGRAD=0 routes K4a through the single-CTA kernel of gemm_tc.cu (timing experiments)
 static bool pair_dgrad_enabled() {
-  static const bool on = getenv("NOTORCH_B200_PAIR_DGRAD") != nullptr && atoi(getenv("NOTORCH_B200_PAIR_DGRAD")) != 0;
-  return on && use_pair_kernels();
+  static const bool off = getenv("NOTORCH_B200_PAIR_DGRAD") != nullptr && atoi(getenv("NOTORCH_B200_PAIR_DGRAD")) == 0;
+  return !off && use_pair_kernels();
 }
 
 static bool tc_shape_ok(int64_t d, const void* a, const void* b, const void* c, const void* e) {
@@ -154,8 +155,6 @@ extern "C" int nt_layer_backward_dgrad(const void* g, const void* W, const void*
   cudaStream_t st = as_stream(stream);
   if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, g, g_m, nullptr, nullptr)) {
     NT_CHECK_ARG(weight_image, "nt_layer_backward_dgrad: tensor-core path needs weight_image (nt_weight_prepare, transpose=1)");
-    // K4a stays on the single-CTA kernel: measured 205 us vs 243 us for the pair kernel at BASELINE configs[1] (its A operand
-    // is a dense tile, so the pair kernel's cp.async producers buy nothing there)
     if (pair_dgrad_enabled())
       return pair_layer_dgrad(static_cast<const float*>(g), weight_image, E, d, dropout_p, seed, offset, static_cast<float*>(g_m),
                               gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);

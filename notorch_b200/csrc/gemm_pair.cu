@@ -107,26 +107,9 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t cta_addr, uint32_t rank)
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("notorch_b200: cluster mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
+  // default semantics (.release.cta) as in CUTLASS ClusterBarrier::arrive(cta_id): the .release.cluster form compiles to
+  // MEMBAR + ERRBAR and its .acquire.cluster counterpart to CCTL.IVALL (an L1 flush per wait) - ncu showed both as top stalls
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
@@ -153,18 +136,26 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_pair(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
+// The kernel is specialised at compile time on (dropout on/off, ReLU vs. the generic activation switch): with the six-way
+// switch (expf / erff / tanhf per element) and Philox inlined into every unrolled unit the hot loops were ~75 KB of SASS and
+// ncu showed the instruction cache as a bottleneck (gcc__cache_requests_type_instruction at 73 % of peak, 12 % of warp
+// samples stalled on no_instructions).
 // Debug trace (CTA 0 only): regions 0 = epilogue thread 0, 1 = MMA issuer, 2 = transform thread 0, 3 = copy-engine warp lane 0.
-__device__ __forceinline__ void trace_event(const Params& p, int region, uint32_t& cursor, int ev, int64_t tile, int aux = 0) {
-  if (p.trace != nullptr && blockIdx.x == 0 && cursor < 16000u) {
+template <bool TRACE>
+__device__ __forceinline__ void trace_event_t(const Params& p, int region, uint32_t& cursor, int ev, int64_t tile, int aux = 0) {
+  if (TRACE && p.trace != nullptr && blockIdx.x == 0 && cursor < 16000u) {
     p.trace[1 + region * 16000 + cursor] = ((unsigned long long)ev << 56) | ((unsigned long long)(tile & 0xFFFF) << 40) |
                                              ((unsigned long long)(aux & 0xFF) << 32) | (unsigned long long)(clock64() & 0xFFFFFFFFull);
     ++cursor;
   }
 }
 
-template <int MODE>  // 0 = K2 forward, 1 = K4a dgrad
+template <int MODE, bool DROP, bool RELU, bool TRACE>  // MODE 0 = K2 forward, 1 = K4a dgrad; TRACE = the role-timeline build (scripts/trace_pair.py)
 __global__ void __launch_bounds__(THREADS, 1)
 layer_gemm_pair(const Params p) {
+  auto trace_event = [](const Params& pp, int region, uint32_t& cursor, int ev, int64_t tile, int aux = 0) {
+    trace_event_t<TRACE>(pp, region, cursor, ev, tile, aux);
+  };
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -271,7 +262,7 @@ layer_gemm_pair(const Params p) {
                 float4 acc = *reinterpret_cast<const float4*>(stage + r * 64 + ((sub ^ ((r >> 1) & 3)) << 4));
                 if (MODE == 0) {
                   acc = make_float4(acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w);
-                  if (p.drop_p > 0.f) {
+                  if (DROP) {
                     float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)col, p.drop_thr, p.inv_keep);
                     acc = make_float4(acc.x * sc.x, acc.y * sc.y, acc.z * sc.z, acc.w * sc.w);
                   }
@@ -306,11 +297,12 @@ layer_gemm_pair(const Params p) {
         for (int nt = 0; nt < geo.n_tiles; ++nt) {
           const uint32_t col_base = tw ? (uint32_t)(512 - geo.n_tile) : 0u;
           if (lane == 0) trace_event(p, 1, tcur, 10, tile);
-          mbar_wait_cluster(bar_tmem_empty, tphase ^ 1);
+          mbar_wait(bar_tmem_empty, tphase ^ 1);
           tc_fence_after();
           if (lane == 0) trace_event(p, 1, tcur, 11, tile);
+#pragma unroll 1
           for (int kb = 0; kb < geo.k_blocks; ++kb) {
-            mbar_wait_cluster(bar_ready + 8 * s, ph);
+            mbar_wait(bar_ready + 8 * s, ph);
             tc_fence_after();
             if (lane == 0) trace_event(p, 1, tcur, 12, tile, kb);
             if (elect_one()) {
@@ -361,12 +353,10 @@ layer_gemm_pair(const Params p) {
     const bool need_lo = p.products == 3;
     for (int64_t tile = first_tile; tile < pair_tiles; tile += tile_stride) {
       const int64_t e0 = tile * (2 * TILE_M) + rank * TILE_M;
-      if (MODE == 0 && p.resid != nullptr && e0 < p.E && elect_one()) {  // the epilogue of this tile adds h[tile rows, :]
-        const int64_t rows = p.E - e0 < TILE_M ? p.E - e0 : TILE_M;
-        l2_prefetch_bulk(p.resid + e0 * d, (uint32_t)(rows * d * 4));
-      }
       __syncwarp();
+#pragma unroll 1
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
+#pragma unroll 1
         for (int kb = 0; kb < geo.k_blocks; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           if (elect_one()) {
@@ -438,15 +428,6 @@ layer_gemm_pair(const Params p) {
       if (q.tile < pair_tiles) {
         mbar_wait(bar_empty + 8 * q.s, q.ph ^ 1);
         if (!(p.ablate & 2)) issue_loads(q);
-        if (q.nt == 0 && q.kb == 1) {
-          // warm L2 with the NEXT tile's rows: the eight threads that share four rows take one (row, operand) pair each
-          const int i = (pt & 3), which = (pt >> 2) & 1;
-          int row = -1;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k == i) row = which == 0 ? na[k] : nb[k];
-          if (row >= 0) l2_prefetch_bulk((which == 0 ? a0g : a1g) + (int64_t)row * d, (uint32_t)(d * 4));
-        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       const int64_t before = q.tile;
@@ -488,10 +469,12 @@ layer_gemm_pair(const Params p) {
           const int64_t e = e0 + r0 + 32 * i;
           float4 m = raw0[i];
           if (MODE == 0) {
-            const float4 a = act_fwd4(raw1[i], p.act, p.act_param);
+            float4 a;
+            if (RELU) a = make_float4(raw1[i].x < 0.f ? 0.f : raw1[i].x, raw1[i].y < 0.f ? 0.f : raw1[i].y, raw1[i].z < 0.f ? 0.f : raw1[i].z, raw1[i].w < 0.f ? 0.f : raw1[i].w);
+            else a = act_fwd4(raw1[i], p.act, p.act_param);
             m = make_float4(m.x - a.x, m.y - a.y, m.z - a.z, m.w - a.w);
             if (col >= d || e >= p.E) m = make_float4(0.f, 0.f, 0.f, 0.f);
-          } else if (p.drop_p > 0.f && e < p.E && col < d) {
+          } else if (DROP && e < p.E && col < d) {
             const float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)col, p.drop_thr, p.inv_keep);
             m = make_float4(m.x * sc.x, m.y * sc.y, m.z * sc.z, m.w * sc.w);
           }
@@ -560,12 +543,12 @@ __global__ void __launch_bounds__(256) pair_weight_prepare_kernel(const float* _
   *reinterpret_cast<float*>(image + geo.part_bytes + off) = lo;
 }
 
-template <int MODE>
-static int launch(const Params& p, cudaStream_t st) {
+template <int MODE, bool DROP, bool RELU, bool TRACE>
+static int launch_variant(const Params& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(layer_gemm_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(layer_gemm_pair<MODE, DROP, RELU, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(layer_gemm_pair)");
   const int64_t pair_tiles = (p.E + 2 * TILE_M - 1) / (2 * TILE_M);
@@ -585,10 +568,20 @@ static int launch(const Params& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, layer_gemm_pair<MODE>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, layer_gemm_pair<MODE, DROP, RELU, TRACE>, p);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(layer_gemm_pair)");
   NT_LAUNCH_CHECK("layer_gemm_pair", 1);
   return NT_OK;
+}
+
+template <int MODE>
+static int launch(const Params& p, cudaStream_t st) {
+  const bool drop = p.drop_p > 0.f;
+  const bool relu = MODE == 1 || p.act == NT_ACT_RELU;  // K4a has no activation
+  if (p.trace != nullptr && !drop && relu) return launch_variant<MODE, false, true, true>(p, st);  // the role-timeline build exists for the default case only
+  if (MODE == 1) return drop ? launch_variant<MODE, true, true, false>(p, st) : launch_variant<MODE, false, true, false>(p, st);
+  if (drop) return relu ? launch_variant<MODE, true, true, false>(p, st) : launch_variant<MODE, true, false, false>(p, st);
+  return relu ? launch_variant<MODE, false, true, false>(p, st) : launch_variant<MODE, false, false, false>(p, st);
 }
 
 unsigned long long* g_trace_buffer = nullptr;

@@ -35,9 +35,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU. The spin loop lives out of line so
+// that the dozens of wait sites in the warp-specialised kernels do not each carry the clock / printf / trap code (the hot
+// loops have to fit the instruction cache).
+static __device__ __noinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
@@ -45,6 +46,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_spin(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
