@@ -50,7 +50,9 @@ constexpr int THREADS = (FIRST_X_WARP + NUM_X_WARPS) * 32;  // 448
 
 constexpr int OFF_A0 = 0, OFF_A1 = A_PART_BYTES, OFF_WHI = 2 * A_PART_BYTES, OFF_WLO = OFF_WHI + W_PART_BYTES;  // inside a stage
 constexpr int OFF_EPI = STAGES * STAGE_BYTES;
-constexpr int OFF_BAR = OFF_EPI + NUM_EPI_WARPS * EPI_WARP_BYTES;
+constexpr int BIAS_WARP_BYTES = 1280;                       // per-epilogue-warp copy of the bias of the current N tile (<= 304 floats)
+constexpr int OFF_BIAS = OFF_EPI + NUM_EPI_WARPS * EPI_WARP_BYTES;
+constexpr int OFF_BAR = OFF_BIAS + NUM_EPI_WARPS * BIAS_WARP_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 static_assert(STAGE_BYTES % 1024 == 0 && W_PART_BYTES % 1024 == 0, "swizzle-128B tiles need 1 KiB alignment");
@@ -175,8 +177,10 @@ layer_gemm_pair(const Params p) {
 
   const Geometry& geo = p.geo;
   const int d = geo.d;
-  const int64_t pair_tiles = (p.E + 2 * TILE_M - 1) / (2 * TILE_M);
-  const int64_t first_tile = blockIdx.x >> 1, tile_stride = gridDim.x >> 1;
+  // tile bookkeeping is 32-bit and re-derived inside every role (blockIdx / gridDim / kernel parameters are free to read):
+  // values computed here would stay live across the whole role dispatch and were spilled to local memory
+#define NT_PAIR_TILE_VARS \
+  const int pair_tiles = (int)((p.E + 2 * TILE_M - 1) / (2 * TILE_M)), first_tile = (int)(blockIdx.x >> 1), tile_stride = (int)(gridDim.x >> 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -201,6 +205,7 @@ layer_gemm_pair(const Params p) {
 
   if (warp < NUM_EPI_WARPS) {
     // ===================================== EPILOGUE =====================================
+    NT_PAIR_TILE_VARS;
     uint8_t* stage = smem + OFF_EPI + warp * EPI_WARP_BYTES;
     const uint32_t tmem_empty_leader = map_to_cta(bar_tmem_empty, 0);
     uint32_t tphase = 0;
@@ -209,9 +214,20 @@ layer_gemm_pair(const Params p) {
     const bool has_resid = MODE == 0 && p.resid != nullptr;
     const int shared_chunks = 2 * geo.n_tile > 512 ? (2 * geo.n_tile - 512) / EPI_COLS : 0;
     int tw = 0;
-    for (int64_t tile = first_tile; tile < pair_tiles; tile += tile_stride) {
-      const int64_t row0 = tile * (2 * TILE_M) + rank * TILE_M + warp * 32;
+    float4* bias_s = reinterpret_cast<float4*>(smem + OFF_BIAS + warp * BIAS_WARP_BYTES);
+    int bias_nt = -1;
+    for (int tile = first_tile; tile < pair_tiles; tile += tile_stride) {
+      const int64_t row0 = (int64_t)tile * (2 * TILE_M) + rank * TILE_M + warp * 32;
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
+        if (MODE == 0 && bias_nt != nt) {  // (re)stage this N tile's bias: once per kernel when d <= 304 (per-chunk global reads cost 18 us)
+          __syncwarp();
+          for (int i = lane; i < geo.n_tile / 4; i += 32) {
+            const int col = nt * geo.n_tile + 4 * i;
+            bias_s[i] = (p.bias != nullptr && col < d) ? ldg4(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          __syncwarp();
+          bias_nt = nt;
+        }
         auto load_resid = [&](int cc, float4 (&dst)[4]) {
           const int col = nt * geo.n_tile + cc * EPI_COLS + sub * 4;
 #pragma unroll
@@ -253,7 +269,7 @@ layer_gemm_pair(const Params p) {
           const int col = nt * geo.n_tile + cc * EPI_COLS + sub * 4;
           if (col < d) {
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (MODE == 0 && p.bias) bias4 = ldg4(p.bias + col);
+            if (MODE == 0) bias4 = bias_s[cc * (EPI_COLS / 4) + sub];
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int r = it * 8 + rsub;
@@ -289,11 +305,12 @@ layer_gemm_pair(const Params p) {
   } else if (warp == MMA_WARP) {
     // ===================================== MMA ISSUER (leader CTA only) =====================================
     if (leader) {
+      NT_PAIR_TILE_VARS;
       const uint32_t idesc_a = make_idesc_pair(geo.n_a);
       const uint32_t idesc_b = make_idesc_pair(geo.n_b > 0 ? geo.n_b : 16);
       int s = 0, tw = 0;
       uint32_t ph = 0, tphase = 0;
-      for (int64_t tile = first_tile; tile < pair_tiles; tile += tile_stride) {
+      for (int tile = first_tile; tile < pair_tiles; tile += tile_stride) {
         for (int nt = 0; nt < geo.n_tiles; ++nt) {
           const uint32_t col_base = tw ? (uint32_t)(512 - geo.n_tile) : 0u;
           if (lane == 0) trace_event(p, 1, tcur, 10, tile);
@@ -347,12 +364,12 @@ layer_gemm_pair(const Params p) {
     }
   } else if (warp == TMA_WARP) {
     // ===================================== W PRODUCER (bulk copies of this CTA's half of the weight tile) =====================================
+    NT_PAIR_TILE_VARS;
     int s = 0;
     uint32_t ph = 0;
     const uint32_t w_bytes = (uint32_t)geo.rows_per_cta * 128u;
     const bool need_lo = p.products == 3;
-    for (int64_t tile = first_tile; tile < pair_tiles; tile += tile_stride) {
-      const int64_t e0 = tile * (2 * TILE_M) + rank * TILE_M;
+    for (int tile = first_tile; tile < pair_tiles; tile += tile_stride) {
       __syncwarp();
 #pragma unroll 1
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
@@ -387,23 +404,28 @@ layer_gemm_pair(const Params p) {
     const float* __restrict__ a0g = p.a0;
     const float* __restrict__ a1g = p.a1;
 
-    struct Cursor { int64_t tile; int nt, kb, s; uint32_t ph; };
+    // 32-bit bookkeeping throughout (E < 2^31): with 64-bit tile counters the two cursors were spilled to local memory and
+    // ncu showed the reloads as ~15 % of all stall samples
+    NT_PAIR_TILE_VARS;
+    const int n_tiles_i = pair_tiles, first_i = first_tile, stride_i = tile_stride;
+    const int E_i = (int)p.E;
+    struct Cursor { int tile, nt, kb, s; uint32_t ph; };
     auto advance = [&](Cursor& q) {
-      if (++q.kb == geo.k_blocks) { q.kb = 0; if (++q.nt == geo.n_tiles) { q.nt = 0; q.tile += tile_stride; } }
+      if (++q.kb == geo.k_blocks) { q.kb = 0; if (++q.nt == geo.n_tiles) { q.nt = 0; q.tile += stride_i; } }
       if (++q.s == STAGES) { q.s = 0; q.ph ^= 1; }
     };
     // row indices (-1 = row past E) of this thread's four rows, for the tile the load cursor is in and for the one after it
     int ra[4], rb[4], na[4], nb[4];
-    auto fetch_rows = [&](int64_t t, int (&xa)[4], int (&xb)[4]) {
+    auto fetch_rows = [&](int t, int (&xa)[4], int (&xb)[4]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int64_t e = t * (2 * TILE_M) + rank * TILE_M + r0 + 32 * i;
-        const bool ok = t < pair_tiles && e < p.E;
+        const int e = t * (2 * TILE_M) + (int)rank * TILE_M + r0 + 32 * i;
+        const bool ok = t < n_tiles_i && e < E_i;
         if (MODE == 0) {
           xa[i] = ok ? __ldg(p.src + e) : -1;
           xb[i] = ok ? __ldg(p.rev + e) : -1;
         } else {
-          xa[i] = ok ? (int)e : -1;
+          xa[i] = ok ? e : -1;
           xb[i] = -1;
         }
       }
@@ -411,7 +433,7 @@ layer_gemm_pair(const Params p) {
     auto issue_loads = [&](const Cursor& q) {
       const int k0 = q.kb * BLOCK_K + c * 4;
       const bool kvalid = k0 < d;
-      const uint32_t dst0 = sbase + q.s * STAGE_BYTES + OFF_A0 + pt * 16, dst1 = sbase + q.s * STAGE_BYTES + OFF_A1 + pt * 16;
+      const uint32_t dst0 = sbase + q.s * STAGE_BYTES + OFF_A0 + pt * 16, dst1 = dst0 + (OFF_A1 - OFF_A0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const bool ok = kvalid && ra[i] >= 0;
@@ -425,30 +447,30 @@ layer_gemm_pair(const Params p) {
       }
     };
     auto load_step = [&](Cursor& q) {  // refill the stage the load cursor points at (once its previous MMAs have retired), then advance
-      if (q.tile < pair_tiles) {
+      if (q.tile < n_tiles_i) {
         mbar_wait(bar_empty + 8 * q.s, q.ph ^ 1);
         if (!(p.ablate & 2)) issue_loads(q);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      const int64_t before = q.tile;
+      const int before = q.tile;
       advance(q);
       if (q.tile != before) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) { ra[i] = na[i]; rb[i] = nb[i]; }
-        fetch_rows(q.tile + tile_stride, na, nb);
+        fetch_rows(q.tile + stride_i, na, nb);
       }
     };
 
-    Cursor ld{first_tile, 0, 0, 0, 0}, cp{first_tile, 0, 0, 0, 0};
-    fetch_rows(first_tile, ra, rb);
-    fetch_rows(first_tile + tile_stride, na, nb);
+    Cursor ld{first_i, 0, 0, 0, 0}, cp{first_i, 0, 0, 0, 0};
+    fetch_rows(first_i, ra, rb);
+    fetch_rows(first_i + stride_i, na, nb);
 #pragma unroll 1
     for (int j = 0; j < STAGES - 1; ++j) load_step(ld);
 #pragma unroll 1
-    while (cp.tile < pair_tiles) {
-      const int64_t e0 = cp.tile * (2 * TILE_M) + rank * TILE_M;
+    while (cp.tile < n_tiles_i) {
+      const int e0 = cp.tile * (2 * TILE_M) + (int)rank * TILE_M;
       uint8_t* a0 = smem + cp.s * STAGE_BYTES + OFF_A0;
-      uint8_t* a1 = smem + cp.s * STAGE_BYTES + OFF_A1;
+      uint8_t* a1 = a0 + (OFF_A1 - OFF_A0);
       if (pt == 0) trace_event(p, 2, tcur, 20, cp.tile, cp.kb);
       asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
       if (pt == 0) trace_event(p, 2, tcur, 21, cp.tile, cp.kb);
@@ -466,15 +488,15 @@ layer_gemm_pair(const Params p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int u = pt + i * NUM_X_THREADS;
-          const int64_t e = e0 + r0 + 32 * i;
+          const int e = e0 + r0 + 32 * i;
           float4 m = raw0[i];
           if (MODE == 0) {
             float4 a;
             if (RELU) a = make_float4(raw1[i].x < 0.f ? 0.f : raw1[i].x, raw1[i].y < 0.f ? 0.f : raw1[i].y, raw1[i].z < 0.f ? 0.f : raw1[i].z, raw1[i].w < 0.f ? 0.f : raw1[i].w);
             else a = act_fwd4(raw1[i], p.act, p.act_param);
             m = make_float4(m.x - a.x, m.y - a.y, m.z - a.z, m.w - a.w);
-            if (col >= d || e >= p.E) m = make_float4(0.f, 0.f, 0.f, 0.f);
-          } else if (DROP && e < p.E && col < d) {
+            if (col >= d || e >= E_i) m = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (DROP && e < E_i && col < d) {
             const float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)col, p.drop_thr, p.inv_keep);
             m = make_float4(m.x * sc.x, m.y * sc.y, m.z * sc.z, m.w * sc.w);
           }
@@ -487,8 +509,8 @@ layer_gemm_pair(const Params p) {
         if (MODE == 0 && p.m_out != nullptr && cp.nt == 0 && col < d && !(p.ablate & 32)) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int64_t e = e0 + r0 + 32 * i;
-            if (e < p.E) stg4_stream(p.m_out + e * d + col, raw0[i]);
+            const int e = e0 + r0 + 32 * i;
+            if (e < E_i) stg4_stream(p.m_out + (int64_t)e * d + col, raw0[i]);
           }
         }
       }
