@@ -1,20 +1,23 @@
-// K4b — weight gradient on tcgen05 with BOTH operands streamed by TMA (the fast path).
+// K4b — weight gradient on tcgen05 with BOTH operands streamed as dense tiles (the fast path).
 //
 //   gW^T[i, o] = sum_e m[e, i] * g_u[e, o]        (D = A^T-free: A = m, B = g_u, both MN-major TF32)
 //
 // m [E, d] is the message tensor K2 forward already produced (n[src] - act(h[rev])) and wrote out as a
-// side output, g [E, d] the incoming gradient: two dense row-major tensors, so each 16-edge K-block is a
-// handful of 2-D TMA boxes (32 features x 16 edges, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B — the one
-// shared-memory layout tcgen05 accepts for MN-major TF32). Out-of-range rows / columns are zero-filled by
-// the copy engine, so there is no tail code.
+// side output, g [E, d] the incoming gradient: two dense row-major tensors, so each 16-edge K-block is
+// 14 chunks of 32 features x 16 edges in the SWIZZLE_128B_BASE32B layout (the one shared-memory layout
+// tcgen05 accepts for MN-major TF32).
 //
-// Pipeline per CTA (4 stages): TMA warp -> raw fp32 tiles in smem -> 8 transform warps split every value
-// into TF32 hi / lo parts in place (same offsets: no layout math, no bank conflicts) -> MMA warp issues
-// lo.hi + hi.lo + hi.hi -> after the CTA's last K-block the 4 epilogue warps drain TMEM to a partial
-// buffer. Edge ranges are reduced afterwards in a fixed order (deterministic split-K). The bias gradient
-// rides along as an all-ones feature row of m when d % 128 != 0.
-#include <cuda.h>
-
+// Pipeline per CTA (4 stages): the eight producer warps copy "their" 16-byte units of the next K-blocks
+// straight from global memory into that layout with cp.async (LDGSTS, zero-filled outside [E, d]) and,
+// once a K-block has landed (cp.async.wait_group: a thread only ever touches its own units, so no barrier
+// is needed), split every value into TF32 hi / lo parts in place -> MMA warp issues lo.hi + hi.lo + hi.hi
+// -> after the CTA's last K-block the 4 epilogue warps drain TMEM to a partial buffer. Edge ranges are
+// reduced afterwards in a fixed order (deterministic split-K). The bias gradient rides along as an
+// all-ones feature row of m when d % 128 != 0.
+//
+// The first version streamed the tiles with cp.async.bulk.tensor (TMA): the copy engine sustains only
+// ~6.5 clk per 128-byte box row (scripts/probes/probe_tma_bw.cu: 19.6 B/clk/SM), i.e. ~1450 clk per
+// K-block of 224 rows against ~960 clk of MMA work, so the kernel was copy-engine bound (312 us).
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -32,12 +35,11 @@ constexpr int A_CHUNKS = TILE_M / 32;        // 4
 constexpr int B_CHUNKS_MAX = MAX_N / 32;     // 10
 constexpr int PART_BYTES = (A_CHUNKS + B_CHUNKS_MAX) * CHUNK_BYTES;  // 28 KiB (hi or lo)
 constexpr int STAGE_BYTES = 2 * PART_BYTES;                          // 56 KiB
-constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, TMA_WARP = 5, FIRST_X_WARP = 6, NUM_X_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, FIRST_X_WARP = 6, NUM_X_WARPS = 8;  // warp 5 is idle (it used to drive the copy engine)
 constexpr int NUM_X_THREADS = NUM_X_WARPS * 32;
 constexpr int THREADS = (FIRST_X_WARP + NUM_X_WARPS) * 32;  // 448
 constexpr int OFF_BAR = STAGES * STAGE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
-constexpr int PREFETCH_BLOCKS = 12;          // L2 prefetch distance of the TMA warp, in K-blocks
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 
 struct Geometry {
@@ -67,6 +69,8 @@ static Geometry make_geometry(int64_t E, int d, int sms) {
 }
 
 struct Params {
+  const float* m;  // [E, d]
+  const float* g;  // [E, d]
   float* partial;  // [splits][m_blocks*128 (i)][ld_partial (o)]
   int64_t E;
   Geometry geo;
@@ -76,16 +80,8 @@ struct Params {
   int products;
 };
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
-
-__global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_m, const __grid_constant__ CUtensorMap tmap_g,
-                                                                const Params p) {
+template <bool DROP>
+__global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -93,12 +89,11 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
     if (threadIdx.x == 0) printf("notorch_b200: dynamic shared memory base is not 1 KiB aligned\n");
     __trap();
   }
-  const uint32_t bar_raw = sbase + OFF_BAR;           // [STAGES] TMA bytes landed
-  const uint32_t bar_ready = bar_raw + 8 * STAGES;    // [STAGES] hi/lo split done
+  const uint32_t bar_ready = sbase + OFF_BAR;         // [STAGES] hi/lo split done
   const uint32_t bar_empty = bar_ready + 8 * STAGES;  // [STAGES] MMAs retired
   const uint32_t bar_tmem_full = bar_empty + 8 * STAGES;
   const uint32_t tmem_slot = bar_tmem_full + 8;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (3 * STAGES + 1));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * STAGES + 1));
 
   const Geometry& geo = p.geo;
   const int d = geo.d;
@@ -115,7 +110,6 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_raw + 8 * s, 1);
       mbar_init(bar_ready + 8 * s, NUM_X_WARPS);
       mbar_init(bar_empty + 8 * s, 1);
     }
@@ -188,68 +182,91 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const __grid_cons
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
-  } else if (warp == TMA_WARP) {
-    // ===================================== TMA PRODUCER =====================================
-    if (elect_one()) {
-      int s = 0;
-      uint32_t ph = 0;
-      const uint32_t bytes = (uint32_t)(A_CHUNKS + b_chunks) * CHUNK_BYTES;
-      for (int64_t kb = 0; kb < nkb; ++kb) {
-        const int e0 = (int)((kb_lo + kb) * BLOCK_E);
-        if (kb + PREFETCH_BLOCKS < nkb) {  // warm L2 well ahead of the smem ring
-          const int ep = e0 + PREFETCH_BLOCKS * BLOCK_E;
-          for (int c = 0; c < A_CHUNKS; ++c)
-            if (i0 + 32 * c < d) tma_prefetch_2d(&tmap_m, i0 + 32 * c, ep);
-          for (int c = 0; c < b_chunks; ++c)
-            if (o0 + 32 * c < d) tma_prefetch_2d(&tmap_g, o0 + 32 * c, ep);
-        }
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const uint32_t st = sbase + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(bar_raw + 8 * s, bytes);
-        for (int c = 0; c < A_CHUNKS; ++c) tma_load_2d(st + c * CHUNK_BYTES, &tmap_m, i0 + 32 * c, e0, bar_raw + 8 * s);
-        for (int c = 0; c < b_chunks; ++c) tma_load_2d(st + (A_CHUNKS + c) * CHUNK_BYTES, &tmap_g, o0 + 32 * c, e0, bar_raw + 8 * s);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-      }
-    }
-  } else {
-    // ===================================== TRANSFORM (hi / lo split in place) =====================================
+  } else if (warp >= FIRST_X_WARP) {
+    // ===================================== PRODUCER: cp.async tiles, then hi / lo split in place =====================================
+    // Thread pt owns the 16-byte units u = pt + 256 k of every stage: chunk u >> 7 (32 features), edge row (u & 127) >> 3,
+    // physical slot u & 7 (the 32-byte-unit XOR swizzle undone to find the feature). It copies those units itself and later
+    // rewrites the same bytes, so cp.async.wait_group is the only synchronisation the raw data needs.
     const int pt = threadIdx.x - FIRST_X_WARP * 32;  // 0..255
+    constexpr int MAX_UNITS = (A_CHUNKS + B_CHUNKS_MAX) * (CHUNK_BYTES / 16) / NUM_X_THREADS;  // 7
     const int units16 = (A_CHUNKS + b_chunks) * (CHUNK_BYTES / 16);
+    const int r = (pt & 127) >> 3, pos = pt & 7;                       // identical for all of this thread's units (256 = 2 chunks apart)
+    const int c16 = ((((pos >> 1) ^ (r & 3)) << 1) | (pos & 1));       // logical 16-byte chunk inside the 128-byte feature row
+    const int E_i = (int)p.E;
     // the all-ones feature row of m (bias gradient) lives in this CTA's A tile iff i0 <= d < i0 + 128
     const bool ones_here = geo.ones_row && d >= i0 && d < i0 + TILE_M;
     const int ones_chunk = ones_here ? (d - i0) / 32 : -1, ones_c16 = ones_here ? ((d - i0) % 32) / 4 : -1;
-    int s = 0;
-    uint32_t ph = 0;
+
+    auto feature_of = [&](int chunk) { return chunk < A_CHUNKS ? i0 + 32 * chunk + 4 * c16 : o0 + 32 * (chunk - A_CHUNKS) + 4 * c16; };
+    auto issue = [&](int64_t kb, int s) {
+      const int e = (int)((kb_lo + kb) * BLOCK_E) + r;
+      const uint32_t dst = sbase + s * STAGE_BYTES + pt * 16;
+#pragma unroll
+      for (int k = 0; k < MAX_UNITS; ++k) {
+        const int u = pt + k * NUM_X_THREADS;
+        if (u < units16) {
+          const int chunk = u >> 7;
+          const int f = feature_of(chunk);
+          const bool ok = e < E_i && f < d;
+          const float* src = (chunk < A_CHUNKS ? p.m : p.g) + (ok ? (int64_t)e * d + f : 0);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + k * (NUM_X_THREADS * 16)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+      }
+    };
+    int ls = 0, cs = 0;
+    uint32_t lph = 0, cph = 0;
+    int64_t lkb = 0;
+    auto load_step = [&]() {
+      if (lkb < nkb) {
+        mbar_wait(bar_empty + 8 * ls, lph ^ 1);
+        issue(lkb, ls);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      ++lkb;
+      if (++ls == STAGES) { ls = 0; lph ^= 1; }
+    };
+#pragma unroll 1
+    for (int j = 0; j < STAGES - 1; ++j) load_step();
+#pragma unroll 1
     for (int64_t kb = 0; kb < nkb; ++kb) {
-      const int64_t e0 = (kb_lo + kb) * BLOCK_E;
-      uint8_t* hi = smem + s * STAGE_BYTES;
+      const int e = (int)((kb_lo + kb) * BLOCK_E) + r;
+      uint8_t* hi = smem + cs * STAGE_BYTES;
       uint8_t* lo = hi + PART_BYTES;
-      mbar_wait(bar_raw + 8 * s, ph);
-      for (int u = pt; u < units16; u += NUM_X_THREADS) {
-        float4 v = *reinterpret_cast<const float4*>(hi + u * 16);
-        const int chunk = u >> 7, r = (u & 127) >> 3, pos = u & 7;
-        if (chunk == ones_chunk || (p.drop_p > 0.f && chunk >= A_CHUNKS)) {
-          const int c16 = ((((pos >> 1) ^ (r & 3)) << 1) | (pos & 1));  // undo the 32-byte-unit swizzle
+      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+      float4 v[MAX_UNITS];
+#pragma unroll
+      for (int k = 0; k < MAX_UNITS; ++k) {  // all reads first: the in-place stores below must not serialise the units
+        const int u = pt + k * NUM_X_THREADS;
+        if (u < units16) v[k] = *reinterpret_cast<const float4*>(hi + u * 16);
+      }
+#pragma unroll
+      for (int k = 0; k < MAX_UNITS; ++k) {
+        const int u = pt + k * NUM_X_THREADS;
+        if (u < units16) {
+          const int chunk = u >> 7;
           if (chunk == ones_chunk) {
-            if (c16 == ones_c16 && e0 + r < p.E) v.x = 1.f;
-          } else {
-            const int o = o0 + (chunk - A_CHUNKS) * 32 + c16 * 4;
-            if (e0 + r < p.E && o < d) {
-              float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)(e0 + r) * (uint64_t)d + (uint64_t)o, p.drop_thr, p.inv_keep);
-              v = make_float4(v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w);
+            if (c16 == ones_c16 && e < E_i) v[k].x = 1.f;
+          } else if (DROP && chunk >= A_CHUNKS) {
+            const int o = feature_of(chunk);
+            if (e < E_i && o < d) {
+              float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)o, p.drop_thr, p.inv_keep);
+              v[k] = make_float4(v[k].x * sc.x, v[k].y * sc.y, v[k].z * sc.z, v[k].w * sc.w);
             }
           }
+          const float4 h4 = make_float4(tf32_rna(v[k].x), tf32_rna(v[k].y), tf32_rna(v[k].z), tf32_rna(v[k].w));
+          const float4 l4 = make_float4(tf32_rna(v[k].x - h4.x), tf32_rna(v[k].y - h4.y), tf32_rna(v[k].z - h4.z), tf32_rna(v[k].w - h4.w));
+          *reinterpret_cast<float4*>(hi + u * 16) = h4;
+          *reinterpret_cast<float4*>(lo + u * 16) = l4;
         }
-        const float4 h4 = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-        const float4 l4 = make_float4(tf32_rna(v.x - h4.x), tf32_rna(v.y - h4.y), tf32_rna(v.z - h4.z), tf32_rna(v.w - h4.w));
-        *reinterpret_cast<float4*>(hi + u * 16) = h4;
-        *reinterpret_cast<float4*>(lo + u * 16) = l4;
       }
       fence_proxy_async();
       __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive(bar_ready + 8 * s);
-      if (++s == STAGES) { s = 0; ph ^= 1; }
+      if ((threadIdx.x & 31) == 0) mbar_arrive(bar_ready + 8 * cs);
+      if (++cs == STAGES) { cs = 0; cph ^= 1; }
+      load_step();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    (void)cph;
   }
 
   tc_fence_before();
@@ -275,40 +292,6 @@ __global__ void __launch_bounds__(256) wgrad_tma_reduce(const float* __restrict_
   else if (gb) gb[o] = s;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  });
-  return fn;
-}
-
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int d) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled is not available from the driver");
-    return NT_ERR_CUDA;
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)d * sizeof(float)};
-  cuuint32_t box[2] = {32u, (cuuint32_t)BLOCK_E};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return NT_ERR_CUDA;
-  }
-  return NT_OK;
-}
-
 }  // namespace wg2
 
 size_t tma_wgrad_workspace_bytes(int64_t E, int64_t d) {
@@ -331,11 +314,8 @@ int tma_layer_wgrad(const float* g, const float* m, int64_t E, int64_t d, float 
     set_error("tma_layer_wgrad: workspace too small");
     return NT_ERR_WORKSPACE;
   }
-  CUtensorMap map_m, map_g;
-  int rc = wg2::make_map(&map_m, m, E, (int)d);
-  if (rc) return rc;
-  rc = wg2::make_map(&map_g, g, E, (int)d);
-  if (rc) return rc;
+  p.m = m;
+  p.g = g;
   p.partial = static_cast<float*>(workspace);
   p.E = E;
   p.products = products;
@@ -348,10 +328,14 @@ int tma_layer_wgrad(const float* g, const float* m, int64_t E, int64_t d, float 
 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(wg2::wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg2::SMEM_BYTES); });
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(wg2::wgrad_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg2::SMEM_BYTES);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(wg2::wgrad_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg2::SMEM_BYTES);
+  });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_tma_kernel)");
   const int grid = p.geo.splits * p.geo.m_blocks * p.geo.n_tiles;
-  wg2::wgrad_tma_kernel<<<grid, wg2::THREADS, wg2::SMEM_BYTES, st>>>(map_m, map_g, p);
+  if (drop_p > 0.f) wg2::wgrad_tma_kernel<true><<<grid, wg2::THREADS, wg2::SMEM_BYTES, st>>>(p);
+  else wg2::wgrad_tma_kernel<false><<<grid, wg2::THREADS, wg2::SMEM_BYTES, st>>>(p);
   const int64_t total = (d + (p.geo.ones_row ? 1 : 0)) * d;
   wg2::wgrad_tma_reduce<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(p.partial, p.geo, gW, gb);
   NT_LAUNCH_CHECK("tma_layer_wgrad", 2);
