@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel-table", action="store_true", help="print the per-kernel table to stderr")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one captured CUDA graph per step")
     return ap.parse_args()
 
 
@@ -241,7 +242,8 @@ def run_ours(args, wl, batch):
     agg = (Sum if wl["agg"] == "sum" else Mean)()
     params = list(embed.parameters()) + list(block.parameters())
     flat = FlatGradients(params)
-    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+    use_graph = not args.no_graph
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=use_graph)
 
     # pinned host copies (e2e leg) and device-resident copies (value leg)
     host = {"node_types": node_types.pin_memory(), "edge_types": edge_types.pin_memory(),
@@ -268,6 +270,42 @@ def run_ours(args, wl, batch):
         opt.step()
         return loss
 
+    def capture(src: dict, from_host: bool):
+        """One step (H2D copies, ~75 kernel launches, optimizer, D2H of the loss) captured as ONE CUDA graph: the step is
+        launch-bound from Python (ctypes + autograd bookkeeping cost more than the 4.8 ms of kernels on a slow host).
+        The batch's indices are validated eagerly once (sync mode) before capture; the replayed graph skips the check."""
+        ops.set_index_validation("sync")
+        step(src, from_host)
+        ops.set_index_validation("off")
+        pinned_loss = torch.zeros(1).pin_memory()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step(src, from_host)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.lib().nt_kernel_launch_count()
+        with torch.cuda.graph(g):
+            loss = step(src, from_host)
+            pinned_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        return g, pinned_loss, _lib.lib().nt_kernel_launch_count() - n0
+
+    graphs: dict[bool, tuple] = {}
+    launch_mode = "eager"
+    if use_graph:
+        try:
+            graphs[False] = capture(resident, False)
+            if not args.no_e2e:
+                graphs[True] = capture(host, True)
+            launch_mode = "cuda_graph"
+        except Exception as exc:  # capture is an optimisation, never a requirement
+            print(f"bench.py: CUDA graph capture failed ({type(exc).__name__}: {exc}); launching eagerly", file=sys.stderr)
+            graphs = {}
+            torch.cuda.synchronize()
+            ops.set_index_validation("deferred")
+
     def timed(nsteps: int, src: dict, from_host: bool):
         if world > 1:
             dist.barrier()
@@ -276,7 +314,14 @@ def run_ours(args, wl, batch):
         t0 = time.perf_counter()
         ev0.record()
         last = None
+        g = graphs.get(from_host)
         for _ in range(nsteps):
+            if g is not None:
+                g[0].replay()
+                if from_host:
+                    torch.cuda.current_stream().synchronize()
+                    last = float(g[1])  # the loss, copied device -> pinned host inside the graph
+                continue
             loss = step(src, from_host)
             if from_host:
                 last = float(loss.detach())  # D2H read of the step's result inside the timed region
@@ -301,19 +346,23 @@ def run_ours(args, wl, batch):
     launches0 = _lib.lib().nt_kernel_launch_count()
     ms_total, _ = timed(args.steps, resident, False)
     launches = _lib.lib().nt_kernel_launch_count() - launches0
+    if False in graphs:
+        launches = graphs[False][2] * args.steps  # a replayed graph launches the kernels counted at capture time
     clocks = sampler.stop() if sampler else None
     value = world * batch * args.steps / (ms_total * 1e-3)
 
     e2e = None
     if not args.no_e2e:
-        for _ in range(2):
-            step(host, True)
+        if True not in graphs:
+            for _ in range(2):
+                step(host, True)
         e2e_ms, _ = timed(args.steps, host, True)
         e2e = {"value": world * batch * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": e2e_ms / args.steps,
                "inputs": "int64 atom/bond type ids [V,7],[E,2] + packed int32 topology (counts, local edge_index, local rev_index), pinned host memory"}
 
-    # ---- per-kernel CUDA-event timing (a separate instrumented pass over the same steps) ----
+    ops.set_index_validation("deferred")
+    # ---- per-kernel CUDA-event timing (a separate instrumented pass over the same steps, launched eagerly) ----
     roof = kernels = None
     nprof = min(args.steps, 10)
     with ops.KernelTimer() as kt:  # every rank runs it (the step contains the collective); rank 0 reports
@@ -361,7 +410,7 @@ def run_ours(args, wl, batch):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "hidden": d, "depth": L, "readout": wl["agg"], "batch_per_gpu": batch, "atoms_per_gpu": V,
-                       "edges_per_gpu": E, "gemm": ops.get_gemm_mode(), "parallelism": f"dp{world}",
+                       "edges_per_gpu": E, "gemm": ops.get_gemm_mode(), "parallelism": f"dp{world}", "launch": launch_mode,
                        "step": "collate+CSR, GraphEmbedding, ChempropBlock, readout, loss, backward, grad all-reduce (N>1), fused Adam",
                        "l2": "working set per step (>1.5 GB) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,

@@ -247,7 +247,7 @@ layer_gemm_pair(const Params p) {
         load_resid(chunks > 1 ? chunk_at(1) : chunks, rB);
         load_resid(chunks > 2 ? chunk_at(2) : chunks, rC);
         if (threadIdx.x == 0) trace_event(p, 0, tcur, 1, tile);
-        mbar_wait(bar_tmem_full, tphase);
+        mbar_wait_relaxed(bar_tmem_full, tphase);
         tc_fence_after();
         if (threadIdx.x == 0) trace_event(p, 0, tcur, 2, tile);
         if (shared_chunks == 0 && lane == 0) mbar_arrive_cluster(tmem_empty_leader);
@@ -375,7 +375,7 @@ layer_gemm_pair(const Params p) {
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
 #pragma unroll 1
         for (int kb = 0; kb < geo.k_blocks; ++kb) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_wait_relaxed(bar_empty + 8 * s, ph ^ 1);
           if (elect_one()) {
             const uint32_t st0 = sbase + s * STAGE_BYTES;
             trace_event(p, 3, tcur, 30, tile, kb);

@@ -51,6 +51,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_spin(bar, parity);
 }
+// Same, for waits that are expected to be LONG (epilogue warps waiting for an accumulator, copy warps waiting for a free
+// stage): after a few polls the warp sleeps between polls, so that its spin loop stops competing for issue slots with the
+// producer warps (ncu: the four epilogue warps of the weight-gradient kernel spent the whole kernel polling, ~28 % of samples).
+static __device__ __noinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  long long t0 = clock64();
+  int polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls > 8) __nanosleep(polls > 64 ? 200 : 40);
+    if ((polls & 255) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("notorch_b200: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_sleep(bar, parity);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

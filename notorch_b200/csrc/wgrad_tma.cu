@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tma_kernel(const Params p) {
     const int i = i0 + warp * 32 + lane;
     float* dst = p.partial + ((int64_t)split * geo.m_blocks * TILE_M + i) * geo.ld_partial + o0;
     if (nkb > 0) {
-      mbar_wait(bar_tmem_full, 0);
+      mbar_wait_relaxed(bar_tmem_full, 0);
       tc_fence_after();
       for (int cc = 0; cc < geo.n_tile / 16; ++cc) {
         uint32_t v[16];
