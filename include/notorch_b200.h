@@ -116,6 +116,16 @@ int nt_seg_reduce(const void* x, int64_t d, const int32_t* rowptr, const int32_t
                   int act, float act_param, int mean, float scale, void* out, int dtype, nt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * nt_seg_reduce with an epilogue, for the atom-state message-passing variant (extension, not in the
+ * reference tree):
+ *   dact_of == NULL : out[s,:] = (base ? base[s,:] : 0) + scale * reduce_j act(x[perm[j],:])               (forward: n = S_e + sum act(h)[src])
+ *   dact_of != NULL : out[s,:] = (base ? base[s,:] : 0) + act'(dact_of[s,:]) * scale * reduce_j x[perm[j],:]   (backward through act)
+ * ---------------------------------------------------------------------------------------------- */
+int nt_seg_reduce_ex(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments,
+                     int act, float act_param, int mean, float scale, const void* base, const void* dact_of,
+                     void* out, int dtype, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * out[i,:] = (base ? base[i,:] : 0) + scale * x[idx[i],:] / (mean_rowptr ? max(count(idx[i]),1) : 1)
  * K0 edge_init      : chemprop.py:83  h0 = x_v[src] + x_e            (base = x_e, x = x_v, idx = src)
  * backward of K1/K3 : g[e] = gE[e] + g_node[dst[e]] (/ indeg for mean);  g_x[v] = gH[batch[v]] (/count)
@@ -132,6 +142,14 @@ int nt_gather_add(const void* base, const void* x, const int32_t* idx, const int
  * ---------------------------------------------------------------------------------------------- */
 size_t nt_weight_image_bytes(int64_t d);
 int nt_weight_prepare(const void* W, int64_t d, int transpose, void* image, int dtype, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense Linear + Dropout + residual on tcgen05 (same CTA-pair kernel as K2, dense A operand):
+ *   out[r,:] = (resid ? resid[r,:] : 0) + Dropout_p(x[r,:] . W^T + bias)
+ * The atom-state update of the atom message-passing variant (row A10); weight_image = nt_weight_prepare(W, transpose = 0).
+ * ---------------------------------------------------------------------------------------------- */
+int nt_dense_forward(const void* x, const void* weight_image, const void* bias, const void* resid, int64_t R, int64_t d,
+                     float dropout_p, uint64_t seed, uint64_t offset, void* out, int dtype, int gemm_mode, nt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2 — one fused message-passing depth, forward. Replaces chemprop.py:40-41 + residual.py:28:

@@ -59,6 +59,7 @@ int pair_weight_prepare(const float*, int64_t, int, void*, cudaStream_t);
 int pair_layer_forward(const float*, const float*, const int32_t*, const int32_t*, const void*, const float*, int64_t, int64_t, int64_t, int, float, int,
                        float, uint64_t, uint64_t, float*, float*, int, cudaStream_t);
 int pair_layer_dgrad(const float*, const void*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
+int pair_dense_forward(const float*, const void*, const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
 // wgrad_tma.cu
 size_t tma_wgrad_workspace_bytes(int64_t E, int64_t d);
 int tma_layer_wgrad(const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, float*, void*, size_t, int, cudaStream_t);
@@ -145,6 +146,20 @@ extern "C" int nt_layer_forward(const void* h, const void* n, const int32_t* src
   if (m_out) { set_error("nt_layer_forward: m_out is only produced by the tensor-core path"); return NT_ERR_UNSUPPORTED; }
   return simt_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, static_cast<const float*>(W),
                             static_cast<const float*>(bias), E, d, act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), st);
+}
+
+extern "C" int nt_dense_forward(const void* x, const void* weight_image, const void* bias, const void* resid, int64_t R, int64_t d, float dropout_p,
+                                uint64_t seed, uint64_t offset, void* out, int dtype, int gemm_mode, nt_stream_t stream) {
+  const int64_t E = R;
+  NT_COMMON_LAYER_CHECKS("nt_dense_forward");
+  if (R == 0) return NT_OK;
+  NT_CHECK_ARG(x && out && weight_image, "nt_dense_forward: null pointer");
+  if (gemm_mode == NT_GEMM_FP32 || !use_pair_kernels() || !tc_shape_ok(d, x, out, bias, resid)) {
+    set_error("nt_dense_forward: needs the tensor-core path (gemm_mode tf32x3 / tf32, d %% 4 == 0, 16-byte aligned rows)");
+    return NT_ERR_UNSUPPORTED;
+  }
+  return pair_dense_forward(static_cast<const float*>(x), weight_image, static_cast<const float*>(bias), static_cast<const float*>(resid), R, d,
+                            dropout_p, seed, offset, static_cast<float*>(out), gemm_mode == NT_GEMM_TF32 ? 1 : 3, as_stream(stream));
 }
 
 extern "C" int nt_layer_backward_dgrad(const void* g, const void* W, const void* weight_image, int64_t E, int64_t d, float dropout_p, uint64_t seed,

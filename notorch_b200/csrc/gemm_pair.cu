@@ -152,7 +152,7 @@ __device__ __forceinline__ void trace_event_t(const Params& p, int region, uint3
   }
 }
 
-template <int MODE, bool DROP, bool RELU, bool TRACE>  // MODE 0 = K2 forward, 1 = K4a dgrad; TRACE = the role-timeline build (scripts/trace_pair.py)
+template <int MODE, bool DROP, bool RELU, bool TRACE>  // MODE 0 = K2 forward, 1 = K4a dgrad, 2 = dense forward (atom message passing); TRACE = the role-timeline build (scripts/trace_pair.py)
 __global__ void __launch_bounds__(THREADS, 1)
 layer_gemm_pair(const Params p) {
   auto trace_event = [](const Params& pp, int region, uint32_t& cursor, int ev, int64_t tile, int aux = 0) {
@@ -211,7 +211,7 @@ layer_gemm_pair(const Params p) {
     uint32_t tphase = 0;
     const int chunks = geo.n_tile / EPI_COLS;
     const int sub = lane & 3, rsub = lane >> 2;
-    const bool has_resid = MODE == 0 && p.resid != nullptr;
+    const bool has_resid = MODE != 1 && p.resid != nullptr;
     const int shared_chunks = 2 * geo.n_tile > 512 ? (2 * geo.n_tile - 512) / EPI_COLS : 0;
     int tw = 0;
     float4* bias_s = reinterpret_cast<float4*>(smem + OFF_BIAS + warp * BIAS_WARP_BYTES);
@@ -219,7 +219,7 @@ layer_gemm_pair(const Params p) {
     for (int tile = first_tile; tile < pair_tiles; tile += tile_stride) {
       const int64_t row0 = (int64_t)tile * (2 * TILE_M) + rank * TILE_M + warp * 32;
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
-        if (MODE == 0 && bias_nt != nt) {  // (re)stage this N tile's bias: once per kernel when d <= 304 (per-chunk global reads cost 18 us)
+        if (MODE != 1 && bias_nt != nt) {  // (re)stage this N tile's bias: once per kernel when d <= 304 (per-chunk global reads cost 18 us)
           __syncwarp();
           for (int i = lane; i < geo.n_tile / 4; i += 32) {
             const int col = nt * geo.n_tile + 4 * i;
@@ -269,14 +269,14 @@ layer_gemm_pair(const Params p) {
           const int col = nt * geo.n_tile + cc * EPI_COLS + sub * 4;
           if (col < d) {
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (MODE == 0) bias4 = bias_s[cc * (EPI_COLS / 4) + sub];
+            if (MODE != 1) bias4 = bias_s[cc * (EPI_COLS / 4) + sub];
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int r = it * 8 + rsub;
               const int64_t e = row0 + r;
               if (e < p.E) {
                 float4 acc = *reinterpret_cast<const float4*>(stage + r * 64 + ((sub ^ ((r >> 1) & 3)) << 4));
-                if (MODE == 0) {
+                if (MODE != 1) {
                   acc = make_float4(acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w);
                   if (DROP) {
                     float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)col, p.drop_thr, p.inv_keep);
@@ -496,7 +496,7 @@ layer_gemm_pair(const Params p) {
             else a = act_fwd4(raw1[i], p.act, p.act_param);
             m = make_float4(m.x - a.x, m.y - a.y, m.z - a.z, m.w - a.w);
             if (col >= d || e >= E_i) m = make_float4(0.f, 0.f, 0.f, 0.f);
-          } else if (DROP && e < E_i && col < d) {
+          } else if (MODE == 1 && DROP && e < E_i && col < d) {
             const float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)col, p.drop_thr, p.inv_keep);
             m = make_float4(m.x * sc.x, m.y * sc.y, m.z * sc.z, m.w * sc.w);
           }
@@ -599,9 +599,9 @@ static int launch_variant(const Params& p, cudaStream_t st) {
 template <int MODE>
 static int launch(const Params& p, cudaStream_t st) {
   const bool drop = p.drop_p > 0.f;
-  const bool relu = MODE == 1 || p.act == NT_ACT_RELU;  // K4a has no activation
-  if (p.trace != nullptr && !drop && relu) return launch_variant<MODE, false, true, true>(p, st);  // the role-timeline build exists for the default case only
-  if (MODE == 1) return drop ? launch_variant<MODE, true, true, false>(p, st) : launch_variant<MODE, false, true, false>(p, st);
+  const bool relu = MODE != 0 || p.act == NT_ACT_RELU;  // the dense modes have no activation prologue
+  if (MODE != 2 && p.trace != nullptr && !drop && relu) return launch_variant<MODE, false, true, true>(p, st);  // the role-timeline build exists for the default case only
+  if (MODE != 0) return drop ? launch_variant<MODE, true, true, false>(p, st) : launch_variant<MODE, false, true, false>(p, st);
   if (drop) return relu ? launch_variant<MODE, true, true, false>(p, st) : launch_variant<MODE, true, false, false>(p, st);
   return relu ? launch_variant<MODE, false, true, false>(p, st) : launch_variant<MODE, false, false, false>(p, st);
 }
@@ -644,6 +644,18 @@ int pair_layer_forward(const float* h, const float* n, const int32_t* src, const
   (void)V;
   p.a0 = n; p.a1 = h;
   return pair::launch<0>(p, st);
+}
+
+// out[r,:] = (resid ? resid[r,:] : 0) + Dropout(x[r,:] . W^T + bias): the Linear + Dropout + residual of an atom-state update
+// (dense A operand; the bias / dropout / residual epilogue of K2)
+int pair_dense_forward(const float* x, const void* wimg, const float* bias, const float* resid, int64_t R, int64_t d, float drop_p, uint64_t seed,
+                       uint64_t offset, float* out, int products, cudaStream_t st) {
+  pair::Params p{};
+  p.a0 = x; p.wimg = static_cast<const uint8_t*>(wimg); p.bias = bias; p.resid = resid; p.out = out; p.E = R;
+  p.geo = pair::make_geometry((int)d);
+  p.act = NT_ACT_IDENTITY; p.products = products;
+  pair::fill_dropout(p, drop_p, seed, offset);
+  return pair::launch<2>(p, st);
 }
 
 int pair_layer_dgrad(const float* g, const void* wimg, int64_t E, int64_t d, float drop_p, uint64_t seed, uint64_t offset, float* g_m, int products,

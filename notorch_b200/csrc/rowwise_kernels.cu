@@ -26,7 +26,10 @@ constexpr int SEG_ITEMS = 2;
 template <bool HAS_PERM>
 __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __restrict__ x, int d, int chunks, const int32_t* __restrict__ rowptr,
                                                               const int32_t* __restrict__ perm, int64_t total, int act, float act_param,
-                                                              int mean, float scale, float* __restrict__ out) {
+                                                              int mean, float scale, const float* __restrict__ base,
+                                                              const float* __restrict__ dact_of, float* __restrict__ out) {
+  // dact_of != nullptr (nt_seg_reduce_ex, backward form): no activation prologue; the reduced row is multiplied by act'(dact_of[s])
+  const int pre_act = dact_of ? NT_ACT_IDENTITY : act;
   const int64_t t0 = (int64_t)blockIdx.x * (ROW_THREADS * SEG_ITEMS) + threadIdx.x;
   int s[SEG_ITEMS], c[SEG_ITEMS], lo[SEG_ITEMS], hi[SEG_ITEMS];
   float4 acc[SEG_ITEMS];
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __r
     for (int k = 0; k < SEG_ITEMS; ++k)
 #pragma unroll
       for (int u = 0; u < 2; ++u)  // ascending item order within the segment: bit-identical to a sequential scatter_add_
-        if (ok[k][u]) acc[k] = add4(acc[k], act != NT_ACT_IDENTITY ? act_fwd4(v[k][u], act, act_param) : v[k][u]);
+        if (ok[k][u]) acc[k] = add4(acc[k], pre_act != NT_ACT_IDENTITY ? act_fwd4(v[k][u], pre_act, act_param) : v[k][u]);
   }
 #pragma unroll
   for (int k = 0; k < SEG_ITEMS; ++k) {
@@ -75,6 +78,12 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __r
       a = make_float4(a.x / cnt, a.y / cnt, a.z / cnt, a.w / cnt);
     }
     if (scale != 1.f) a = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+    if (dact_of) {
+      const float4 hv = ldg4(dact_of + (int64_t)s[k] * d + c[k]);
+      a = make_float4(a.x * act_bwd(hv.x, act, act_param), a.y * act_bwd(hv.y, act, act_param), a.z * act_bwd(hv.z, act, act_param),
+                      a.w * act_bwd(hv.w, act, act_param));
+    }
+    if (base) a = add4(ldg4_stream(base + (int64_t)s[k] * d + c[k]), a);
     stg4(out + (int64_t)s[k] * d + c[k], a);
   }
 }
@@ -82,19 +91,23 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __r
 // scalar fallback for d % 4 != 0 (or unaligned bases): one thread per (segment, element)
 __global__ void __launch_bounds__(ROW_THREADS) seg_reduce_s(const float* __restrict__ x, int d, const int32_t* __restrict__ rowptr,
                                                              const int32_t* __restrict__ perm, int64_t total, int act, float act_param, int mean,
-                                                             float scale, float* __restrict__ out) {
+                                                             float scale, const float* __restrict__ base, const float* __restrict__ dact_of,
+                                                             float* __restrict__ out) {
   int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
   if (t >= total) return;
   int s = (int)(t / d);
   int c = (int)(t - (int64_t)s * d);
   int lo = __ldg(rowptr + s), hi = __ldg(rowptr + s + 1);
+  const int pre_act = dact_of ? NT_ACT_IDENTITY : act;
   float acc = 0.f;
   for (int j = lo; j < hi; ++j) {
     int r = perm ? __ldg(perm + j) : j;
-    acc += act_fwd(__ldg(x + (int64_t)r * d + c), act, act_param);
+    acc += act_fwd(__ldg(x + (int64_t)r * d + c), pre_act, act_param);
   }
   if (mean) acc = acc / (float)max(hi - lo, 1);
   if (scale != 1.f) acc *= scale;
+  if (dact_of) acc *= act_bwd(__ldg(dact_of + t), act, act_param);
+  if (base) acc = __ldg(base + t) + acc;
   out[(int64_t)s * d + c] = acc;
 }
 
@@ -186,29 +199,42 @@ static bool vec_ok(int64_t d, const void* a, const void* b = nullptr, const void
   return d % 4 == 0 && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(e) && aligned16(f);
 }
 
-extern "C" int nt_seg_reduce(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int act, float act_param,
-                             int mean, float scale, void* out, int dtype, nt_stream_t stream) {
-  NT_CHECK_ARG(dtype == NT_F32 || dtype == NT_BF16, "nt_seg_reduce: bad dtype");
-  if (dtype != NT_F32) { set_error("nt_seg_reduce: only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
-  NT_CHECK_ARG(d > 0 && d < (1 << 20) && num_segments >= 0 && num_segments < INT32_MAX, "nt_seg_reduce: bad sizes");
-  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "nt_seg_reduce: bad activation");
+static int seg_reduce_impl(const char* fn, const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int act,
+                           float act_param, int mean, float scale, const void* base, const void* dact_of, void* out, int dtype,
+                           nt_stream_t stream) {
+  NT_CHECK_ARG(dtype == NT_F32 || dtype == NT_BF16, "%s: bad dtype", fn);
+  if (dtype != NT_F32) { set_error("%s: only NT_F32 is implemented", fn); return NT_ERR_UNSUPPORTED; }
+  NT_CHECK_ARG(d > 0 && d < (1 << 20) && num_segments >= 0 && num_segments < INT32_MAX, "%s: bad sizes", fn);
+  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "%s: bad activation", fn);
   if (num_segments == 0) return NT_OK;
-  NT_CHECK_ARG(rowptr && out, "nt_seg_reduce: null pointer");
+  NT_CHECK_ARG(rowptr && out, "%s: null pointer", fn);
   cudaStream_t st = as_stream(stream);
   const float* xf = static_cast<const float*>(x);
+  const float* bf = static_cast<const float*>(base);
+  const float* df = static_cast<const float*>(dact_of);
   float* of = static_cast<float*>(out);
-  if (vec_ok(d, x, out)) {
+  if (vec_ok(d, x, out, base, dact_of)) {
     int chunks = (int)(d / 4);
     int64_t total = num_segments * chunks;
     unsigned grid = (unsigned)cdiv(total, ROW_THREADS * SEG_ITEMS);
-    if (perm) seg_reduce_v4<true><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, of);
-    else seg_reduce_v4<false><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, of);
+    if (perm) seg_reduce_v4<true><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);
+    else seg_reduce_v4<false><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);
   } else {
     int64_t total = num_segments * d;
-    seg_reduce_s<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(xf, (int)d, rowptr, perm, total, act, act_param, mean, scale, of);
+    seg_reduce_s<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(xf, (int)d, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);
   }
-  NT_LAUNCH_CHECK("nt_seg_reduce", 1);
+  NT_LAUNCH_CHECK(fn, 1);
   return NT_OK;
+}
+
+extern "C" int nt_seg_reduce(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int act, float act_param,
+                             int mean, float scale, void* out, int dtype, nt_stream_t stream) {
+  return seg_reduce_impl("nt_seg_reduce", x, d, rowptr, perm, num_segments, act, act_param, mean, scale, nullptr, nullptr, out, dtype, stream);
+}
+
+extern "C" int nt_seg_reduce_ex(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int act, float act_param,
+                                int mean, float scale, const void* base, const void* dact_of, void* out, int dtype, nt_stream_t stream) {
+  return seg_reduce_impl("nt_seg_reduce_ex", x, d, rowptr, perm, num_segments, act, act_param, mean, scale, base, dact_of, out, dtype, stream);
 }
 
 extern "C" int nt_gather_add(const void* base, const void* x, const int32_t* idx, const int32_t* mean_rowptr, int64_t n, int64_t d, float scale,

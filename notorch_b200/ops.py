@@ -535,6 +535,120 @@ def layer(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, *, act:
     return _Layer.apply(h, weight, bias, csr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)
 
 
+# ------------------------------------------------------------------------------------------------
+# atom-state message passing (extension named by BASELINE configs[3]; not in the reference tree)
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class AtomCSR:
+    """Atom-to-atom neighbour lists derived from a GraphCSR: for every atom the SOURCE atoms of its incoming edges
+    (``nbr_in``, ascending edge order) and the DESTINATION atoms of its outgoing edges (``nbr_out``)."""
+
+    V: int
+    E: int
+    nbr_in: SegmentCSR   # rowptr = by_dst.rowptr, perm[j] = src[by_dst.perm[j]]
+    nbr_out: SegmentCSR  # rowptr = by_src.rowptr, perm[j] = dst[by_src.perm[j]]
+    ident: Tensor        # arange(V) int32 (identity gather index)
+
+
+def atom_csr(csr: GraphCSR) -> AtomCSR:
+    cached = getattr(csr, "_atom_csr", None)
+    if cached is not None:
+        return cached
+    src, dst = csr.src, csr.dst
+    perm_in = src[csr.by_dst.perm.long()].contiguous()
+    perm_out = dst[csr.by_src.perm.long()].contiguous()
+    acsr = AtomCSR(csr.V, csr.E, SegmentCSR(csr.by_dst.rowptr, perm_in, perm_in, csr.V), SegmentCSR(csr.by_src.rowptr, perm_out, perm_out, csr.V),
+                   torch.arange(csr.V, dtype=torch.int32, device=src.device))
+    csr._atom_csr = acsr
+    return acsr
+
+
+def _seg_reduce_ex_raw(x: Tensor, seg: SegmentCSR, act: int, act_param: float, mean: bool, base: Tensor | None, dact_of: Tensor | None,
+                       tag: str) -> Tensor:
+    d = x.shape[1]
+    out = torch.empty((seg.num_segments, d), dtype=x.dtype, device=x.device)
+    _run(f"{tag}:nt_seg_reduce_ex", _lib.lib().nt_seg_reduce_ex, _p(x), d, _p(seg.rowptr), _p(seg.perm), seg.num_segments, act, act_param,
+         int(mean), 1.0, _p(base), _p(dact_of), _p(out), NT_F32, _stream())
+    return out
+
+
+class _AtomLayer(torch.autograd.Function):
+    """One depth of atom-state message passing:
+
+        n[v]  = reduce_{e: dst[e]=v} (act(h)[src[e]] + x_e[e]) = reduce_in(act(h)[src]) + s_e[v]      (s_e = reduce_dst(x_e), once per batch)
+        h'    = [h +] Dropout(Linear(n))
+
+    forward: nt_seg_reduce_ex (neighbour gather-reduce with activation prologue, no [E,d] intermediate) + nt_dense_forward (tcgen05);
+    backward: K4b/K4a on [V,d] operands, then nt_seg_reduce_ex in its backward form over the outgoing-neighbour list.
+    """
+
+    @staticmethod
+    def forward(ctx, h: Tensor, s_e: Tensor, W: Tensor, b: Tensor | None, acsr: AtomCSR, act: int, act_param: float, mean: bool,
+                residual: bool, p: float, seed: int, offset: int, mode: int):
+        h, s_e, W = _require_float(h, "node_feats"), _require_float(s_e, "edge aggregate"), _require_float(W, "weight")
+        V, d = h.shape
+        if V != acsr.V or s_e.shape != h.shape or W.shape != (d, d):
+            raise RuntimeError(f"notorch_b200: atom layer shape mismatch: h {tuple(h.shape)}, s_e {tuple(s_e.shape)}, W {tuple(W.shape)}, V={acsr.V}")
+        if mode == GEMM_FP32 or d % 4 != 0:
+            raise NotImplementedError("notorch_b200: atom message passing runs on the tensor-core path only (gemm_mode tf32x3 / tf32, d % 4 == 0)")
+        if b is not None:
+            b = _require(b, "bias", torch.float32, 1)
+        L = _lib.lib()
+        with torch.cuda.device(h.device):
+            n = _seg_reduce_ex_raw(h, acsr.nbr_in, act, act_param, mean, s_e, None, tag="A1")
+            img = _weight_image(W, False)
+            out = torch.empty_like(h)
+            _run("A2:nt_dense_forward", L.nt_dense_forward, _p(n), _p(img), _p(b), _p(h) if residual else None, V, d, p, seed, offset, _p(out),
+                 NT_F32, mode, _stream())
+        ctx.save_for_backward(h, n, W)
+        ctx.acsr, ctx.cfg, ctx.has_bias = acsr, (act, act_param, mean, residual, p, seed, offset, mode), b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        h, n, W = ctx.saved_tensors
+        acsr = ctx.acsr
+        act, act_param, mean, residual, p, seed, offset, mode = ctx.cfg
+        V, d = h.shape
+        g = g.contiguous()
+        L = _lib.lib()
+        gW = gb = gh = gs = None
+        with torch.cuda.device(g.device):
+            if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
+                gW = torch.empty_like(W)
+                gb = torch.empty(d, dtype=W.dtype, device=W.device) if ctx.has_bias else None
+                ws = _workspace(g.device, L.nt_layer_backward_wgrad_workspace_bytes(V, d), slot=1)
+                _run("A4b:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(g), _p(n), None, None, None, None, V, V, d, act, act_param, p, seed,
+                     offset, _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream())
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                g_n = torch.empty_like(h)
+                _run("A4a:nt_layer_backward_dgrad", L.nt_layer_backward_dgrad, _p(g), _p(W), _p(_weight_image(W, True)), V, d, p, seed, offset,
+                     _p(g_n), NT_F32, mode, _stream())
+                gs = g_n  # n = s_e + reduce(...): the edge aggregate receives g_n as is
+                if ctx.needs_input_grad[0]:
+                    # mean: every incoming message of atom v carries 1 / indeg(v)
+                    g_msg = _gather_add_raw(None, g_n, acsr.ident, acsr.nbr_in.rowptr, tag="A5") if mean else g_n
+                    gh = _seg_reduce_ex_raw(g_msg, acsr.nbr_out, act, act_param, False, g if residual else None, h, tag="A6")
+        return gh, gs, gW, gb, None, None, None, None, None, None, None, None, None
+
+
+def atom_layer(h: Tensor, s_e: Tensor, weight: Tensor, bias: Tensor | None, acsr: AtomCSR, *, act: tuple[int, float] = (_lib.ACT_RELU, 0.0),
+               reduce: str = "sum", residual: bool = True, dropout: float = 0.0, training: bool = False) -> Tensor:
+    global _dropout_calls
+    if reduce not in ("sum", "mean"):
+        raise NotImplementedError(f"notorch_b200: reduce='{reduce}' is not implemented (sum and mean are); no fallback")
+    p = float(dropout) if training else 0.0
+    if not 0.0 <= p < 1.0:
+        raise ValueError(f"dropout probability has to be in [0, 1), but got {p}")
+    seed = offset = 0
+    if p > 0.0:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        _dropout_calls += 1
+        offset = _dropout_calls
+    return _AtomLayer.apply(h, s_e, weight, bias, acsr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)
+
+
 def dropout_mask(n_rows: int, d: int, p: float, seed: int, offset: int, device) -> Tensor:
     """The keep-mask K2/K4 derive from (seed, offset) — exposed for tests."""
     mask = torch.empty((n_rows, d), dtype=torch.float32, device=device)
