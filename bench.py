@@ -42,6 +42,9 @@ WORKLOADS = {
                                                                      "batch 4096 synthetic ZINC-size graphs per GPU, fp32 training step"),
     "c1": dict(config=1, batch=64, d=300, depth=3, agg="sum", desc="BASELINE configs[0]: batch 64 ~25-atom molecules"),
     "c3": dict(config=3, batch=16384, d=1024, depth=5, agg="mean", desc="BASELINE configs[2]: depth=5 hidden=1024 Mean readout, batch 16384 per GPU"),
+    "c4": dict(config=2, batch=16384, d=300, depth=3, agg="norm", inference=True,
+               desc="BASELINE configs[3]: atom message passing depth=3 hidden=300, Norm pooling, inference-only screening, 16384 molecules per launch "
+                    "per GPU (10 M molecules = 611 launches; shards are independent, no collective)"),
 }
 
 
@@ -213,6 +216,157 @@ def run_reference_arm(args, wl, batch):
 # ------------------------------------------------------------------------------------------------
 # CUDA leg
 # ------------------------------------------------------------------------------------------------
+
+def run_screening(args, wl, batch):
+    """BASELINE configs[3]: inference-only screening with the atom message-passing variant. One step = one launch of `batch`
+    molecules through GraphEmbedding -> AtomMessagePassing -> Norm; ranks are independent replicas on disjoint shards."""
+    import torch.distributed as dist
+
+    from notorch_b200 import BatchedGraph, _lib, ops
+    from notorch_b200.nn import AtomMessagePassing, GraphEmbedding, Norm
+
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)  # only for the barrier / max-over-ranks of the timing
+    if args.gemm:
+        ops.set_gemm_mode(args.gemm)
+    mols, node_types, edge_types = make_workload(wl, rank, batch)
+    V, E, d, L = mols.total_atoms, mols.total_edges, wl["d"], wl["depth"]
+    torch.manual_seed(0)
+    embed = GraphEmbedding(NUM_ATOM_TYPES, NUM_BOND_TYPES, hidden_dim=d).to(dev).eval()
+    block = AtomMessagePassing(hidden_dim=d, depth=L).to(dev).eval()
+    agg = Norm(100.0)
+    host = {"node_types": node_types.pin_memory(), "edge_types": edge_types.pin_memory(),
+            "num_atoms": torch.from_numpy(mols.num_atoms).pin_memory(), "num_edges": torch.from_numpy(mols.num_edges).pin_memory(),
+            "edge_index": torch.from_numpy(mols.edge_index).pin_memory(), "rev_index": torch.from_numpy(mols.rev_index).pin_memory()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = torch.empty((batch, d), dtype=torch.float32).pin_memory()
+
+    class Packed:
+        def __init__(self, t):
+            self.num_atoms, self.num_edges, self.edge_index, self.rev_index = t["num_atoms"], t["num_edges"], t["edge_index"], t["rev_index"]
+
+    def step(src, from_host):
+        with torch.no_grad():
+            t = {k: v.to(dev, non_blocking=True) for k, v in src.items()} if from_host else src
+            G = BatchedGraph.from_packed(Packed(t), t["node_types"], t["edge_types"], device=dev)
+            H = agg(block(embed(G)))
+            if from_host:
+                out_host.copy_(H, non_blocking=True)  # the screening result: one embedding per molecule
+            return H
+
+    ops.set_index_validation("sync")
+    step(resident, False)
+    ops.set_index_validation("off")
+    graphs = {}
+    launch_mode = "eager"
+    if not args.no_graph:
+        try:
+            for fh, src in ((False, resident), (True, host)):
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        step(src, fh)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = _lib.lib().nt_kernel_launch_count()
+                with torch.cuda.graph(g):
+                    step(src, fh)
+                graphs[fh] = (g, _lib.lib().nt_kernel_launch_count() - n0)
+            launch_mode = "cuda_graph"
+        except Exception as exc:
+            print(f"bench.py: CUDA graph capture failed ({type(exc).__name__}: {exc}); launching eagerly", file=sys.stderr)
+            graphs = {}
+            torch.cuda.synchronize()
+
+    def timed(nsteps, src, from_host):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(nsteps):
+            if from_host in graphs:
+                graphs[from_host][0].replay()
+            else:
+                step(src, from_host)
+            if from_host:
+                torch.cuda.current_stream().synchronize()  # the embeddings are on the host before the next launch is issued
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if from_host:
+            ms = max(ms, (time.perf_counter() - t0) * 1e3)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt)
+        return ms
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        step(resident, False)
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.mark_start()
+    n0 = _lib.lib().nt_kernel_launch_count()
+    ms_total = timed(args.steps, resident, False)
+    launches = graphs[False][1] * args.steps if False in graphs else _lib.lib().nt_kernel_launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    e2e_ms = timed(args.steps, host, True)
+    ops.set_index_validation("deferred")
+    with ops.KernelTimer() as kt:
+        for _ in range(min(args.steps, 10)):
+            step(resident, False)
+    summ = kt.summary()
+    if rank == 0:
+        nprof = min(args.steps, 10)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        s4 = d * 4
+        alg = {"A1": (E + 2 * V) * s4 + 4 * (E + V + 1),  # reads ~E gathered atom rows + s_e, writes n
+               "A2": 3 * V * s4 + d * s4,                   # reads n, h (residual); writes h'
+               "K1": (E + V) * s4 + 4 * (E + V + 1), "K3": (V + batch) * s4 + 4 * (batch + 1),
+               "emb": 0.5 * ((V * 7 + E * 2) * 8 + (V + E) * s4)}
+        kernels = []
+        for tag, rec in sorted(summ.items(), key=lambda kv: -kv[1]["total_ms"]):
+            cls = tag.split(":")[0]
+            row = {"kernel": tag, "launches_per_step": rec["launches"] / nprof, "avg_ms": rec["avg_ms"], "ms_per_step": rec["total_ms"] / nprof}
+            if cls in alg:
+                row["alg_bytes"] = alg[cls]
+                row["gbs"] = alg[cls] / (rec["avg_ms"] * 1e-3) / 1e9
+                row["hbm_frac"] = row["gbs"] / hbm_peak
+            kernels.append(row)
+        dom = next((k for k in kernels if "alg_bytes" in k), None)
+        roof = None if dom is None else {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                                         "frac": dom["hbm_frac"], "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback",
+                                         "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": dom["avg_ms"]}
+        _emit({"metric": "molecules/sec inference, atom message passing d=3 h=300, Norm read-out", "value": world * batch * args.steps / (ms_total * 1e-3),
+               "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": wl["desc"], "hidden": d, "depth": L, "readout": "norm", "batch_per_gpu": batch, "atoms_per_gpu": V, "edges_per_gpu": E,
+                          "gemm": ops.get_gemm_mode(), "parallelism": f"replicas x{world}", "launch": launch_mode,
+                          "l2": "working set per launch (>1 GB) exceeds the 126 MB L2; no explicit flush"},
+               "clocks": clocks,
+               "e2e": {"value": world * batch * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                       "d2h_bytes_per_step": batch * d * 4, "ms_per_step": e2e_ms / args.steps},
+               "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None, "kernels": kernels})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
 
 def run_ours(args, wl, batch):
     import torch.distributed as dist
@@ -437,6 +591,8 @@ def main():
     args = parse_args()
     wl = WORKLOADS[args.workload]
     batch = args.batch or wl["batch"]
+    if wl.get("inference") and args.impl != "reference":
+        return run_screening(args, wl, batch)
     if args.impl == "reference":
         run_reference_arm(args, wl, batch)
     else:
