@@ -410,7 +410,7 @@ def run_ours(args, wl, batch):
         def __init__(self, t):
             self.num_atoms, self.num_edges, self.edge_index, self.rev_index = t["num_atoms"], t["num_edges"], t["edge_index"], t["rev_index"]
 
-    def step(src: dict, from_host: bool):
+    def fwd_bwd(src: dict, from_host: bool):
         if from_host:
             t = {k: v.to(dev, non_blocking=True) for k, v in src.items()}
         else:
@@ -420,14 +420,20 @@ def run_ours(args, wl, batch):
         loss = H.square().mean()
         flat.zero()
         loss.backward()  # K3bwd, K1bwd, L x (K4b, K4a, K5, K6), K5
+        return loss
+
+    def step(src: dict, from_host: bool):
+        loss = fwd_bwd(src, from_host)
         flat.all_reduce_mean()  # NCCL over NVLink when world > 1 (no-op otherwise)
         opt.step()
         return loss
 
     def capture(src: dict, from_host: bool):
-        """One step (H2D copies, ~75 kernel launches, optimizer, D2H of the loss) captured as ONE CUDA graph: the step is
-        launch-bound from Python (ctypes + autograd bookkeeping cost more than the 4.8 ms of kernels on a slow host).
-        The batch's indices are validated eagerly once (sync mode) before capture; the replayed graph skips the check."""
+        """The step captured as CUDA graphs: launched eagerly it is bound by Python (ctypes + autograd bookkeeping cost more
+        than the 4.8 ms of kernels on a slow host). One GPU: ONE graph (H2D copies, ~75 kernel launches, optimizer, D2H of the
+        loss). Several GPUs: TWO graphs (forward + backward | optimizer) with the NCCL all-reduce launched eagerly between
+        them - a collective captured inside the graph deadlocked the 2-rank run. The batch's indices are validated eagerly
+        once (sync mode) before capture; the replayed graph skips the check."""
         ops.set_index_validation("sync")
         step(src, from_host)
         ops.set_index_validation("off")
@@ -440,11 +446,26 @@ def run_ours(args, wl, batch):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        g2 = None
         n0 = _lib.lib().nt_kernel_launch_count()
-        with torch.cuda.graph(g):
-            loss = step(src, from_host)
-            pinned_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-        return g, pinned_loss, _lib.lib().nt_kernel_launch_count() - n0
+        if world == 1:
+            with torch.cuda.graph(g):
+                loss = step(src, from_host)
+                pinned_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        else:
+            with torch.cuda.graph(g):
+                loss = fwd_bwd(src, from_host)
+                pinned_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, pool=g.pool()):
+                opt.step()
+        return g, pinned_loss, _lib.lib().nt_kernel_launch_count() - n0, g2
+
+    def replay(g: tuple):
+        g[0].replay()
+        if g[3] is not None:
+            flat.all_reduce_mean()
+            g[3].replay()
 
     graphs: dict[bool, tuple] = {}
     launch_mode = "eager"
@@ -471,7 +492,7 @@ def run_ours(args, wl, batch):
         g = graphs.get(from_host)
         for _ in range(nsteps):
             if g is not None:
-                g[0].replay()
+                replay(g)
                 if from_host:
                     torch.cuda.current_stream().synchronize()
                     last = float(g[1])  # the loss, copied device -> pinned host inside the graph
