@@ -42,17 +42,15 @@ constexpr int MAX_N_TILE = 304;
 constexpr int A_PART_BYTES = TILE_M * 128;                  // 16 KiB: one raw / hi / lo tile of 128 rows x 32 fp32
 constexpr int W_PART_BYTES = (MAX_N_TILE / 2) * 128;        // 19 KiB: this CTA's half of the weight tile (hi or lo)
 constexpr int STAGE_BYTES = 2 * A_PART_BYTES + 2 * W_PART_BYTES;  // 70 KiB
-constexpr int EPI_COLS = 16;
-constexpr int EPI_WARP_BYTES = 32 * EPI_COLS * 4;
+constexpr int EPI_COLS = 32;
+constexpr int EPI_WARP_BYTES = 32 * EPI_COLS * 4;  // 4 KiB staging tile per epilogue warp
 constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, TMA_WARP = 5, FIRST_X_WARP = 6, NUM_X_WARPS = 8;
 constexpr int NUM_X_THREADS = NUM_X_WARPS * 32;
 constexpr int THREADS = (FIRST_X_WARP + NUM_X_WARPS) * 32;  // 448
 
 constexpr int OFF_A0 = 0, OFF_A1 = A_PART_BYTES, OFF_WHI = 2 * A_PART_BYTES, OFF_WLO = OFF_WHI + W_PART_BYTES;  // inside a stage
 constexpr int OFF_EPI = STAGES * STAGE_BYTES;
-constexpr int BIAS_WARP_BYTES = 1280;                       // per-epilogue-warp copy of the bias of the current N tile (<= 304 floats)
-constexpr int OFF_BIAS = OFF_EPI + NUM_EPI_WARPS * EPI_WARP_BYTES;
-constexpr int OFF_BAR = OFF_BIAS + NUM_EPI_WARPS * BIAS_WARP_BYTES;
+constexpr int OFF_BAR = OFF_EPI + NUM_EPI_WARPS * EPI_WARP_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 static_assert(STAGE_BYTES % 1024 == 0 && W_PART_BYTES % 1024 == 0, "swizzle-128B tiles need 1 KiB alignment");
@@ -205,77 +203,90 @@ layer_gemm_pair(const Params p) {
 
   if (warp < NUM_EPI_WARPS) {
     // ===================================== EPILOGUE =====================================
+    // 32 accumulator columns per step: two tcgen05.ld of 16 columns -> XOR-swizzled 4 KiB staging tile (thread = row) ->
+    // 128-byte row segments (8 lanes per row, 4 rows per instruction): + bias, dropout, + residual, coalesced stores.
+    // Residual rows and the bias piece are fetched TWO steps ahead into registers. (The first version moved 16 columns per
+    // step in 64-byte segments: 19 dependent chains per tile and twice the L1TEX requests; the role trace showed the
+    // epilogue busy 55 k of every 60 k clk.)
     NT_PAIR_TILE_VARS;
     uint8_t* stage = smem + OFF_EPI + warp * EPI_WARP_BYTES;
     const uint32_t tmem_empty_leader = map_to_cta(bar_tmem_empty, 0);
     uint32_t tphase = 0;
-    const int chunks = geo.n_tile / EPI_COLS;
-    const int sub = lane & 3, rsub = lane >> 2;
+    const int rem = geo.n_tile % EPI_COLS;                              // 0 or 16: one narrow step when n_tile is not a multiple of 32
+    const int chunks = geo.n_tile / EPI_COLS + (rem ? 1 : 0);
+    const int sub = lane & 7, rsub = lane >> 3;
     const bool has_resid = MODE != 1 && p.resid != nullptr;
-    const int shared_chunks = 2 * geo.n_tile > 512 ? (2 * geo.n_tile - 512) / EPI_COLS : 0;
+    const int shared_chunks = 2 * geo.n_tile > 512 ? (2 * geo.n_tile - 512) / EPI_COLS : 0;  // overlap of the two TMEM windows
     int tw = 0;
-    float4* bias_s = reinterpret_cast<float4*>(smem + OFF_BIAS + warp * BIAS_WARP_BYTES);
-    int bias_nt = -1;
     for (int tile = first_tile; tile < pair_tiles; tile += tile_stride) {
       const int64_t row0 = (int64_t)tile * (2 * TILE_M) + rank * TILE_M + warp * 32;
       for (int nt = 0; nt < geo.n_tiles; ++nt) {
-        if (MODE != 1 && bias_nt != nt) {  // (re)stage this N tile's bias: once per kernel when d <= 304 (per-chunk global reads cost 18 us)
-          __syncwarp();
-          for (int i = lane; i < geo.n_tile / 4; i += 32) {
-            const int col = nt * geo.n_tile + 4 * i;
-            bias_s[i] = (p.bias != nullptr && col < d) ? ldg4(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          __syncwarp();
-          bias_nt = nt;
-        }
-        auto load_resid = [&](int cc, float4 (&dst)[4]) {
-          const int col = nt * geo.n_tile + cc * EPI_COLS + sub * 4;
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int64_t e = row0 + it * 8 + rsub;
-            dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_resid && cc < chunks && col < d && e < p.E && !(p.ablate & 1)) dst[it] = ldg4_stream(p.resid + e * d + col);
-          }
-        };
-        // TMEM windows alternate between columns [0, n_tile) and [512 - n_tile, 512); where they overlap (n_tile > 256)
-        // this pass drains the overlap first and then hands tensor memory back (see gemm_tc.cu).
+        // TMEM windows alternate between columns [0, n_tile) and [512 - n_tile, 512); where they overlap (n_tile > 256) this
+        // pass drains the overlap first and then hands tensor memory back, so the next tile's MMAs run under the rest of
+        // the epilogue. Window 0 shares its LAST columns, window 1 its first: window 0 therefore puts the narrow step first,
+        // so that the overlap is a whole number of 32-column steps in both.
         const int col_base = tw ? 512 - geo.n_tile : 0;
+        const bool narrow_first = tw == 0 && rem != 0 && shared_chunks > 0;
         const int first = (tw == 0 && shared_chunks > 0) ? chunks - shared_chunks : 0;
         auto chunk_at = [&](int k) { int c = k + first; return c >= chunks ? c - chunks : c; };
-        float4 rA[4], rB[4], rC[4];
-        load_resid(chunk_at(0), rA);
-        load_resid(chunks > 1 ? chunk_at(1) : chunks, rB);
-        load_resid(chunks > 2 ? chunk_at(2) : chunks, rC);
+        auto chunk_c0 = [&](int cc) { return narrow_first ? (cc == 0 ? 0 : rem + EPI_COLS * (cc - 1)) : EPI_COLS * cc; };
+        auto chunk_w = [&](int cc) { return rem == 0 ? EPI_COLS : (narrow_first ? (cc == 0 ? rem : EPI_COLS) : (cc == chunks - 1 ? rem : EPI_COLS)); };
+        auto prefetch = [&](int k, float4 (&dst)[8], float4& bias4) {  // residual rows + bias piece of the k-th step of this pass
+          bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) dst[it] = bias4;
+          if (k >= chunks) return;
+          const int cc = chunk_at(k);
+          const int col = nt * geo.n_tile + chunk_c0(cc) + sub * 4;
+          if (sub * 4 >= chunk_w(cc) || col >= d) return;
+          if (MODE != 1 && p.bias != nullptr) bias4 = ldg4(p.bias + col);
+          if (!has_resid || (p.ablate & 1)) return;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int64_t e = row0 + it * 4 + rsub;
+            if (e < p.E) dst[it] = ldg4_stream(p.resid + e * d + col);
+          }
+        };
+        float4 rA[8], rB[8], bA, bB;
+        prefetch(0, rA, bA);
+        prefetch(1, rB, bB);
         if (threadIdx.x == 0) trace_event(p, 0, tcur, 1, tile);
         mbar_wait_relaxed(bar_tmem_full, tphase);
         tc_fence_after();
         if (threadIdx.x == 0) trace_event(p, 0, tcur, 2, tile);
         if (shared_chunks == 0 && lane == 0) mbar_arrive_cluster(tmem_empty_leader);
-        auto do_chunk = [&](int k, float4 (&cur)[4]) {
+        auto do_chunk = [&](int k, float4 (&cur)[8], float4& bias4) {
           const int cc = chunk_at(k);
+          const int c0 = chunk_c0(cc), w = chunk_w(cc);
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(col_base + c0);
           uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(col_base + cc * EPI_COLS), v);
+          tmem_ld16(taddr, v);
           tmem_ld_wait();
-          if (shared_chunks > 0 && k == shared_chunks - 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (w > 16) {
+            tmem_ld16(taddr + 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(stage + lane * 128 + (((q + 4) ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+          if (shared_chunks > 0 && k == shared_chunks - 1) {  // the overlap has left tensor memory: the next pass may start its MMAs
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
             if (threadIdx.x == 0) trace_event(p, 0, tcur, 3, tile);
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           __syncwarp();
-          const int col = nt * geo.n_tile + cc * EPI_COLS + sub * 4;
-          if (col < d) {
-            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (MODE != 1) bias4 = bias_s[cc * (EPI_COLS / 4) + sub];
+          const int col = nt * geo.n_tile + c0 + sub * 4;
+          if (sub * 4 < w && col < d) {
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int r = it * 8 + rsub;
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + rsub;
               const int64_t e = row0 + r;
               if (e < p.E) {
-                float4 acc = *reinterpret_cast<const float4*>(stage + r * 64 + ((sub ^ ((r >> 1) & 3)) << 4));
+                float4 acc = *reinterpret_cast<const float4*>(stage + r * 128 + ((sub ^ (r & 7)) << 4));
                 if (MODE != 1) {
                   acc = make_float4(acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w);
                   if (DROP) {
@@ -289,12 +300,11 @@ layer_gemm_pair(const Params p) {
             }
           }
           __syncwarp();
-          load_resid(k + 3 < chunks ? chunk_at(k + 3) : chunks, cur);
+          prefetch(k + 2, cur, bias4);
         };
-        for (int k = 0; k < chunks; k += 3) {
-          do_chunk(k, rA);
-          if (k + 1 < chunks) do_chunk(k + 1, rB);
-          if (k + 2 < chunks) do_chunk(k + 2, rC);
+        for (int k = 0; k < chunks; k += 2) {
+          do_chunk(k, rA, bA);
+          if (k + 1 < chunks) do_chunk(k + 1, rB, bB);
         }
         tc_fence_before();
         if (threadIdx.x == 0) trace_event(p, 0, tcur, 4, tile);
