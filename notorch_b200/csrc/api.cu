@@ -63,6 +63,9 @@ int pair_dense_forward(const float*, const void*, const float*, const float*, in
 // wgrad_tma.cu
 size_t tma_wgrad_workspace_bytes(int64_t E, int64_t d);
 int tma_layer_wgrad(const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, float*, void*, size_t, int, cudaStream_t);
+// wgrad_pair.cu (K4b on a CTA pair)
+size_t pair_wgrad_workspace_bytes(int64_t E, int64_t d);
+int pair_layer_wgrad(const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, float*, void*, size_t, int, cudaStream_t);
 // wgrad_tc.cu
 int tc_bias_grad(const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, void*, size_t, cudaStream_t);
 size_t tc_wgrad_workspace_bytes(int64_t E, int64_t d);
@@ -80,6 +83,12 @@ static bool use_pair_kernels() {
 static bool pair_dgrad_enabled() {
   static const bool off = getenv("NOTORCH_B200_PAIR_DGRAD") != nullptr && atoi(getenv("NOTORCH_B200_PAIR_DGRAD")) == 0;
   return !off && use_pair_kernels();
+}
+
+// NOTORCH_B200_WGRAD_V1=1 keeps K4b on the single-CTA kernel of wgrad_tma.cu (timing experiments)
+static bool pair_wgrad_enabled() {
+  static const bool v1 = getenv("NOTORCH_B200_WGRAD_V1") != nullptr && atoi(getenv("NOTORCH_B200_WGRAD_V1")) != 0;
+  return !v1 && use_pair_kernels();
 }
 
 static bool tc_shape_ok(int64_t d, const void* a, const void* b, const void* c, const void* e) {
@@ -185,6 +194,8 @@ extern "C" size_t nt_layer_backward_wgrad_workspace_bytes(int64_t E, int64_t d) 
   size_t tcb = tc_wgrad_workspace_bytes(E, d);
   size_t tmab = tma_wgrad_workspace_bytes(E, d);
   if (tmab > tcb) tcb = tmab;
+  size_t pairb = pair_wgrad_workspace_bytes(E, d);
+  if (pairb > tcb) tcb = pairb;
   return (simt > tcb ? simt : tcb) + 256;
 }
 
@@ -210,12 +221,13 @@ extern "C" int nt_layer_backward_wgrad(const void* g, const void* m, const void*
       set_error("nt_layer_backward_wgrad: a saved m needs the tensor-core path (d %% 4 == 0, 16-byte aligned)");
       return NT_ERR_UNSUPPORTED;
     }
-    int rc = tma_layer_wgrad(static_cast<const float*>(g), static_cast<const float*>(m), E, d, dropout_p, seed, offset, static_cast<float*>(gW),
-                             static_cast<float*>(gb), workspace, workspace_bytes, gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+    auto wgrad = pair_wgrad_enabled() ? pair_layer_wgrad : tma_layer_wgrad;
+    int rc = wgrad(static_cast<const float*>(g), static_cast<const float*>(m), E, d, dropout_p, seed, offset, static_cast<float*>(gW),
+                   static_cast<float*>(gb), workspace, workspace_bytes, gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
     if (rc != NT_ERR_UNSUPPORTED) return rc;
-    // d % 128 == 0: no spare row for the bias gradient -> weight gradient here, column sums of g_u below
-    rc = tma_layer_wgrad(static_cast<const float*>(g), static_cast<const float*>(m), E, d, dropout_p, seed, offset, static_cast<float*>(gW), nullptr,
-                         workspace, workspace_bytes, gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+    // no spare padded feature row for the bias gradient (d % 128 == 0 resp. d % 256 == 0): weight gradient here, column sums of g_u below
+    rc = wgrad(static_cast<const float*>(g), static_cast<const float*>(m), E, d, dropout_p, seed, offset, static_cast<float*>(gW), nullptr,
+               workspace, workspace_bytes, gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
     if (rc) return rc;
     return tc_bias_grad(static_cast<const float*>(g), E, d, dropout_p, seed, offset, static_cast<float*>(gb), workspace, workspace_bytes, st);
   }

@@ -1,0 +1,368 @@
+// K4b on a CTA pair (tcgen05 cta_group::2): the weight gradient with M = 256 feature rows per MMA.
+//
+//   gW^T[i, o] = sum_e m[e, i] * g_u[e, o]        (A = m, B = g_u, both MN-major TF32; see wgrad_tma.cu)
+//
+// Why a pair: the single-CTA kernel (wgrad_tma.cu) is bound by the per-K-block producer chain (wait for the stage, issue the
+// copies, wait for them, hi / lo split, proxy fence, arrive: ~2400 clk) against ~960 clk of MMA work per 16-edge K-block
+// (ncu: tensor pipe 43 % active at d = 300, 32 % at d = 1024). A pair shares the B operand: each CTA stages its own 128
+// feature rows of m plus HALF of the g columns, i.e. 9 instead of 14 chunks per 16 edges at d = 300 (8 instead of 12 at
+// d = 1024), which lets a K-block cover 32 edges in the same shared memory: twice the MMA work (M = 256) per handshake.
+//
+// Roles per CTA (448 threads): warps 0-3 epilogue (drain TMEM once at the end), warp 4 MMA issuer (leader CTA only; both
+// CTAs allocate tensor memory), warp 5 idle, warps 6-13 producers (cp.async copies of "their" 16-byte units, STAGES - 1
+// K-blocks ahead, then the TF32 hi / lo split in place - a thread only touches its own units, so the raw data needs no
+// barrier). Barriers: ready[s] lives in the leader (16 producer warps arrive, the peer's remotely), empty[s] and tmem_full
+// are signalled in both CTAs by tcgen05.commit ... multicast::cluster.
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace nt {
+namespace wgp {
+
+using namespace nt::tc;
+
+constexpr int BLOCK_E = 32;                  // edges per K-block (4 MMA k-steps of 8)
+constexpr int STAGES = 3;
+constexpr int MAX_N = 320;
+constexpr int CHUNK_BYTES = BLOCK_E * 128;   // 32 features x 32 edges
+constexpr int A_CHUNKS = TILE_M / 32;        // 4: this CTA's 128 feature rows of m
+constexpr int B_CHUNKS_MAX = MAX_N / 64;     // 5: this CTA's half of the g columns
+constexpr int PART_BYTES = (A_CHUNKS + B_CHUNKS_MAX) * CHUNK_BYTES;  // 36 KiB (hi or lo)
+constexpr int STAGE_BYTES = 2 * PART_BYTES;                          // 72 KiB
+constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, FIRST_X_WARP = 6, NUM_X_WARPS = 8;
+constexpr int NUM_X_THREADS = NUM_X_WARPS * 32;
+constexpr int THREADS = (FIRST_X_WARP + NUM_X_WARPS) * 32;  // 448
+constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
+
+struct Geometry {
+  int d, m_units, n_tiles, n_tile, n_a, n_b, ones_row, splits, ld_partial;
+  int64_t kb_total, kb_per_split;
+};
+
+static Geometry make_geometry(int64_t E, int d, int sms) {
+  Geometry g;
+  g.d = d;
+  g.m_units = (d + 2 * TILE_M - 1) / (2 * TILE_M);      // pair units of 256 feature rows
+  g.ones_row = (d % (2 * TILE_M) != 0) ? 1 : 0;          // a spare padded feature row of m exists: all ones -> D[d, :] = bias gradient
+  int n_pad = (d + 63) / 64 * 64;                        // each CTA holds half of every MMA's N, in 32-feature chunks
+  if (n_pad <= MAX_N) { g.n_tile = n_pad; g.n_tiles = 1; }
+  else { g.n_tile = 256; g.n_tiles = (n_pad + 255) / 256; }
+  if (g.n_tile <= 256) { g.n_a = g.n_tile; g.n_b = 0; }
+  else { g.n_a = 128; g.n_b = g.n_tile - 128; }
+  g.ld_partial = g.n_tiles * g.n_tile;
+  g.kb_total = (E + BLOCK_E - 1) / BLOCK_E;
+  int64_t units = (int64_t)g.m_units * g.n_tiles;
+  int64_t s = (sms / 2) / units;
+  if (s < 1) s = 1;
+  if (s > g.kb_total) s = g.kb_total > 0 ? g.kb_total : 1;
+  g.splits = (int)s;
+  g.kb_per_split = (g.kb_total + s - 1) / s;
+  return g;
+}
+
+struct Params {
+  const float* m;  // [E, d]
+  const float* g;  // [E, d]
+  float* partial;  // [splits][m_units * 256 (i)][ld_partial (o)]
+  int64_t E;
+  Geometry geo;
+  float drop_p, inv_keep;
+  uint32_t drop_thr;
+  uint64_t seed, offset;
+  int products;
+};
+
+// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both MN-major, M = 256 (pair)
+__device__ __forceinline__ uint32_t make_idesc_pair_mn(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (3u << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("notorch_b200: dynamic shared memory base is not 1 KiB aligned\n");
+    __trap();
+  }
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t bar_ready = sbase + OFF_BAR;         // [STAGES] (leader's copy is the live one)
+  const uint32_t bar_empty = bar_ready + 8 * STAGES;  // [STAGES]
+  const uint32_t bar_tmem_full = bar_empty + 8 * STAGES;
+  const uint32_t tmem_slot = bar_tmem_full + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * STAGES + 1));
+
+  const Geometry& geo = p.geo;
+  const int d = geo.d;
+  const int units = geo.m_units * geo.n_tiles;
+  const int pair_id = blockIdx.x >> 1;
+  const int unit = pair_id % units;  // pairs of one edge range are adjacent: the g tiles they share hit in L2
+  const int split = pair_id / units;
+  const int mu = unit % geo.m_units, nt = unit / geo.m_units;
+  const int i0 = mu * 2 * TILE_M + (int)rank * TILE_M;      // this CTA's 128 feature rows of m
+  const int o0 = nt * geo.n_tile;
+  const int ha = geo.n_a / 2, hb = geo.n_b / 2;             // this CTA's share of the two MMAs' N (multiples of 32)
+  const int b_chunks = (ha + hb) / 32;
+  const int64_t kb_lo = (int64_t)split * geo.kb_per_split;
+  int64_t kb_hi = kb_lo + geo.kb_per_split;
+  if (kb_hi > geo.kb_total) kb_hi = geo.kb_total;
+  const int64_t nkb = kb_hi > kb_lo ? kb_hi - kb_lo : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_ready + 8 * s, 2 * NUM_X_WARPS);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < NUM_EPI_WARPS) {
+    // ===================================== EPILOGUE (once) =====================================
+    const int i = i0 + warp * 32 + lane;
+    float* dst = p.partial + ((int64_t)split * geo.m_units * 2 * TILE_M + i) * geo.ld_partial + o0;
+    if (nkb > 0) {
+      mbar_wait_relaxed(bar_tmem_full, 0);
+      tc_fence_after();
+      for (int cc = 0; cc < geo.n_tile / 16; ++cc) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(dst + cc * 16 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    } else {
+      for (int c = 0; c < geo.n_tile; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================================== MMA ISSUER (leader CTA only) =====================================
+    if (leader) {
+      const uint32_t idesc_a = make_idesc_pair_mn(geo.n_a);
+      const uint32_t idesc_b = make_idesc_pair_mn(geo.n_b > 0 ? geo.n_b : 64);
+      int s = 0;
+      uint32_t ph = 0;
+#pragma unroll 1
+      for (int64_t kb = 0; kb < nkb; ++kb) {
+        mbar_wait(bar_ready + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st0 = sbase + s * STAGE_BYTES;
+          const uint32_t a_hi = mnmajor_desc_lo(st0, CHUNK_BYTES), b_hi = mnmajor_desc_lo(st0 + A_CHUNKS * CHUNK_BYTES, CHUNK_BYTES);
+          const uint32_t a_lo = mnmajor_desc_lo(st0 + PART_BYTES, CHUNK_BYTES), b_lo = mnmajor_desc_lo(st0 + PART_BYTES + A_CHUNKS * CHUNK_BYTES, CHUNK_BYTES);
+          const uint32_t d1 = tmem_base + (uint32_t)geo.n_a;
+          const uint32_t boff = (uint32_t)(ha / 32) * (CHUNK_BYTES >> 4);  // this CTA's columns of the second MMA follow its ha / 32 chunks of the first
+#pragma unroll
+          for (int j = 0; j < BLOCK_E / 8; ++j) {
+            const uint32_t k16 = j * (1024u >> 4);  // next 8 edges = the next two 4-row swizzle atoms of every chunk
+            const uint32_t acc = (kb | j) != 0 ? 1u : 0u;
+            if (p.products == 3) {
+              umma2_tf32_lo(tmem_base, a_lo + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, acc);
+              umma2_tf32_lo(tmem_base, a_hi + k16, b_lo + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, 1u);
+              umma2_tf32_lo(tmem_base, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, 1u);
+              if (geo.n_b > 0) {
+                umma2_tf32_lo(d1, a_lo + k16, b_hi + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, acc);
+                umma2_tf32_lo(d1, a_hi + k16, b_lo + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, 1u);
+                umma2_tf32_lo(d1, a_hi + k16, b_hi + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, 1u);
+              }
+            } else {
+              umma2_tf32_lo(tmem_base, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, acc);
+              if (geo.n_b > 0) umma2_tf32_lo(d1, a_hi + k16, b_hi + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, acc);
+            }
+          }
+          umma2_commit_both(bar_empty + 8 * s);
+          if (kb == nkb - 1) umma2_commit_both(bar_tmem_full);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= FIRST_X_WARP) {
+    // ===================================== PRODUCER: cp.async tiles, then hi / lo split in place =====================================
+    // Thread pt owns the 16-byte units u = pt + 256 k of every stage: chunk u >> 8 (32 features x 32 edges = 256 units), edge
+    // row (u & 255) >> 3, physical slot u & 7 (the 32-byte-unit XOR swizzle undone to find the feature).
+    const int pt = threadIdx.x - FIRST_X_WARP * 32;  // 0..255: one unit per chunk
+    constexpr int MAX_UNITS = A_CHUNKS + B_CHUNKS_MAX;  // 9
+    const int n_chunks = A_CHUNKS + b_chunks;
+    const int r = pt >> 3, pos = pt & 7;
+    const int c16 = ((((pos >> 1) ^ (r & 3)) << 1) | (pos & 1));  // logical 16-byte chunk inside the 128-byte feature row
+    const int E_i = (int)p.E;
+    const uint32_t ready_leader = map_to_cta(bar_ready, 0);
+    // the all-ones feature row of m (bias gradient) lives in this CTA's A tile iff i0 <= d < i0 + 128
+    const bool ones_here = geo.ones_row && d >= i0 && d < i0 + TILE_M;
+    const int ones_chunk = ones_here ? (d - i0) / 32 : -1, ones_c16 = ones_here ? ((d - i0) % 32) / 4 : -1;
+
+    auto feature_of = [&](int chunk) {  // first feature of this thread's unit in chunk `chunk`
+      if (chunk < A_CHUNKS) return i0 + 32 * chunk + 4 * c16;
+      const int f = 32 * (chunk - A_CHUNKS);  // offset inside this CTA's share of the g columns
+      return f < ha ? o0 + (int)rank * ha + f + 4 * c16 : o0 + geo.n_a + (int)rank * hb + (f - ha) + 4 * c16;
+    };
+    auto issue = [&](int64_t kb, int s) {
+      const int e = (int)((kb_lo + kb) * BLOCK_E) + r;
+      const uint32_t dst = sbase + s * STAGE_BYTES + pt * 16;
+#pragma unroll
+      for (int k = 0; k < MAX_UNITS; ++k) {
+        if (k < n_chunks) {
+          const int f = feature_of(k);
+          const bool ok = e < E_i && f < d;
+          const float* src = (k < A_CHUNKS ? p.m : p.g) + (ok ? (int64_t)e * d + f : 0);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + k * CHUNK_BYTES), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+      }
+    };
+    int ls = 0, cs = 0;
+    uint32_t lph = 0;
+    int64_t lkb = 0;
+    auto load_step = [&]() {
+      if (lkb < nkb) {
+        mbar_wait(bar_empty + 8 * ls, lph ^ 1);
+        issue(lkb, ls);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      ++lkb;
+      if (++ls == STAGES) { ls = 0; lph ^= 1; }
+    };
+#pragma unroll 1
+    for (int j = 0; j < STAGES - 1; ++j) load_step();
+#pragma unroll 1
+    for (int64_t kb = 0; kb < nkb; ++kb) {
+      const int e = (int)((kb_lo + kb) * BLOCK_E) + r;
+      uint8_t* hi = smem + cs * STAGE_BYTES + pt * 16;
+      uint8_t* lo = hi + PART_BYTES;
+      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+      float4 v[MAX_UNITS];
+#pragma unroll
+      for (int k = 0; k < MAX_UNITS; ++k)  // all reads first: the in-place stores below must not serialise the units
+        if (k < n_chunks) v[k] = *reinterpret_cast<const float4*>(hi + k * CHUNK_BYTES);
+#pragma unroll
+      for (int k = 0; k < MAX_UNITS; ++k) {
+        if (k < n_chunks) {
+          if (k == ones_chunk) {
+            if (c16 == ones_c16 && e < E_i) v[k].x = 1.f;
+          } else if (DROP && k >= A_CHUNKS) {
+            const int o = feature_of(k);
+            if (e < E_i && o < d) {
+              float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)o, p.drop_thr, p.inv_keep);
+              v[k] = make_float4(v[k].x * sc.x, v[k].y * sc.y, v[k].z * sc.z, v[k].w * sc.w);
+            }
+          }
+          const float4 h4 = make_float4(tf32_rna(v[k].x), tf32_rna(v[k].y), tf32_rna(v[k].z), tf32_rna(v[k].w));
+          const float4 l4 = make_float4(tf32_rna(v[k].x - h4.x), tf32_rna(v[k].y - h4.y), tf32_rna(v[k].z - h4.z), tf32_rna(v[k].w - h4.w));
+          *reinterpret_cast<float4*>(hi + k * CHUNK_BYTES) = h4;
+          *reinterpret_cast<float4*>(lo + k * CHUNK_BYTES) = l4;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(bar_ready + 8 * cs);
+        else mbar_arrive_cluster(ready_leader + 8 * cs);
+      }
+      if (++cs == STAGES) cs = 0;
+      load_step();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may retire while its partner can still read its shared memory or signal its barriers
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// gW[o,i] = sum_z partial[z][i][o] in ascending z; gb[o] = the all-ones row i == d when present.
+__global__ void __launch_bounds__(256) wgrad_pair_reduce(const float* __restrict__ partial, Geometry geo, float* __restrict__ gW, float* __restrict__ gb) {
+  const int d = geo.d;
+  const int rows = d + (geo.ones_row ? 1 : 0);
+  int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (int64_t)rows * d) return;
+  const int i = (int)(t / d), o = (int)(t - (int64_t)i * d);  // o fastest: coalesced reads of the partial planes
+  const int64_t plane = (int64_t)geo.m_units * 2 * TILE_M * geo.ld_partial;
+  const float* src = partial + (int64_t)i * geo.ld_partial + o;
+  float s = 0.f;
+  for (int z = 0; z < geo.splits; ++z) s += __ldg(src + z * plane);
+  if (i < d) gW[(int64_t)o * d + i] = s;
+  else if (gb) gb[o] = s;
+}
+
+}  // namespace wgp
+
+size_t pair_wgrad_workspace_bytes(int64_t E, int64_t d) {
+  if (d % 4 != 0 || E <= 0) return 0;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  wgp::Geometry geo = wgp::make_geometry(E, (int)d, sms);
+  return (size_t)geo.splits * geo.m_units * 2 * tc::TILE_M * geo.ld_partial * sizeof(float) + 1024;
+}
+
+// returns NT_ERR_UNSUPPORTED when the bias gradient cannot ride along (d % 256 == 0) and gb is requested
+int pair_layer_wgrad(const float* g, const float* m, int64_t E, int64_t d, float drop_p, uint64_t seed, uint64_t offset, float* gW, float* gb,
+                     void* workspace, size_t workspace_bytes, int products, cudaStream_t st) {
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  wgp::Params p{};
+  p.geo = wgp::make_geometry(E, (int)d, sms);
+  if (gb && !p.geo.ones_row) return NT_ERR_UNSUPPORTED;
+  if (workspace_bytes < pair_wgrad_workspace_bytes(E, d)) {
+    set_error("pair_layer_wgrad: workspace too small");
+    return NT_ERR_WORKSPACE;
+  }
+  p.m = m;
+  p.g = g;
+  p.partial = static_cast<float*>(workspace);
+  p.E = E;
+  p.products = products;
+  p.drop_p = drop_p;
+  p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  double t = (double)drop_p * 4294967296.0;
+  p.drop_thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  p.seed = seed;
+  p.offset = offset;
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(wgp::wgrad_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgp::SMEM_BYTES);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(wgp::wgrad_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgp::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_pair_kernel)");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * p.geo.splits * p.geo.m_units * p.geo.n_tiles));
+  cfg.blockDim = dim3(wgp::THREADS);
+  cfg.dynamicSmemBytes = wgp::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = drop_p > 0.f ? cudaLaunchKernelEx(&cfg, wgp::wgrad_pair_kernel<true>, p) : cudaLaunchKernelEx(&cfg, wgp::wgrad_pair_kernel<false>, p);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(wgrad_pair_kernel)");
+  const int64_t total = (d + (p.geo.ones_row ? 1 : 0)) * d;
+  wgp::wgrad_pair_reduce<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(p.partial, p.geo, gW, gb);
+  NT_LAUNCH_CHECK("pair_layer_wgrad", 2);
+  return NT_OK;
+}
+
+}  // namespace nt
