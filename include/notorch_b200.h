@@ -126,6 +126,17 @@ int nt_seg_reduce_ex(const void* x, int64_t d, const int32_t* rowptr, const int3
                      void* out, int dtype, nt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * ELL acceleration of the segmented reductions (same arithmetic and accumulation order as nt_seg_reduce / nt_seg_reduce_ex):
+ * nt_csr_to_ell writes ell[s] = the first four item ids of segment s (ascending, -1 padded; int32 x 4, 16-byte aligned), built
+ * once per batch next to the CSR; nt_seg_reduce_ell reads all row indices of a segment with one load (degree <= 4 for molecular
+ * graphs; longer segments continue through rowptr / perm). Replaces the same reference lines as nt_seg_reduce.
+ * ---------------------------------------------------------------------------------------------- */
+int nt_csr_to_ell(const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int32_t* ell, nt_stream_t stream);
+int nt_seg_reduce_ell(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, const int32_t* ell,
+                      int64_t num_segments, int act, float act_param, int mean, float scale, const void* base,
+                      const void* dact_of, void* out, int dtype, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * out[i,:] = (base ? base[i,:] : 0) + scale * x[idx[i],:] / (mean_rowptr ? max(count(idx[i]),1) : 1)
  * K0 edge_init      : chemprop.py:83  h0 = x_v[src] + x_e            (base = x_e, x = x_v, idx = src)
  * backward of K1/K3 : g[e] = gE[e] + g_node[dst[e]] (/ indeg for mean);  g_x[v] = gH[batch[v]] (/count)

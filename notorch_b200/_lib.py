@@ -34,6 +34,8 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "nt_build_csr": (_int, [_i64p, _i64, _i64, _i32p, _i32p, _i32p, _i32p, _vp, _sz, _vp]),
     "nt_seg_reduce": (_int, [_vp, _i64, _i32p, _i32p, _i64, _int, _f32, _int, _f32, _vp, _int, _vp]),
     "nt_seg_reduce_ex": (_int, [_vp, _i64, _i32p, _i32p, _i64, _int, _f32, _int, _f32, _vp, _vp, _vp, _int, _vp]),
+    "nt_csr_to_ell": (_int, [_i32p, _i32p, _i64, _i32p, _vp]),
+    "nt_seg_reduce_ell": (_int, [_vp, _i64, _i32p, _i32p, _i32p, _i64, _int, _f32, _int, _f32, _vp, _vp, _vp, _int, _vp]),
     "nt_dense_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _u64, _u64, _vp, _int, _int, _vp]),
     "nt_gather_add": (_int, [_vp, _vp, _i32p, _i32p, _i64, _i64, _f32, _vp, _int, _vp]),
     "nt_weight_image_bytes": (_sz, [_i64]),

@@ -88,6 +88,79 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// seg_reduce over an ELL copy of the CSR: ell[s] = the first four item ids of segment s (ascending, -1 padded)
+// ------------------------------------------------------------------------------------------------
+// Molecular graphs have in/out-degree <= 4, so one 16-byte load yields every row index of the segment and the four row
+// loads are issued together: the rowptr -> perm -> row chain of seg_reduce_v4 (three dependent DRAM latencies, 60 % of HBM
+// peak) becomes the two-level chain of the gather kernels (82-98 %). Segments longer than four continue through rowptr /
+// perm. The accumulation order (ascending item id, starting from 0) is unchanged, so results stay bit-identical.
+__global__ void __launch_bounds__(ROW_THREADS) csr_to_ell_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, int64_t S,
+                                                                 int4* __restrict__ ell) {
+  int64_t s = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
+  if (s >= S) return;
+  const int lo = __ldg(rowptr + s), hi = __ldg(rowptr + s + 1);
+  int v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = lo + j < hi ? (perm ? __ldg(perm + lo + j) : lo + j) : -1;
+  ell[s] = make_int4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void __launch_bounds__(ROW_THREADS, 4) seg_reduce_ell_v4(const float* __restrict__ x, int d, int chunks, const int32_t* __restrict__ rowptr,
+                                                                   const int32_t* __restrict__ perm, const int4* __restrict__ ell, int64_t total,
+                                                                   int act, float act_param, int mean, float scale, const float* __restrict__ base,
+                                                                   const float* __restrict__ dact_of, float* __restrict__ out) {
+  const int pre_act = dact_of ? NT_ACT_IDENTITY : act;
+  const int64_t t0 = (int64_t)blockIdx.x * (ROW_THREADS * SEG_ITEMS) + threadIdx.x;
+  int s[SEG_ITEMS], c[SEG_ITEMS], lo[SEG_ITEMS], hi[SEG_ITEMS];
+  int4 nb[SEG_ITEMS];
+  bool live[SEG_ITEMS];
+#pragma unroll
+  for (int k = 0; k < SEG_ITEMS; ++k) {
+    const int64_t t = t0 + (int64_t)k * ROW_THREADS;
+    live[k] = t < total;
+    s[k] = live[k] ? (int)(t / chunks) : 0;
+    c[k] = live[k] ? (int)(t - (int64_t)s[k] * chunks) * 4 : 0;
+    nb[k] = live[k] ? __ldg(ell + s[k]) : make_int4(-1, -1, -1, -1);
+    lo[k] = live[k] ? __ldg(rowptr + s[k]) : 0;
+    hi[k] = live[k] ? __ldg(rowptr + s[k] + 1) : 0;
+  }
+  float4 v[SEG_ITEMS][4];
+#pragma unroll
+  for (int k = 0; k < SEG_ITEMS; ++k) {
+    const int id[4] = {nb[k].x, nb[k].y, nb[k].z, nb[k].w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (id[u] >= 0) v[k][u] = ldg4(x + (int64_t)id[u] * d + c[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < SEG_ITEMS; ++k) {
+    if (!live[k]) continue;
+    const int id[4] = {nb[k].x, nb[k].y, nb[k].z, nb[k].w};
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)  // ascending item order within the segment: bit-identical to a sequential scatter_add_
+      if (id[u] >= 0) a = add4(a, pre_act != NT_ACT_IDENTITY ? act_fwd4(v[k][u], pre_act, act_param) : v[k][u]);
+    for (int j = lo[k] + 4; j < hi[k]; ++j) {  // degree > 4: the rest of the segment through the CSR
+      const int rr = perm ? __ldg(perm + j) : j;
+      const float4 w = ldg4(x + (int64_t)rr * d + c[k]);
+      a = add4(a, pre_act != NT_ACT_IDENTITY ? act_fwd4(w, pre_act, act_param) : w);
+    }
+    if (mean) {
+      const float cnt = (float)max(hi[k] - lo[k], 1);
+      a = make_float4(a.x / cnt, a.y / cnt, a.z / cnt, a.w / cnt);
+    }
+    if (scale != 1.f) a = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+    if (dact_of) {
+      const float4 hv = ldg4(dact_of + (int64_t)s[k] * d + c[k]);
+      a = make_float4(a.x * act_bwd(hv.x, act, act_param), a.y * act_bwd(hv.y, act, act_param), a.z * act_bwd(hv.z, act, act_param),
+                      a.w * act_bwd(hv.w, act, act_param));
+    }
+    if (base) a = add4(ldg4_stream(base + (int64_t)s[k] * d + c[k]), a);
+    stg4(out + (int64_t)s[k] * d + c[k], a);
+  }
+}
+
 // scalar fallback for d % 4 != 0 (or unaligned bases): one thread per (segment, element)
 __global__ void __launch_bounds__(ROW_THREADS) seg_reduce_s(const float* __restrict__ x, int d, const int32_t* __restrict__ rowptr,
                                                              const int32_t* __restrict__ perm, int64_t total, int act, float act_param, int mean,
@@ -199,9 +272,9 @@ static bool vec_ok(int64_t d, const void* a, const void* b = nullptr, const void
   return d % 4 == 0 && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(e) && aligned16(f);
 }
 
-static int seg_reduce_impl(const char* fn, const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int act,
-                           float act_param, int mean, float scale, const void* base, const void* dact_of, void* out, int dtype,
-                           nt_stream_t stream) {
+static int seg_reduce_impl(const char* fn, const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, const int32_t* ell,
+                           int64_t num_segments, int act, float act_param, int mean, float scale, const void* base, const void* dact_of, void* out,
+                           int dtype, nt_stream_t stream) {
   NT_CHECK_ARG(dtype == NT_F32 || dtype == NT_BF16, "%s: bad dtype", fn);
   if (dtype != NT_F32) { set_error("%s: only NT_F32 is implemented", fn); return NT_ERR_UNSUPPORTED; }
   NT_CHECK_ARG(d > 0 && d < (1 << 20) && num_segments >= 0 && num_segments < INT32_MAX, "%s: bad sizes", fn);
@@ -217,7 +290,10 @@ static int seg_reduce_impl(const char* fn, const void* x, int64_t d, const int32
     int chunks = (int)(d / 4);
     int64_t total = num_segments * chunks;
     unsigned grid = (unsigned)cdiv(total, ROW_THREADS * SEG_ITEMS);
-    if (perm) seg_reduce_v4<true><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);
+    if (ell && aligned16(ell))
+      seg_reduce_ell_v4<<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, reinterpret_cast<const int4*>(ell), total, act, act_param, mean,
+                                                      scale, bf, df, of);
+    else if (perm) seg_reduce_v4<true><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);
     else seg_reduce_v4<false><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);
   } else {
     int64_t total = num_segments * d;
@@ -229,12 +305,29 @@ static int seg_reduce_impl(const char* fn, const void* x, int64_t d, const int32
 
 extern "C" int nt_seg_reduce(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int act, float act_param,
                              int mean, float scale, void* out, int dtype, nt_stream_t stream) {
-  return seg_reduce_impl("nt_seg_reduce", x, d, rowptr, perm, num_segments, act, act_param, mean, scale, nullptr, nullptr, out, dtype, stream);
+  return seg_reduce_impl("nt_seg_reduce", x, d, rowptr, perm, nullptr, num_segments, act, act_param, mean, scale, nullptr, nullptr, out, dtype, stream);
 }
 
 extern "C" int nt_seg_reduce_ex(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int act, float act_param,
                                 int mean, float scale, const void* base, const void* dact_of, void* out, int dtype, nt_stream_t stream) {
-  return seg_reduce_impl("nt_seg_reduce_ex", x, d, rowptr, perm, num_segments, act, act_param, mean, scale, base, dact_of, out, dtype, stream);
+  return seg_reduce_impl("nt_seg_reduce_ex", x, d, rowptr, perm, nullptr, num_segments, act, act_param, mean, scale, base, dact_of, out, dtype, stream);
+}
+
+extern "C" int nt_seg_reduce_ell(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, const int32_t* ell, int64_t num_segments, int act,
+                                 float act_param, int mean, float scale, const void* base, const void* dact_of, void* out, int dtype,
+                                 nt_stream_t stream) {
+  NT_CHECK_ARG(ell, "nt_seg_reduce_ell: null ell");
+  return seg_reduce_impl("nt_seg_reduce_ell", x, d, rowptr, perm, ell, num_segments, act, act_param, mean, scale, base, dact_of, out, dtype, stream);
+}
+
+extern "C" int nt_csr_to_ell(const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int32_t* ell, nt_stream_t stream) {
+  NT_CHECK_ARG(num_segments >= 0 && num_segments < INT32_MAX, "nt_csr_to_ell: bad sizes");
+  if (num_segments == 0) return NT_OK;
+  NT_CHECK_ARG(rowptr && ell && aligned16(ell), "nt_csr_to_ell: null or unaligned pointer");
+  csr_to_ell_kernel<<<(unsigned)cdiv(num_segments, ROW_THREADS), ROW_THREADS, 0, as_stream(stream)>>>(rowptr, perm, num_segments,
+                                                                                                   reinterpret_cast<int4*>(ell));
+  NT_LAUNCH_CHECK("nt_csr_to_ell", 1);
+  return NT_OK;
 }
 
 extern "C" int nt_gather_add(const void* base, const void* x, const int32_t* idx, const int32_t* mean_rowptr, int64_t n, int64_t d, float scale,

@@ -175,6 +175,18 @@ class SegmentCSR:
     keys32: Tensor  # [n] int32
     num_segments: int
     status: Tensor | None = None  # [1] int32 device flag, bit 0 = key out of range
+    ell: Tensor | None = None  # [S, 4] int32: first four item ids of every segment (-1 padded), see nt_csr_to_ell
+
+
+def _ell_of(csr: "SegmentCSR") -> Tensor | None:
+    """ELL copy of a permuted CSR (built once per batch, cached on the CSR object); contiguous segments keep the plain kernel."""
+    if csr.perm is None or csr.num_segments == 0:
+        return None
+    if csr.ell is None:
+        ell = torch.empty((csr.num_segments, 4), dtype=torch.int32, device=csr.rowptr.device)
+        _run("ell:nt_csr_to_ell", _lib.lib().nt_csr_to_ell, _p(csr.rowptr), _p(csr.perm), csr.num_segments, _p(ell), _stream())
+        csr.ell = ell
+    return csr.ell
 
 
 _STATUS_SLOTS = 256
@@ -346,6 +358,11 @@ def _seg_reduce_raw(x: Tensor, csr: SegmentCSR, act: int = 0, act_param: float =
                     tag: str = "K1") -> Tensor:
     d = x.shape[1]
     out = torch.empty((csr.num_segments, d), dtype=x.dtype, device=x.device)
+    ell = _ell_of(csr)
+    if ell is not None:
+        _run(f"{tag}:nt_seg_reduce", _lib.lib().nt_seg_reduce_ell, _p(x), d, _p(csr.rowptr), _p(csr.perm), _p(ell), csr.num_segments, act, act_param,
+             int(mean), scale, None, None, _p(out), NT_F32, _stream())
+        return out
     _run(f"{tag}:nt_seg_reduce", _lib.lib().nt_seg_reduce, _p(x), d, _p(csr.rowptr), _p(csr.perm), csr.num_segments, act, act_param, int(mean),
          scale, _p(out), NT_F32, _stream())
     return out
@@ -568,6 +585,11 @@ def _seg_reduce_ex_raw(x: Tensor, seg: SegmentCSR, act: int, act_param: float, m
                        tag: str) -> Tensor:
     d = x.shape[1]
     out = torch.empty((seg.num_segments, d), dtype=x.dtype, device=x.device)
+    ell = _ell_of(seg)
+    if ell is not None:
+        _run(f"{tag}:nt_seg_reduce_ex", _lib.lib().nt_seg_reduce_ell, _p(x), d, _p(seg.rowptr), _p(seg.perm), _p(ell), seg.num_segments, act,
+             act_param, int(mean), 1.0, _p(base), _p(dact_of), _p(out), NT_F32, _stream())
+        return out
     _run(f"{tag}:nt_seg_reduce_ex", _lib.lib().nt_seg_reduce_ex, _p(x), d, _p(seg.rowptr), _p(seg.perm), seg.num_segments, act, act_param,
          int(mean), 1.0, _p(base), _p(dact_of), _p(out), NT_F32, _stream())
     return out
