@@ -473,7 +473,13 @@ def run_ours(args, wl, batch):
         try:
             graphs[False] = capture(resident, False)
             if not args.no_e2e:
-                graphs[True] = capture(host, True)
+                # end-to-end leg: two device input buffers; the H2D copy of step t + 1 (pinned host -> device, on a copy stream)
+                # overlaps the compute of step t, the way a training loop prefetches its next batch
+                devbuf = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+                for b in devbuf:
+                    for k, v in host.items():
+                        b[k].copy_(v)
+                graphs[True] = (capture(devbuf[0], False), capture(devbuf[1], False))
             launch_mode = "cuda_graph"
         except Exception as exc:  # capture is an optimisation, never a requirement
             print(f"bench.py: CUDA graph capture failed ({type(exc).__name__}: {exc}); launching eagerly", file=sys.stderr)
@@ -490,12 +496,38 @@ def run_ours(args, wl, batch):
         ev0.record()
         last = None
         g = graphs.get(from_host)
+        if g is not None and from_host:
+            cstream = torch.cuda.Stream()
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+            def prefetch(i: int):
+                with torch.cuda.stream(cstream):
+                    for k, v in host.items():
+                        devbuf[i][k].copy_(v, non_blocking=True)
+                    ready[i].record(cstream)
+
+            cstream.wait_stream(torch.cuda.current_stream())
+            prefetch(0)
+            for t in range(nsteps):
+                i = t & 1
+                torch.cuda.current_stream().wait_event(ready[i])
+                replay(g[i])
+                if t + 1 < nsteps:
+                    prefetch(1 - i)  # its previous reader (step t - 1) has completed: we synchronised on its loss
+                torch.cuda.current_stream().synchronize()
+                last = float(g[i][1])  # the loss, copied device -> pinned host inside the graph
+            ev1.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            ms = max(ev0.elapsed_time(ev1), wall * 1e3)
+            if world > 1:
+                tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms = float(tt)
+            return ms, last
         for _ in range(nsteps):
             if g is not None:
                 replay(g)
-                if from_host:
-                    torch.cuda.current_stream().synchronize()
-                    last = float(g[1])  # the loss, copied device -> pinned host inside the graph
                 continue
             loss = step(src, from_host)
             if from_host:
@@ -531,10 +563,13 @@ def run_ours(args, wl, batch):
         if True not in graphs:
             for _ in range(2):
                 step(host, True)
+        else:
+            timed(2, host, True)
         e2e_ms, _ = timed(args.steps, host, True)
         e2e = {"value": world * batch * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": e2e_ms / args.steps,
-               "inputs": "int64 atom/bond type ids [V,7],[E,2] + packed int32 topology (counts, local edge_index, local rev_index), pinned host memory"}
+               "inputs": "int64 atom/bond type ids [V,7],[E,2] + packed int32 topology (counts, local edge_index, local rev_index), pinned host memory; "
+                         "the copy of step t+1 overlaps the compute of step t (two device buffers, copy stream); the loss is read back every step"}
 
     ops.set_index_validation("deferred")
     # ---- per-kernel CUDA-event timing (a separate instrumented pass over the same steps, launched eagerly) ----
