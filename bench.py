@@ -600,9 +600,22 @@ def run_ours(args, wl, batch):
                 row["alg_tflops"] = gemm_flops(E, d) / (rec["avg_ms"] * 1e-3) / 1e12
             kernels.append(row)
         dom = next((k for k in kernels if "alg_bytes" in k), None)
+        # DRAM traffic and tensor-pipe activity per launch come from the committed ncu capture of this same step (a profiler
+        # cannot run inside the timed process): profiles/r01_ncu_traffic.json, written by the round's evidence pass
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        except Exception:
+            pass
+        for k in kernels:
+            rec = ncu.get(k["kernel"])
+            if rec and wl is WORKLOADS["c2"] and batch == wl["batch"]:
+                k["ncu_dram_bytes"] = rec["dram_bytes_per_launch"]
+                k["ncu_tensor_pipe_active_pct"] = rec["tensor_pipe_active_pct"]
         if dom is not None:
             roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"],
-                    "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": dom["avg_ms"],
+                    "traffic": dom.get("ncu_dram_bytes"), "traffic_source": ncu.get("_source") if "ncu_dram_bytes" in dom else None,
+                    "tensor_pipe_active_pct": dom.get("ncu_tensor_pipe_active_pct"), "peak_source": peak_src, "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": dom["avg_ms"],
                     "measured_over": f"{nprof} instrumented steps after the timed region (CUDA events around every C-ABI call)",
                     "step_alg_bytes": alg["step"], "step_hbm_frac": alg["step"] / (ms_total / args.steps * 1e-3) / 1e9 / hbm_peak}
         if args.kernel_table:
