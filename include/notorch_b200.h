@@ -18,7 +18,8 @@
  *  - Thread-safe and re-entrant (PyTorch calls backward from its autograd thread).
  *  - Index tensors handed to the floating-point kernels are int32 (built once per batch by
  *    nt_graph_prepare from the reference's int64 tensors); sizes must be < 2^31.
- *  - dtype: NT_F32 only in this round (NT_BF16 is reserved and returns NT_ERR_UNSUPPORTED).
+ *  - dtype: NT_F32 activations only in this round (NT_BF16 selects the bf16 weight image in nt_weight_prepare and returns
+ *    NT_ERR_UNSUPPORTED everywhere else); the bf16 OPERAND mode is a gemm_mode, see NT_GEMM_BF16.
  */
 #ifndef NOTORCH_B200_H_
 #define NOTORCH_B200_H_
@@ -58,7 +59,11 @@ enum nt_act {
 enum nt_gemm_mode {
   NT_GEMM_TF32X3 = 0, /* tcgen05 tensor cores, 3xTF32 error-compensated split, fp32 accumulate in TMEM */
   NT_GEMM_FP32 = 1,   /* fp32 FFMA on CUDA cores (strict fp32; also used when d % 4 != 0) */
-  NT_GEMM_TF32 = 2    /* tcgen05, single-pass TF32 (10-bit mantissa; NOT within the fp32 parity bound) */
+  NT_GEMM_TF32 = 2,   /* tcgen05, single-pass TF32 (10-bit mantissa; NOT within the fp32 parity bound) */
+  NT_GEMM_BF16 = 3    /* BASELINE configs[4]: W_h and the message operand rounded to bf16, ONE tcgen05.mma.kind::f16 pass, fp32
+                         accumulation in TMEM (K2, K4a, nt_dense_forward); the weight gradient runs as a single TF32 pass.
+                         Activations stay fp32 in HBM. Weight image: nt_weight_prepare(..., dtype = NT_BF16). Stated bound:
+                         rel-to-max 2e-2 on embeddings, 5e-2 on gradients (tests/test_bf16_mode.py) */
 };
 
 const char* nt_last_error_string(void);

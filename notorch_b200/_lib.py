@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libnotorch_b200.so")
 
 # enums of include/notorch_b200.h
 NT_F32, NT_BF16 = 0, 1
-GEMM_TF32X3, GEMM_FP32, GEMM_TF32 = 0, 1, 2
+GEMM_TF32X3, GEMM_FP32, GEMM_TF32, GEMM_BF16 = 0, 1, 2, 3
 ACT_IDENTITY, ACT_RELU, ACT_LEAKY_RELU, ACT_ELU, ACT_SILU, ACT_GELU, ACT_TANH = range(7)
 
 _i32p, _i64p, _vp = C.c_void_p, C.c_void_p, C.c_void_p  # raw device addresses

@@ -55,7 +55,7 @@ int tc_layer_forward(const float*, const float*, const int32_t*, const int32_t*,
 int tc_layer_dgrad(const float*, const void*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
 // gemm_pair.cu (second-generation K2 / K4a: CTA pairs, copy-engine gathers)
 void pair_set_trace_buffer(void* ptr);
-int pair_weight_prepare(const float*, int64_t, int, void*, cudaStream_t);
+int pair_weight_prepare(const float*, int64_t, int, void*, int, cudaStream_t);
 int pair_layer_forward(const float*, const float*, const int32_t*, const int32_t*, const void*, const float*, int64_t, int64_t, int64_t, int, float, int,
                        float, uint64_t, uint64_t, float*, float*, int, cudaStream_t);
 int pair_layer_dgrad(const float*, const void*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
@@ -91,6 +91,11 @@ static bool pair_wgrad_enabled() {
   return !v1 && use_pair_kernels();
 }
 
+// MMA passes per product: 3 = 3xTF32, 1 = single TF32 pass, 0 = bf16 operands (one kind::f16 pass)
+static int products_of(int gemm_mode) { return gemm_mode == NT_GEMM_TF32 ? 1 : gemm_mode == NT_GEMM_BF16 ? 0 : 3; }
+// the weight gradient has no bf16 kernel: in bf16 mode it runs as a single TF32 pass (no less precise than bf16 operands)
+static int wgrad_products_of(int gemm_mode) { return gemm_mode == NT_GEMM_TF32X3 ? 3 : 1; }
+
 static bool tc_shape_ok(int64_t d, const void* a, const void* b, const void* c, const void* e) {
   return d % 4 == 0 && d >= 4 && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(e);
 }
@@ -120,16 +125,17 @@ extern "C" int nt_device_supported(void) {
   if (dtype != NT_F32) { set_error(fn ": only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }       \
   NT_CHECK_ARG(d > 0 && d < (1 << 20) && E >= 0 && E < INT32_MAX, fn ": bad sizes");                      \
   NT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, fn ": dropout_p must be in [0, 1)");                  \
-  NT_CHECK_ARG(gemm_mode == NT_GEMM_TF32X3 || gemm_mode == NT_GEMM_FP32 || gemm_mode == NT_GEMM_TF32, fn ": bad gemm_mode")
+  NT_CHECK_ARG(gemm_mode == NT_GEMM_TF32X3 || gemm_mode == NT_GEMM_FP32 || gemm_mode == NT_GEMM_TF32 || gemm_mode == NT_GEMM_BF16, fn ": bad gemm_mode")
 
 extern "C" size_t nt_weight_image_bytes(int64_t d) { return d > 0 ? tc_weight_image_bytes(d) : 0; }
 
 extern "C" int nt_weight_prepare(const void* W, int64_t d, int transpose, void* image, int dtype, nt_stream_t stream) {
-  if (dtype != NT_F32) { set_error("nt_weight_prepare: only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
+  NT_CHECK_ARG(dtype == NT_F32 || dtype == NT_BF16, "nt_weight_prepare: bad dtype");
   NT_CHECK_ARG(W && image && d > 0 && d < (1 << 20), "nt_weight_prepare: bad arguments");
+  if (dtype == NT_BF16 && !use_pair_kernels()) { set_error("nt_weight_prepare: the bf16 image needs the CTA-pair kernels"); return NT_ERR_UNSUPPORTED; }
   if (!aligned16(image)) { set_error("nt_weight_prepare: image must be 16-byte aligned"); return NT_ERR_ALIGN; }
   // forward image (transpose = 0): CTA-pair layout of gemm_pair.cu; dgrad image (transpose = 1): single-CTA layout of gemm_tc.cu
-  if (use_pair_kernels() && (!transpose || pair_dgrad_enabled())) return pair_weight_prepare(static_cast<const float*>(W), d, transpose != 0, image, as_stream(stream));
+  if (use_pair_kernels() && (!transpose || pair_dgrad_enabled() || dtype == NT_BF16)) return pair_weight_prepare(static_cast<const float*>(W), d, transpose != 0, image, dtype == NT_BF16, as_stream(stream));
   return tc_weight_prepare(static_cast<const float*>(W), d, transpose != 0, image, as_stream(stream));
 }
 
@@ -147,7 +153,8 @@ extern "C" int nt_layer_forward(const void* h, const void* n, const int32_t* src
     if (use_pair_kernels())
       return pair_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, weight_image, static_cast<const float*>(bias), E,
                                 V, d, act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), static_cast<float*>(m_out),
-                                gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+                                products_of(gemm_mode), st);
+    if (gemm_mode == NT_GEMM_BF16) { set_error("nt_layer_forward: NT_GEMM_BF16 needs the CTA-pair kernels"); return NT_ERR_UNSUPPORTED; }
     return tc_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, weight_image, static_cast<const float*>(bias), E, d,
                             act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), static_cast<float*>(m_out),
                             gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
@@ -168,7 +175,7 @@ extern "C" int nt_dense_forward(const void* x, const void* weight_image, const v
     return NT_ERR_UNSUPPORTED;
   }
   return pair_dense_forward(static_cast<const float*>(x), weight_image, static_cast<const float*>(bias), static_cast<const float*>(resid), R, d,
-                            dropout_p, seed, offset, static_cast<float*>(out), gemm_mode == NT_GEMM_TF32 ? 1 : 3, as_stream(stream));
+                            dropout_p, seed, offset, static_cast<float*>(out), products_of(gemm_mode), as_stream(stream));
 }
 
 extern "C" int nt_layer_backward_dgrad(const void* g, const void* W, const void* weight_image, int64_t E, int64_t d, float dropout_p, uint64_t seed,
@@ -181,7 +188,8 @@ extern "C" int nt_layer_backward_dgrad(const void* g, const void* W, const void*
     NT_CHECK_ARG(weight_image, "nt_layer_backward_dgrad: tensor-core path needs weight_image (nt_weight_prepare, transpose=1)");
     if (pair_dgrad_enabled())
       return pair_layer_dgrad(static_cast<const float*>(g), weight_image, E, d, dropout_p, seed, offset, static_cast<float*>(g_m),
-                              gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+                              products_of(gemm_mode), st);
+    if (gemm_mode == NT_GEMM_BF16) { set_error("nt_layer_backward_dgrad: NT_GEMM_BF16 needs the CTA-pair kernels"); return NT_ERR_UNSUPPORTED; }
     return tc_layer_dgrad(static_cast<const float*>(g), weight_image, E, d, dropout_p, seed, offset, static_cast<float*>(g_m),
                           gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
   }
@@ -223,11 +231,11 @@ extern "C" int nt_layer_backward_wgrad(const void* g, const void* m, const void*
     }
     auto wgrad = pair_wgrad_enabled() ? pair_layer_wgrad : tma_layer_wgrad;
     int rc = wgrad(static_cast<const float*>(g), static_cast<const float*>(m), E, d, dropout_p, seed, offset, static_cast<float*>(gW),
-                   static_cast<float*>(gb), workspace, workspace_bytes, gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+                   static_cast<float*>(gb), workspace, workspace_bytes, wgrad_products_of(gemm_mode), st);
     if (rc != NT_ERR_UNSUPPORTED) return rc;
     // no spare padded feature row for the bias gradient (d % 128 == 0 resp. d % 256 == 0): weight gradient here, column sums of g_u below
     rc = wgrad(static_cast<const float*>(g), static_cast<const float*>(m), E, d, dropout_p, seed, offset, static_cast<float*>(gW), nullptr,
-               workspace, workspace_bytes, gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+               workspace, workspace_bytes, wgrad_products_of(gemm_mode), st);
     if (rc) return rc;
     return tc_bias_grad(static_cast<const float*>(g), E, d, dropout_p, seed, offset, static_cast<float*>(gb), workspace, workspace_bytes, st);
   }
@@ -235,7 +243,7 @@ extern "C" int nt_layer_backward_wgrad(const void* g, const void* m, const void*
   if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, g, h, n, workspace)) {
     int rc = tc_layer_wgrad(static_cast<const float*>(g), static_cast<const float*>(h), static_cast<const float*>(n), src, rev, E, d, act, act_param,
                             dropout_p, seed, offset, static_cast<float*>(gW), static_cast<float*>(gb), workspace, workspace_bytes,
-                            gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+                            wgrad_products_of(gemm_mode), st);
     if (rc != NT_ERR_UNSUPPORTED) return rc;
   }
   return simt_layer_wgrad(static_cast<const float*>(g), static_cast<const float*>(h), static_cast<const float*>(n), src, rev, E, d, act, act_param,

@@ -25,6 +25,7 @@
 //   empty[s]      local   tcgen05.commit multicast to both CTAs -> W producer and A producers of each CTA
 //   tmem_full     local   tcgen05.commit multicast -> epilogue warps of each CTA
 //   tmem_empty    L       8 epilogue warps -> MMA issuer
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -105,6 +106,27 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_pair(int n) {
 // switch (expf / erff / tanhf per element) and Philox inlined into every unrolled unit the hot loops were ~75 KB of SASS and
 // ncu showed the instruction cache as a bottleneck (gcc__cache_requests_type_instruction at 73 % of peak, 12 % of warp
 // samples stalled on no_instructions).
+// ---- bf16 operand mode (BASELINE configs[4]: "bf16 W_h with fp32 accumulation") -----------------------------------------
+// Operands are rounded to bf16 and multiplied by ONE tcgen05.mma.kind::f16 pass (fp32 accumulation in TMEM); a K-block of
+// 32 values is a 64-byte row, i.e. the 64-byte-swizzled K-major layout (Swizzle<2,4,3>: 16-byte chunk ^= (row >> 1) & 3).
+__host__ __device__ __forceinline__ uint32_t make_idesc_pair_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+constexpr uint32_t KMAJOR_SW64_DESC_HI = (512u >> 4) | (1u << 14) | (4u << 29);  // SBO = 512 B, version 1, SWIZZLE_64B
+// byte offset of the four bf16 values of (row r, 4-value chunk c in [0, 8)) inside a 64-byte-swizzled K-major tile
+__host__ __device__ __forceinline__ uint32_t swz64_bf16(uint32_t r, uint32_t c) {
+  return (r >> 3) * 512u + (r & 7u) * 64u + ((((c >> 1) ^ ((r >> 1) & 3u))) << 4) + (c & 1u) * 8u;
+}
+__device__ __forceinline__ void umma2_bf16_lo(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // Debug trace (CTA 0 only): regions 0 = epilogue thread 0, 1 = MMA issuer, 2 = transform thread 0, 3 = copy-engine warp lane 0.
 template <bool TRACE>
 __device__ __forceinline__ void trace_event_t(const Params& p, int region, uint32_t& cursor, int ev, int64_t tile, int aux = 0) {
@@ -115,7 +137,7 @@ __device__ __forceinline__ void trace_event_t(const Params& p, int region, uint3
   }
 }
 
-template <int MODE, bool DROP, bool RELU, bool TRACE>  // MODE 0 = K2 forward, 1 = K4a dgrad, 2 = dense forward (atom message passing); TRACE = the role-timeline build (scripts/trace_pair.py)
+template <int MODE, bool DROP, bool RELU, bool TRACE, bool BF16>  // BF16 = bf16 operands, one kind::f16 pass; MODE 0 = K2 forward, 1 = K4a dgrad, 2 = dense forward (atom message passing); TRACE = the role-timeline build (scripts/trace_pair.py)
 __global__ void __launch_bounds__(THREADS, 1)
 layer_gemm_pair(const Params p) {
   auto trace_event = [](const Params& pp, int region, uint32_t& cursor, int ev, int64_t tile, int aux = 0) {
@@ -281,8 +303,8 @@ layer_gemm_pair(const Params p) {
     // ===================================== MMA ISSUER (leader CTA only) =====================================
     if (leader) {
       NT_PAIR_TILE_VARS;
-      const uint32_t idesc_a = make_idesc_pair(geo.n_a);
-      const uint32_t idesc_b = make_idesc_pair(geo.n_b > 0 ? geo.n_b : 16);
+      const uint32_t idesc_a = BF16 ? make_idesc_pair_bf16(geo.n_a) : make_idesc_pair(geo.n_a);
+      const uint32_t idesc_b = BF16 ? make_idesc_pair_bf16(geo.n_b > 0 ? geo.n_b : 16) : make_idesc_pair(geo.n_b > 0 ? geo.n_b : 16);
       int s = 0, tw = 0;
       uint32_t ph = 0, tphase = 0;
       for (int tile = first_tile; tile < pair_tiles; tile += tile_stride) {
@@ -299,11 +321,25 @@ layer_gemm_pair(const Params p) {
             if (lane == 0) trace_event(p, 1, tcur, 12, tile, kb);
             if (elect_one()) {
               const int rem = d - kb * BLOCK_K;
-              const int ksteps = (p.ablate & 8) ? 0 : (rem >= BLOCK_K ? BLOCK_K / 8 : (rem + 7) / 8);
               const uint32_t st0 = sbase + s * STAGE_BYTES;
+              const uint32_t d0 = tmem_base + col_base, d1 = d0 + (uint32_t)geo.n_a;
+              if (BF16) {
+                const int ksteps = (p.ablate & 8) ? 0 : (rem >= BLOCK_K ? 2 : (rem + 15) / 16);  // K = 16 bf16 per MMA
+                const uint32_t a_bf = kmajor_desc_lo(st0 + OFF_A0), w_bf = kmajor_desc_lo(st0 + OFF_WHI);
+                const uint32_t woff = (uint32_t)(geo.n_a / 2) * (64u >> 4);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  if (j < ksteps) {
+                    const uint32_t k16 = j * 2;  // 16 bf16 = 32 bytes inside the 64-byte swizzle row
+                    const uint32_t acc = (kb | j) != 0 ? 1u : 0u;
+                    umma2_bf16_lo(d0, a_bf + k16, w_bf + k16, KMAJOR_SW64_DESC_HI, idesc_a, acc);
+                    if (geo.n_b > 0) umma2_bf16_lo(d1, a_bf + k16, w_bf + woff + k16, KMAJOR_SW64_DESC_HI, idesc_b, acc);
+                  }
+                }
+              } else {
+              const int ksteps = (p.ablate & 8) ? 0 : (rem >= BLOCK_K ? BLOCK_K / 8 : (rem + 7) / 8);
               const uint32_t a_hi = kmajor_desc_lo(st0 + OFF_A0), a_lo = kmajor_desc_lo(st0 + OFF_A1);
               const uint32_t w_hi = kmajor_desc_lo(st0 + OFF_WHI), w_lo = kmajor_desc_lo(st0 + OFF_WLO);
-              const uint32_t d0 = tmem_base + col_base, d1 = d0 + (uint32_t)geo.n_a;
               const uint32_t woff = (uint32_t)(geo.n_a / 2) * (128u >> 4);  // this CTA's rows of the second MMA follow its n_a / 2 rows of the first
 #pragma unroll
               for (int j = 0; j < BLOCK_K / 8; ++j) {
@@ -325,6 +361,7 @@ layer_gemm_pair(const Params p) {
                   }
                 }
               }
+              }
               umma2_commit_both(bar_empty + 8 * s);
               if (kb == geo.k_blocks - 1) umma2_commit_both(bar_tmem_full);
             }
@@ -342,8 +379,8 @@ layer_gemm_pair(const Params p) {
     NT_PAIR_TILE_VARS;
     int s = 0;
     uint32_t ph = 0;
-    const uint32_t w_bytes = (uint32_t)geo.rows_per_cta * 128u;
-    const bool need_lo = p.products == 3;
+    const uint32_t w_bytes = (uint32_t)geo.rows_per_cta * (BF16 ? 64u : 128u);
+    const bool need_lo = !BF16 && p.products == 3;
     for (int tile = first_tile; tile < pair_tiles; tile += tile_stride) {
       __syncwarp();
 #pragma unroll 1
@@ -360,7 +397,7 @@ layer_gemm_pair(const Params p) {
             } else {
               mbar_arrive_expect_tx(bar_w + 8 * s, need_lo ? 2 * w_bytes : w_bytes);
               bulk_copy_g2s(st0 + OFF_WHI, p.wimg + off, w_bytes, bar_w + 8 * s);
-              if (need_lo) bulk_copy_g2s(st0 + OFF_WLO, p.wimg + geo.part_bytes + off, w_bytes, bar_w + 8 * s);
+              if (need_lo) bulk_copy_g2s(st0 + OFF_WLO, p.wimg + geo.part_bytes + off, w_bytes, bar_w + 8 * s);  // (bf16 image: one part only)
             }
           }
           __syncwarp();
@@ -475,11 +512,26 @@ layer_gemm_pair(const Params p) {
             const float4 sc = dropout_scale4(p.seed, p.offset, (uint64_t)e * (uint64_t)d + (uint64_t)col, p.drop_thr, p.inv_keep);
             m = make_float4(m.x * sc.x, m.y * sc.y, m.z * sc.z, m.w * sc.w);
           }
-          const float4 hi = make_float4(tf32_rna(m.x), tf32_rna(m.y), tf32_rna(m.z), tf32_rna(m.w));
-          const float4 lo = make_float4(tf32_rna(m.x - hi.x), tf32_rna(m.y - hi.y), tf32_rna(m.z - hi.z), tf32_rna(m.w - hi.w));
-          *reinterpret_cast<float4*>(a0 + u * 16) = hi;
-          *reinterpret_cast<float4*>(a1 + u * 16) = lo;
+          if (!BF16) {
+            const float4 hi = make_float4(tf32_rna(m.x), tf32_rna(m.y), tf32_rna(m.z), tf32_rna(m.w));
+            const float4 lo = make_float4(tf32_rna(m.x - hi.x), tf32_rna(m.y - hi.y), tf32_rna(m.z - hi.z), tf32_rna(m.w - hi.w));
+            *reinterpret_cast<float4*>(a0 + u * 16) = hi;
+            *reinterpret_cast<float4*>(a1 + u * 16) = lo;
+          }
           raw0[i] = m;
+        }
+        if (BF16) {
+          // the bf16 tile (8 KiB, 64-byte rows) overwrites the raw fp32 tile: every producer thread must have read its raw units first
+          asm volatile("bar.sync 1, %0;" ::"n"(NUM_X_THREADS) : "memory");
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 lo2 = __float22bfloat162_rn(make_float2(raw0[i].x, raw0[i].y));
+            const __nv_bfloat162 hi2 = __float22bfloat162_rn(make_float2(raw0[i].z, raw0[i].w));
+            uint2 packed;
+            packed.x = *reinterpret_cast<const uint32_t*>(&lo2);
+            packed.y = *reinterpret_cast<const uint32_t*>(&hi2);
+            *reinterpret_cast<uint2*>(a0 + swz64_bf16((uint32_t)(r0 + 32 * i), (uint32_t)c)) = packed;
+          }
         }
         if (MODE == 0 && p.m_out != nullptr && cp.nt == 0 && col < d && !(p.ablate & 32)) {
 #pragma unroll
@@ -540,12 +592,42 @@ __global__ void __launch_bounds__(256) pair_weight_prepare_kernel(const float* _
   *reinterpret_cast<float*>(image + geo.part_bytes + off) = lo;
 }
 
-template <int MODE, bool DROP, bool RELU, bool TRACE>
+// bf16 image: same (N tile, K block, CTA rank) order, one part, 64-byte-swizzled rows of 32 bf16
+__global__ void __launch_bounds__(256) pair_weight_prepare_bf16_kernel(const float* __restrict__ W, Geometry geo, int transpose, uint8_t* __restrict__ image) {
+  const int64_t total = (int64_t)geo.n_tiles * geo.k_blocks * geo.n_tile * (BLOCK_K / 4);  // one thread per 4 values
+  int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % (BLOCK_K / 4));
+  int64_t q = t / (BLOCK_K / 4);
+  const int j = (int)(q % geo.rows_per_cta);
+  q /= geo.rows_per_cta;
+  const int rank = (int)(q % 2);
+  q /= 2;
+  const int kb = (int)(q % geo.k_blocks);
+  const int nt = (int)(q / geo.k_blocks);
+  const int ha = geo.n_a / 2, hb = geo.n_b / 2;
+  const int r = j < ha ? rank * ha + j : geo.n_a + rank * hb + (j - ha);
+  const int n = nt * geo.n_tile + r;
+  float v[4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int k = kb * BLOCK_K + 4 * c + x;
+    v[x] = (n < geo.d && k < geo.d) ? (transpose ? __ldg(W + (int64_t)k * geo.d + n) : __ldg(W + (int64_t)n * geo.d + k)) : 0.f;
+  }
+  const __nv_bfloat162 lo2 = __float22bfloat162_rn(make_float2(v[0], v[1])), hi2 = __float22bfloat162_rn(make_float2(v[2], v[3]));
+  uint2 packed;
+  packed.x = *reinterpret_cast<const uint32_t*>(&lo2);
+  packed.y = *reinterpret_cast<const uint32_t*>(&hi2);
+  const size_t off = ((((size_t)nt * geo.k_blocks + kb) * 2 + rank) * geo.rows_per_cta) * 64 + swz64_bf16((uint32_t)j, (uint32_t)c);
+  *reinterpret_cast<uint2*>(image + off) = packed;
+}
+
+template <int MODE, bool DROP, bool RELU, bool TRACE, bool BF16>
 static int launch_variant(const Params& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(layer_gemm_pair<MODE, DROP, RELU, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(layer_gemm_pair<MODE, DROP, RELU, TRACE, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(layer_gemm_pair)");
   const int64_t pair_tiles = (p.E + 2 * TILE_M - 1) / (2 * TILE_M);
@@ -565,7 +647,7 @@ static int launch_variant(const Params& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, layer_gemm_pair<MODE, DROP, RELU, TRACE>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, layer_gemm_pair<MODE, DROP, RELU, TRACE, BF16>, p);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(layer_gemm_pair)");
   NT_LAUNCH_CHECK("layer_gemm_pair", 1);
   return NT_OK;
@@ -575,10 +657,15 @@ template <int MODE>
 static int launch(const Params& p, cudaStream_t st) {
   const bool drop = p.drop_p > 0.f;
   const bool relu = MODE != 0 || p.act == NT_ACT_RELU;  // the dense modes have no activation prologue
-  if (MODE != 2 && p.trace != nullptr && !drop && relu) return launch_variant<MODE, false, true, true>(p, st);  // the role-timeline build exists for the default case only
-  if (MODE != 0) return drop ? launch_variant<MODE, true, true, false>(p, st) : launch_variant<MODE, false, true, false>(p, st);
-  if (drop) return relu ? launch_variant<MODE, true, true, false>(p, st) : launch_variant<MODE, true, false, false>(p, st);
-  return relu ? launch_variant<MODE, false, true, false>(p, st) : launch_variant<MODE, false, false, false>(p, st);
+  if (p.products == 0) {  // bf16 operands
+    if (MODE != 0) return drop ? launch_variant<MODE, true, true, false, true>(p, st) : launch_variant<MODE, false, true, false, true>(p, st);
+    if (drop) return relu ? launch_variant<MODE, true, true, false, true>(p, st) : launch_variant<MODE, true, false, false, true>(p, st);
+    return relu ? launch_variant<MODE, false, true, false, true>(p, st) : launch_variant<MODE, false, false, false, true>(p, st);
+  }
+  if (MODE != 2 && p.trace != nullptr && !drop && relu) return launch_variant<MODE, false, true, true, false>(p, st);  // the role-timeline build exists for the default case only
+  if (MODE != 0) return drop ? launch_variant<MODE, true, true, false, false>(p, st) : launch_variant<MODE, false, true, false, false>(p, st);
+  if (drop) return relu ? launch_variant<MODE, true, true, false, false>(p, st) : launch_variant<MODE, true, false, false, false>(p, st);
+  return relu ? launch_variant<MODE, false, true, false, false>(p, st) : launch_variant<MODE, false, false, false, false>(p, st);
 }
 
 unsigned long long* g_trace_buffer = nullptr;
@@ -599,8 +686,14 @@ static void fill_dropout(Params& p, float drop_p, uint64_t seed, uint64_t offset
 
 void pair_set_trace_buffer(void* ptr) { pair::g_trace_buffer = static_cast<unsigned long long*>(ptr); }
 
-int pair_weight_prepare(const float* W, int64_t d, int transpose, void* image, cudaStream_t st) {
+int pair_weight_prepare(const float* W, int64_t d, int transpose, void* image, int bf16, cudaStream_t st) {
   pair::Geometry geo = pair::make_geometry((int)d);
+  if (bf16) {
+    const int64_t total4 = (int64_t)geo.n_tiles * geo.k_blocks * geo.n_tile * (pair::BLOCK_K / 4);
+    pair::pair_weight_prepare_bf16_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, st>>>(W, geo, transpose, static_cast<uint8_t*>(image));
+    NT_LAUNCH_CHECK("pair_weight_prepare_bf16_kernel", 1);
+    return NT_OK;
+  }
   const int64_t total = (int64_t)geo.n_tiles * geo.k_blocks * geo.n_tile * pair::BLOCK_K;
   pair::pair_weight_prepare_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(W, geo, transpose, static_cast<uint8_t*>(image));
   NT_LAUNCH_CHECK("pair_weight_prepare_kernel", 1);

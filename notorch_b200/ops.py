@@ -15,7 +15,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import GEMM_FP32, GEMM_TF32, GEMM_TF32X3, NT_F32
+from ._lib import GEMM_BF16, GEMM_FP32, GEMM_TF32, GEMM_TF32X3, NT_BF16, NT_F32
 
 __all__ = [
     "GraphCSR", "SegmentCSR", "build_segment_csr", "graph_csr", "segment_csr_for", "seg_reduce", "gather_add",
@@ -33,13 +33,14 @@ ACT_CODES = {
     torch.nn.Tanh: (_lib.ACT_TANH, lambda m: 0.0),
 }
 
-_GEMM_MODES = {"tf32x3": GEMM_TF32X3, "fp32": GEMM_FP32, "tf32": GEMM_TF32}
+_GEMM_MODES = {"tf32x3": GEMM_TF32X3, "fp32": GEMM_FP32, "tf32": GEMM_TF32, "bf16": GEMM_BF16}
 _gemm_mode = _GEMM_MODES[os.environ.get("NOTORCH_B200_GEMM", "tf32x3").lower()]
 _validate_mode = os.environ.get("NOTORCH_B200_VALIDATE", "sync").lower()  # "sync" | "deferred" | "off"
 
 
 def set_gemm_mode(mode: str) -> None:
-    """``"tf32x3"`` (tcgen05, error-compensated; default), ``"fp32"`` (FFMA) or ``"tf32"`` (single pass)."""
+    """``"tf32x3"`` (tcgen05, error-compensated; default), ``"fp32"`` (FFMA), ``"tf32"`` (single pass) or ``"bf16"`` (bf16 operands
+    for W_h and the message tensor, one tcgen05 kind::f16 pass with fp32 accumulation - BASELINE configs[4]; NOT within the fp32 bound)."""
     global _gemm_mode
     _gemm_mode = _GEMM_MODES[mode.lower()]
 
@@ -382,7 +383,7 @@ def _weight_image(W: Tensor, transpose: bool) -> Tensor | None:
     L = _lib.lib()
     d = W.shape[0]
     img = torch.empty(L.nt_weight_image_bytes(d), dtype=torch.uint8, device=W.device)
-    _run("Wprep:nt_weight_prepare", L.nt_weight_prepare, _p(W), d, int(transpose), _p(img), NT_F32, _stream())
+    _run("Wprep:nt_weight_prepare", L.nt_weight_prepare, _p(W), d, int(transpose), _p(img), NT_BF16 if _gemm_mode == GEMM_BF16 else NT_F32, _stream())
     return img
 
 
