@@ -42,6 +42,9 @@ WORKLOADS = {
                                                                      "batch 4096 synthetic ZINC-size graphs per GPU, fp32 training step"),
     "c1": dict(config=1, batch=64, d=300, depth=3, agg="sum", desc="BASELINE configs[0]: batch 64 ~25-atom molecules"),
     "c3": dict(config=3, batch=16384, d=1024, depth=5, agg="mean", desc="BASELINE configs[2]: depth=5 hidden=1024 Mean readout, batch 16384 per GPU"),
+    "c5": dict(config=5, batch=1024, d=2048, depth=6, agg="sum", gemm="bf16",
+               desc="BASELINE configs[4]: large-molecule stress, 100-300-atom graphs, depth=6 hidden=2048, bf16 W_h with fp32 accumulation, "
+                    "batch 1024 per GPU"),
     "c4": dict(config=2, batch=16384, d=300, depth=3, agg="norm", inference=True,
                desc="BASELINE configs[3]: atom message passing depth=3 hidden=300, Norm pooling, inference-only screening, 16384 molecules per launch "
                     "per GPU (10 M molecules = 611 launches; shards are independent, no collective)"),
@@ -56,7 +59,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="override molecules per GPU")
-    ap.add_argument("--gemm", default=None, choices=["tf32x3", "fp32", "tf32"])
+    ap.add_argument("--gemm", default=None, choices=["tf32x3", "fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel-table", action="store_true", help="print the per-kernel table to stderr")
@@ -384,8 +387,8 @@ def run_ours(args, wl, batch):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if args.gemm:
-        ops.set_gemm_mode(args.gemm)
+    if args.gemm or wl.get("gemm"):
+        ops.set_gemm_mode(args.gemm or wl["gemm"])
     ops.set_index_validation("deferred")  # no per-batch device sync; an out-of-range index still raises (one batch late)
 
     mols, node_types, edge_types = make_workload(wl, rank, batch)
@@ -631,7 +634,7 @@ def run_ours(args, wl, batch):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "bf16 operands, f32 accumulate / activations" if ops.get_gemm_mode() == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "hidden": d, "depth": L, "readout": wl["agg"], "batch_per_gpu": batch, "atoms_per_gpu": V,
                        "edges_per_gpu": E, "gemm": ops.get_gemm_mode(), "parallelism": f"dp{world}", "launch": launch_mode,
                        "step": "collate+CSR, GraphEmbedding, ChempropBlock, readout, loss, backward, grad all-reduce (N>1), fused Adam",
