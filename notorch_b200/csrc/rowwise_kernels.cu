@@ -15,6 +15,22 @@ constexpr int ROW_THREADS = 256;
 
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
+// Compile-time activation kind of the segmented reductions: 0 = identity, 1 = ReLU, 2 = the generic six-way switch. With the
+// switch (expf / erff / tanhf per element) inlined into every unrolled row the ELL kernel was 97 KB of SASS and instruction
+// fetch, not HBM, set its speed; the two hot cases are now ~3 KB each.
+template <int AK>
+__device__ __forceinline__ float4 seg_act_fwd4(float4 v, int act, float p) {
+  if (AK == 0) return v;
+  if (AK == 1) return make_float4(v.x < 0.f ? 0.f : v.x, v.y < 0.f ? 0.f : v.y, v.z < 0.f ? 0.f : v.z, v.w < 0.f ? 0.f : v.w);
+  return act_fwd4(v, act, p);
+}
+template <int AK>
+__device__ __forceinline__ float seg_act_bwd(float x, int act, float p) {
+  if (AK == 0) return 1.f;
+  if (AK == 1) return x > 0.f ? 1.f : 0.f;
+  return act_bwd(x, act, p);
+}
+
 // ------------------------------------------------------------------------------------------------
 // seg_reduce, vectorised: one thread per (segment, float4 chunk)
 // ------------------------------------------------------------------------------------------------
@@ -23,13 +39,13 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(
 // (in-degree ~2), so the independent chains of several items are what keeps enough bytes in flight.
 constexpr int SEG_ITEMS = 2;
 
-template <bool HAS_PERM>
+template <bool HAS_PERM, int AK>
 __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __restrict__ x, int d, int chunks, const int32_t* __restrict__ rowptr,
                                                               const int32_t* __restrict__ perm, int64_t total, int act, float act_param,
                                                               int mean, float scale, const float* __restrict__ base,
                                                               const float* __restrict__ dact_of, float* __restrict__ out) {
   // dact_of != nullptr (nt_seg_reduce_ex, backward form): no activation prologue; the reduced row is multiplied by act'(dact_of[s])
-  const int pre_act = dact_of ? NT_ACT_IDENTITY : act;
+  const bool pre = dact_of == nullptr;
   const int64_t t0 = (int64_t)blockIdx.x * (ROW_THREADS * SEG_ITEMS) + threadIdx.x;
   int s[SEG_ITEMS], c[SEG_ITEMS], lo[SEG_ITEMS], hi[SEG_ITEMS];
   float4 acc[SEG_ITEMS];
@@ -66,7 +82,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __r
     for (int k = 0; k < SEG_ITEMS; ++k)
 #pragma unroll
       for (int u = 0; u < 2; ++u)  // ascending item order within the segment: bit-identical to a sequential scatter_add_
-        if (ok[k][u]) acc[k] = add4(acc[k], pre_act != NT_ACT_IDENTITY ? act_fwd4(v[k][u], pre_act, act_param) : v[k][u]);
+        if (ok[k][u]) acc[k] = add4(acc[k], pre ? seg_act_fwd4<AK>(v[k][u], act, act_param) : v[k][u]);
   }
 #pragma unroll
   for (int k = 0; k < SEG_ITEMS; ++k) {
@@ -80,8 +96,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __r
     if (scale != 1.f) a = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
     if (dact_of) {
       const float4 hv = ldg4(dact_of + (int64_t)s[k] * d + c[k]);
-      a = make_float4(a.x * act_bwd(hv.x, act, act_param), a.y * act_bwd(hv.y, act, act_param), a.z * act_bwd(hv.z, act, act_param),
-                      a.w * act_bwd(hv.w, act, act_param));
+      a = make_float4(a.x * seg_act_bwd<AK>(hv.x, act, act_param), a.y * seg_act_bwd<AK>(hv.y, act, act_param),
+                      a.z * seg_act_bwd<AK>(hv.z, act, act_param), a.w * seg_act_bwd<AK>(hv.w, act, act_param));
     }
     if (base) a = add4(ldg4_stream(base + (int64_t)s[k] * d + c[k]), a);
     stg4(out + (int64_t)s[k] * d + c[k], a);
@@ -106,11 +122,12 @@ __global__ void __launch_bounds__(ROW_THREADS) csr_to_ell_kernel(const int32_t* 
   ell[s] = make_int4(v[0], v[1], v[2], v[3]);
 }
 
+template <int AK>
 __global__ void __launch_bounds__(ROW_THREADS, 4) seg_reduce_ell_v4(const float* __restrict__ x, int d, int chunks, const int32_t* __restrict__ rowptr,
                                                                    const int32_t* __restrict__ perm, const int4* __restrict__ ell, int64_t total,
                                                                    int act, float act_param, int mean, float scale, const float* __restrict__ base,
                                                                    const float* __restrict__ dact_of, float* __restrict__ out) {
-  const int pre_act = dact_of ? NT_ACT_IDENTITY : act;
+  const bool pre = dact_of == nullptr;
   const int64_t t0 = (int64_t)blockIdx.x * (ROW_THREADS * SEG_ITEMS) + threadIdx.x;
   int s[SEG_ITEMS], c[SEG_ITEMS], lo[SEG_ITEMS], hi[SEG_ITEMS];
   int4 nb[SEG_ITEMS];
@@ -140,11 +157,11 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) seg_reduce_ell_v4(const float*
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < 4; ++u)  // ascending item order within the segment: bit-identical to a sequential scatter_add_
-      if (id[u] >= 0) a = add4(a, pre_act != NT_ACT_IDENTITY ? act_fwd4(v[k][u], pre_act, act_param) : v[k][u]);
+      if (id[u] >= 0) a = add4(a, pre ? seg_act_fwd4<AK>(v[k][u], act, act_param) : v[k][u]);
     for (int j = lo[k] + 4; j < hi[k]; ++j) {  // degree > 4: the rest of the segment through the CSR
       const int rr = perm ? __ldg(perm + j) : j;
       const float4 w = ldg4(x + (int64_t)rr * d + c[k]);
-      a = add4(a, pre_act != NT_ACT_IDENTITY ? act_fwd4(w, pre_act, act_param) : w);
+      a = add4(a, pre ? seg_act_fwd4<AK>(w, act, act_param) : w);
     }
     if (mean) {
       const float cnt = (float)max(hi[k] - lo[k], 1);
@@ -153,8 +170,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) seg_reduce_ell_v4(const float*
     if (scale != 1.f) a = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
     if (dact_of) {
       const float4 hv = ldg4(dact_of + (int64_t)s[k] * d + c[k]);
-      a = make_float4(a.x * act_bwd(hv.x, act, act_param), a.y * act_bwd(hv.y, act, act_param), a.z * act_bwd(hv.z, act, act_param),
-                      a.w * act_bwd(hv.w, act, act_param));
+      a = make_float4(a.x * seg_act_bwd<AK>(hv.x, act, act_param), a.y * seg_act_bwd<AK>(hv.y, act, act_param),
+                      a.z * seg_act_bwd<AK>(hv.z, act, act_param), a.w * seg_act_bwd<AK>(hv.w, act, act_param));
     }
     if (base) a = add4(ldg4_stream(base + (int64_t)s[k] * d + c[k]), a);
     stg4(out + (int64_t)s[k] * d + c[k], a);
@@ -290,11 +307,21 @@ static int seg_reduce_impl(const char* fn, const void* x, int64_t d, const int32
     int chunks = (int)(d / 4);
     int64_t total = num_segments * chunks;
     unsigned grid = (unsigned)cdiv(total, ROW_THREADS * SEG_ITEMS);
-    if (ell && aligned16(ell))
-      seg_reduce_ell_v4<<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, reinterpret_cast<const int4*>(ell), total, act, act_param, mean,
-                                                      scale, bf, df, of);
-    else if (perm) seg_reduce_v4<true><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);
-    else seg_reduce_v4<false><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);
+    const int ak = act == NT_ACT_IDENTITY ? 0 : act == NT_ACT_RELU ? 1 : 2;
+#define NT_SEG_LAUNCH(AK)                                                                                                                        \
+  do {                                                                                                                                           \
+    if (ell && aligned16(ell))                                                                                                                   \
+      seg_reduce_ell_v4<AK><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, reinterpret_cast<const int4*>(ell), total, act,      \
+                                                          act_param, mean, scale, bf, df, of);                                                  \
+    else if (perm)                                                                                                                               \
+      seg_reduce_v4<true, AK><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);   \
+    else                                                                                                                                         \
+      seg_reduce_v4<false, AK><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);  \
+  } while (0)
+    if (ak == 0) NT_SEG_LAUNCH(0);
+    else if (ak == 1) NT_SEG_LAUNCH(1);
+    else NT_SEG_LAUNCH(2);
+#undef NT_SEG_LAUNCH
   } else {
     int64_t total = num_segments * d;
     seg_reduce_s<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(xf, (int)d, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);
