@@ -46,7 +46,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __r
                                                               const float* __restrict__ dact_of, float* __restrict__ out) {
   // dact_of != nullptr (nt_seg_reduce_ex, backward form): no activation prologue; the reduced row is multiplied by act'(dact_of[s])
   const bool pre = dact_of == nullptr;
-  const int64_t t0 = (int64_t)blockIdx.x * (ROW_THREADS * SEG_ITEMS) + threadIdx.x;
+  // blocks walk the segments from the END: the producer kernel wrote its output front to back, so the tail is what is still in
+  // the 126 MB L2 when this kernel starts (reading front to back would evict it before reaching it)
+  const int64_t t0 = (int64_t)(gridDim.x - 1 - blockIdx.x) * (ROW_THREADS * SEG_ITEMS) + threadIdx.x;
   int s[SEG_ITEMS], c[SEG_ITEMS], lo[SEG_ITEMS], hi[SEG_ITEMS];
   float4 acc[SEG_ITEMS];
   int maxlen = 0;
@@ -128,7 +130,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) seg_reduce_ell_v4(const float*
                                                                    int act, float act_param, int mean, float scale, const float* __restrict__ base,
                                                                    const float* __restrict__ dact_of, float* __restrict__ out) {
   const bool pre = dact_of == nullptr;
-  const int64_t t0 = (int64_t)blockIdx.x * (ROW_THREADS * SEG_ITEMS) + threadIdx.x;
+  // blocks walk the segments from the END: the producer kernel wrote its output front to back, so the tail is what is still in
+  // the 126 MB L2 when this kernel starts (reading front to back would evict it before reaching it)
+  const int64_t t0 = (int64_t)(gridDim.x - 1 - blockIdx.x) * (ROW_THREADS * SEG_ITEMS) + threadIdx.x;
   int s[SEG_ITEMS], c[SEG_ITEMS], lo[SEG_ITEMS], hi[SEG_ITEMS];
   int4 nb[SEG_ITEMS];
   bool live[SEG_ITEMS];
