@@ -91,7 +91,7 @@ def test_emulation_reproduces_the_exact_reference_when_switched_off():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("act,d,depth,batch", [("relu", 300, 3, 64), ("relu", 64, 2, 32), ("relu", 256, 2, 48), ("silu", 300, 3, 64),
-                                               ("tanh", 128, 2, 32), ("relu", 512, 1, 24)])
+                                               ("tanh", 128, 2, 32), ("relu", 512, 1, 24), ("silu", 2048, 1, 8)])
 def test_block_bf16_mode(bf16_mode, act, d, depth, batch):
     from notorch_b200 import BatchedGraph
     from notorch_b200.nn import ChempropBlock, Sum
