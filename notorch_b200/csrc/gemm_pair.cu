@@ -58,6 +58,10 @@ static_assert(STAGE_BYTES % 1024 == 0 && W_PART_BYTES % 1024 == 0, "swizzle-128B
 
 struct Geometry {
   int d, n_tile, n_tiles, k_blocks, n_a, n_b, rows_per_cta;
+  // Long reductions (d > 1024): even and odd K-blocks accumulate into TWO tensor-memory windows that the epilogue adds in fp32.
+  // The tensor core truncates when it adds into its accumulator, so the 3xTF32 residue grows with the reduction length (1.2e-5
+  // rel-to-max at d = 2048 with one accumulator); halving the length per accumulator halves it. Costs the epilogue / MMA overlap.
+  int split_acc;
   size_t part_bytes;  // bytes of one (hi or lo) image
 };
 
@@ -71,6 +75,7 @@ __host__ __device__ inline Geometry make_geometry(int d) {
   if (g.n_tile <= 256) { g.n_a = g.n_tile; g.n_b = 0; }
   else { g.n_a = ((g.n_tile / 2) + 15) / 16 * 16; g.n_b = g.n_tile - g.n_a; }
   g.rows_per_cta = g.n_tile / 2;  // n_a / 2 rows of the first MMA followed by n_b / 2 rows of the second
+  g.split_acc = (g.k_blocks > 32 && g.n_tile <= 256) ? 1 : 0;
   g.part_bytes = (size_t)g.n_tiles * g.k_blocks * g.n_tile * 128;
   return g;
 }
@@ -137,7 +142,7 @@ __device__ __forceinline__ void trace_event_t(const Params& p, int region, uint3
   }
 }
 
-template <int MODE, bool DROP, bool RELU, bool TRACE, bool BF16>  // BF16 = bf16 operands, one kind::f16 pass; MODE 0 = K2 forward, 1 = K4a dgrad, 2 = dense forward (atom message passing); TRACE = the role-timeline build (scripts/trace_pair.py)
+template <int MODE, bool DROP, bool RELU, bool TRACE, bool BF16, bool SPLIT>  // SPLIT = two accumulators per pass (d > 1024); BF16 = bf16 operands, one kind::f16 pass; MODE 0 = K2 forward, 1 = K4a dgrad, 2 = dense forward (atom message passing); TRACE = the role-timeline build (scripts/trace_pair.py)
 __global__ void __launch_bounds__(THREADS, 1)
 layer_gemm_pair(const Params p) {
   auto trace_event = [](const Params& pp, int region, uint32_t& cursor, int ev, int64_t tile, int aux = 0) {
@@ -203,7 +208,8 @@ layer_gemm_pair(const Params p) {
     const int chunks = geo.n_tile / EPI_COLS + (rem ? 1 : 0);
     const int sub = lane & 7, rsub = lane >> 3;
     const bool has_resid = MODE != 1 && p.resid != nullptr;
-    const int shared_chunks = 2 * geo.n_tile > 512 ? (2 * geo.n_tile - 512) / EPI_COLS : 0;  // overlap of the two TMEM windows
+    // overlap of the two TMEM windows (with two accumulators per pass everything is "shared": hand back after the last step)
+    const int shared_chunks = SPLIT ? chunks : (2 * geo.n_tile > 512 ? (2 * geo.n_tile - 512) / EPI_COLS : 0);
     int tw = 0;
     for (int tile = first_tile; tile < pair_tiles; tile += tile_stride) {
       const int64_t row0 = (int64_t)tile * (2 * TILE_M) + rank * TILE_M + warp * 32;
@@ -212,9 +218,9 @@ layer_gemm_pair(const Params p) {
         // pass drains the overlap first and then hands tensor memory back, so the next tile's MMAs run under the rest of
         // the epilogue. Window 0 shares its LAST columns, window 1 its first: window 0 therefore puts the narrow step first,
         // so that the overlap is a whole number of 32-column steps in both.
-        const int col_base = tw ? 512 - geo.n_tile : 0;
-        const bool narrow_first = tw == 0 && rem != 0 && shared_chunks > 0;
-        const int first = (tw == 0 && shared_chunks > 0) ? chunks - shared_chunks : 0;
+        const int col_base = (tw && !SPLIT) ? 512 - geo.n_tile : 0;
+        const bool narrow_first = tw == 0 && rem != 0 && shared_chunks > 0 && !SPLIT;
+        const int first = (tw == 0 && shared_chunks > 0 && !SPLIT) ? chunks - shared_chunks : 0;
         auto chunk_at = [&](int k) { int c = k + first; return c >= chunks ? c - chunks : c; };
         auto chunk_c0 = [&](int cc) { return narrow_first ? (cc == 0 ? 0 : rem + EPI_COLS * (cc - 1)) : EPI_COLS * cc; };
         auto chunk_w = [&](int cc) { return rem == 0 ? EPI_COLS : (narrow_first ? (cc == 0 ? rem : EPI_COLS) : (cc == chunks - 1 ? rem : EPI_COLS)); };
@@ -247,18 +253,29 @@ layer_gemm_pair(const Params p) {
           const int c0 = chunk_c0(cc), w = chunk_w(cc);
           const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(col_base + c0);
           uint32_t v[16];
-          tmem_ld16(taddr, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          if (w > 16) {
-            tmem_ld16(taddr + 16, v);
+          // thread = accumulator row: 16 columns -> pieces `half * 4 .. + 3` of its 128-byte staging row (XOR-swizzled). With two
+          // accumulators per pass the second one is added through the staging row (read-modify-write of the thread's own pieces),
+          // which keeps the register footprint of the common single-accumulator case unchanged.
+          auto stage16 = [&](uint32_t ta, int half) {
+            tmem_ld16(ta, v);
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(stage + lane * 128 + (((q + 4) ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          }
+              *reinterpret_cast<uint4*>(stage + lane * 128 + (((q + 4 * half) ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            if (SPLIT) {
+              tmem_ld16(ta + 256u, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float4* slot = reinterpret_cast<float4*>(stage + lane * 128 + (((q + 4 * half) ^ (lane & 7)) << 4));
+                float4 a = *slot;
+                a.x += __uint_as_float(v[4 * q]); a.y += __uint_as_float(v[4 * q + 1]); a.z += __uint_as_float(v[4 * q + 2]); a.w += __uint_as_float(v[4 * q + 3]);
+                *slot = a;
+              }
+            }
+          };
+          stage16(taddr, 0);
+          if (w > 16) stage16(taddr + 16, 1);
           if (shared_chunks > 0 && k == shared_chunks - 1) {  // the overlap has left tensor memory: the next pass may start its MMAs
             tc_fence_before();
             __syncwarp();
@@ -309,7 +326,7 @@ layer_gemm_pair(const Params p) {
       uint32_t ph = 0, tphase = 0;
       for (int tile = first_tile; tile < pair_tiles; tile += tile_stride) {
         for (int nt = 0; nt < geo.n_tiles; ++nt) {
-          const uint32_t col_base = tw ? (uint32_t)(512 - geo.n_tile) : 0u;
+          const uint32_t win_base = (tw && !SPLIT) ? (uint32_t)(512 - geo.n_tile) : 0u;
           if (lane == 0) trace_event(p, 1, tcur, 10, tile);
           mbar_wait(bar_tmem_empty, tphase ^ 1);
           tc_fence_after();
@@ -322,6 +339,8 @@ layer_gemm_pair(const Params p) {
             if (elect_one()) {
               const int rem = d - kb * BLOCK_K;
               const uint32_t st0 = sbase + s * STAGE_BYTES;
+              const uint32_t col_base = SPLIT ? (uint32_t)(kb & 1) * 256u : win_base;  // odd K-blocks -> the second accumulator
+              const int kfirst = SPLIT ? kb >> 1 : kb;                                   // 0 on an accumulator's first K-block
               const uint32_t d0 = tmem_base + col_base, d1 = d0 + (uint32_t)geo.n_a;
               if (BF16) {
                 const int ksteps = (p.ablate & 8) ? 0 : (rem >= BLOCK_K ? 2 : (rem + 15) / 16);  // K = 16 bf16 per MMA
@@ -331,7 +350,7 @@ layer_gemm_pair(const Params p) {
                 for (int j = 0; j < 2; ++j) {
                   if (j < ksteps) {
                     const uint32_t k16 = j * 2;  // 16 bf16 = 32 bytes inside the 64-byte swizzle row
-                    const uint32_t acc = (kb | j) != 0 ? 1u : 0u;
+                    const uint32_t acc = (kfirst | j) != 0 ? 1u : 0u;
                     umma2_bf16_lo(d0, a_bf + k16, w_bf + k16, KMAJOR_SW64_DESC_HI, idesc_a, acc);
                     if (geo.n_b > 0) umma2_bf16_lo(d1, a_bf + k16, w_bf + woff + k16, KMAJOR_SW64_DESC_HI, idesc_b, acc);
                   }
@@ -345,7 +364,7 @@ layer_gemm_pair(const Params p) {
               for (int j = 0; j < BLOCK_K / 8; ++j) {
                 if (j < ksteps) {
                   const uint32_t k16 = j * 2;
-                  const uint32_t acc = (kb | j) != 0 ? 1u : 0u;
+                  const uint32_t acc = (kfirst | j) != 0 ? 1u : 0u;
                   if (p.products == 3) {
                     umma2_tf32_lo(d0, a_lo + k16, w_hi + k16, KMAJOR_SW128_DESC_HI, idesc_a, acc);
                     umma2_tf32_lo(d0, a_hi + k16, w_lo + k16, KMAJOR_SW128_DESC_HI, idesc_a, 1u);
@@ -622,12 +641,12 @@ __global__ void __launch_bounds__(256) pair_weight_prepare_bf16_kernel(const flo
   *reinterpret_cast<uint2*>(image + off) = packed;
 }
 
-template <int MODE, bool DROP, bool RELU, bool TRACE, bool BF16>
+template <int MODE, bool DROP, bool RELU, bool TRACE, bool BF16, bool SPLIT>
 static int launch_variant(const Params& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(layer_gemm_pair<MODE, DROP, RELU, TRACE, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(layer_gemm_pair<MODE, DROP, RELU, TRACE, BF16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(layer_gemm_pair)");
   const int64_t pair_tiles = (p.E + 2 * TILE_M - 1) / (2 * TILE_M);
@@ -647,25 +666,29 @@ static int launch_variant(const Params& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, layer_gemm_pair<MODE, DROP, RELU, TRACE, BF16>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, layer_gemm_pair<MODE, DROP, RELU, TRACE, BF16, SPLIT>, p);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(layer_gemm_pair)");
   NT_LAUNCH_CHECK("layer_gemm_pair", 1);
   return NT_OK;
 }
 
-template <int MODE>
-static int launch(const Params& p, cudaStream_t st) {
+template <int MODE, bool BF16, bool SPLIT>
+static int launch_by_flags(const Params& p, cudaStream_t st) {
   const bool drop = p.drop_p > 0.f;
   const bool relu = MODE != 0 || p.act == NT_ACT_RELU;  // the dense modes have no activation prologue
-  if (p.products == 0) {  // bf16 operands
-    if (MODE != 0) return drop ? launch_variant<MODE, true, true, false, true>(p, st) : launch_variant<MODE, false, true, false, true>(p, st);
-    if (drop) return relu ? launch_variant<MODE, true, true, false, true>(p, st) : launch_variant<MODE, true, false, false, true>(p, st);
-    return relu ? launch_variant<MODE, false, true, false, true>(p, st) : launch_variant<MODE, false, false, false, true>(p, st);
-  }
-  if (MODE != 2 && p.trace != nullptr && !drop && relu) return launch_variant<MODE, false, true, true, false>(p, st);  // the role-timeline build exists for the default case only
-  if (MODE != 0) return drop ? launch_variant<MODE, true, true, false, false>(p, st) : launch_variant<MODE, false, true, false, false>(p, st);
-  if (drop) return relu ? launch_variant<MODE, true, true, false, false>(p, st) : launch_variant<MODE, true, false, false, false>(p, st);
-  return relu ? launch_variant<MODE, false, true, false, false>(p, st) : launch_variant<MODE, false, false, false, false>(p, st);
+  if (MODE != 0) return drop ? launch_variant<MODE, true, true, false, BF16, SPLIT>(p, st) : launch_variant<MODE, false, true, false, BF16, SPLIT>(p, st);
+  if (drop) return relu ? launch_variant<MODE, true, true, false, BF16, SPLIT>(p, st) : launch_variant<MODE, true, false, false, BF16, SPLIT>(p, st);
+  return relu ? launch_variant<MODE, false, true, false, BF16, SPLIT>(p, st) : launch_variant<MODE, false, false, false, BF16, SPLIT>(p, st);
+}
+
+template <int MODE>
+static int launch(const Params& p, cudaStream_t st) {
+  if (p.products == 0) return launch_by_flags<MODE, true, false>(p, st);  // bf16 operands (the mode's error dwarfs the accumulator's)
+  if (p.geo.split_acc) return launch_by_flags<MODE, false, true>(p, st);  // d > 1024: two accumulators per pass
+  const bool drop = p.drop_p > 0.f;
+  const bool relu = MODE != 0 || p.act == NT_ACT_RELU;
+  if (MODE != 2 && p.trace != nullptr && !drop && relu) return launch_variant<MODE, false, true, true, false, false>(p, st);  // the role-timeline build exists for the default case only
+  return launch_by_flags<MODE, false, false>(p, st);
 }
 
 unsigned long long* g_trace_buffer = nullptr;
@@ -708,6 +731,7 @@ int pair_layer_forward(const float* h, const float* n, const int32_t* src, const
   p.src = src; p.rev = rev; p.wimg = static_cast<const uint8_t*>(wimg); p.bias = bias;
   p.resid = residual ? h : nullptr; p.out = out; p.E = E; p.geo = pair::make_geometry((int)d);
   p.act = act; p.act_param = act_param; p.products = products;
+  if (products == 0) p.geo.split_acc = 0;
   pair::fill_dropout(p, drop_p, seed, offset);
   (void)V;
   p.a0 = n; p.a1 = h;
@@ -722,6 +746,7 @@ int pair_dense_forward(const float* x, const void* wimg, const float* bias, cons
   p.a0 = x; p.wimg = static_cast<const uint8_t*>(wimg); p.bias = bias; p.resid = resid; p.out = out; p.E = R;
   p.geo = pair::make_geometry((int)d);
   p.act = NT_ACT_IDENTITY; p.products = products;
+  if (products == 0) p.geo.split_acc = 0;
   pair::fill_dropout(p, drop_p, seed, offset);
   return pair::launch<2>(p, st);
 }
@@ -731,6 +756,7 @@ int pair_layer_dgrad(const float* g, const void* wimg, int64_t E, int64_t d, flo
   pair::Params p{};
   p.wimg = static_cast<const uint8_t*>(wimg); p.out = g_m; p.E = E; p.geo = pair::make_geometry((int)d);
   p.act = NT_ACT_IDENTITY; p.products = products;
+  if (products == 0) p.geo.split_acc = 0;
   pair::fill_dropout(p, drop_p, seed, offset);
   p.a0 = g;
   return pair::launch<1>(p, st);
