@@ -1,4 +1,5 @@
-// K2 forward and K4a dgrad, second generation: CTA-pair tcgen05 (cta_group::2) with every bulk transfer on the copy engine.
+// K2 forward, K4a dgrad and the dense Linear of the atom variant, second generation: CTA-pair tcgen05 (cta_group::2), A operand
+// gathered with cp.async (LDGSTS), weight tiles on the copy engine (cp.async.bulk).
 //
 //   D[256 edges, N] = A[256, K] . B[N, K]^T     fp32 in, fp32 out, 3xTF32 error-compensated (see gemm_tc.cu)
 //
@@ -11,12 +12,13 @@
 // The A operand is produced by eight warps in two steps:
 //   1. each thread copies "its" 16-byte units of the next tiles straight from global memory into the 128-byte-swizzled
 //      K-major layout with cp.async (LDGSTS): rows n[src[e]] and h[rev[e]] for K2, rows of g for K4a. No registers are
-//      tied up, so STAGES - 1 K-blocks (64 KB per SM) stay in flight; the next tile's rows are pulled into L2 one tile
-//      ahead with cp.async.bulk.prefetch.L2. (tile::gather4 on the copy engine was measured first: it sustains only
-//      ~17 B/clk/SM for 128-byte rows — scripts/probes/probe_tma_bw.cu — about half of what this kernel needs.)
+//      tied up, so STAGES - 1 K-blocks (64 KB per SM) stay in flight. (tile::gather4 on the copy engine was measured
+//      first: it sustains only ~17 B/clk/SM for 128-byte rows - scripts/probes/probe_tma_bw.cu - about half of what this
+//      kernel needs; explicit L2 prefetches of the next tile's rows were measured too and bought nothing.)
 //   2. the same thread rewrites the units IN PLACE once they have landed (cp.async.wait_group — a thread's own copies,
 //      no barrier): m = n - act(h) (K2) or dropout(g) (K4a), split into TF32 hi (over the n tile) and lo (over the h
-//      tile); K2 also streams m to global memory for the weight gradient.
+//      tile); K2 also streams m to global memory for the weight gradient. In bf16 mode the tile is rounded to bf16 instead
+//      (64-byte rows, one kind::f16 MMA pass).
 // W arrives as two bulk copies (hi, lo) of the pre-split, pre-swizzled per-CTA image written by pair_weight_prepare.
 //
 // Synchronisation (mbarriers; L = lives in the leader CTA and is also arrived on remotely by the peer):
