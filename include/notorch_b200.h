@@ -219,6 +219,17 @@ int nt_layer_backward_epilogue(const void* g, const void* h, const void* g_n, co
                                void* g_h, int dtype, nt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K5 + K6 fused (same arithmetic as nt_seg_reduce over the by-source CSR followed by nt_layer_backward_epilogue, bit-identical):
+ * every edge sums the g_m rows of the outgoing edges of its destination atom itself (src_ell / src_rowptr / src_perm: the CSR of
+ * edge_index[0] and its ELL copy from nt_csr_to_ell), so g_n is never written or read.
+ * ---------------------------------------------------------------------------------------------- */
+int nt_layer_backward_epilogue_fused(const void* g, const void* h, const void* g_m, const int32_t* dst,
+                                     const int32_t* src_rowptr, const int32_t* src_perm, const int32_t* src_ell,
+                                     const int32_t* rev_rowptr, const int32_t* rev_perm, const int32_t* dst_rowptr,
+                                     int64_t E, int64_t d, int act, float act_param, int residual, int mean,
+                                     void* g_h, int dtype, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * GraphEmbedding (row N1, the step before the block) — replaces the two nn.EmbeddingBag(mode="sum") of
  * notorch/nn/gnn/embed.py:20-24 on 2-D index input: out[i,:] = sum_{j<bag} table[idx[i,j],:]  (idx int64 [n,bag]).
  * *status bit 0 is set if an index is outside [0, num_types). Backward: g_table[t,:] = sum over all (i,j) with

@@ -279,6 +279,49 @@ __global__ void __launch_bounds__(ROW_THREADS) layer_bwd_epilogue(const float* _
   }
 }
 
+// K5 + K6 fused: instead of reading a precomputed g_n[dst[e]] (K5 = segmented sum of g_m over the outgoing edges of every atom,
+// an [E,d] read and a [V,d] write per depth), every edge sums the g_m rows of the outgoing edges of ITS destination atom itself,
+// through the ELL copy of the by-source CSR (same ascending order, so the value is bit-identical to K5's). The ~2.2 extra rows
+// per edge are rows its neighbours in the same molecule read too: they come from L2 / L1, not from DRAM.
+template <int AK>
+__global__ void __launch_bounds__(ROW_THREADS) layer_bwd_epilogue_fused(const float* __restrict__ g, const float* __restrict__ h,
+                                                                         const float* __restrict__ g_m, const int32_t* __restrict__ dst,
+                                                                         const int32_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_perm,
+                                                                         const int4* __restrict__ src_ell, const int32_t* __restrict__ rev_rowptr,
+                                                                         const int32_t* __restrict__ rev_perm, const int32_t* __restrict__ dst_rowptr,
+                                                                         int d, int chunks, int64_t total, int act, float act_param, int residual,
+                                                                         int mean, float* __restrict__ g_h) {
+  int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
+  if (t >= total) return;
+  const int e = (int)(t / chunks);
+  const int c = (int)(t - (int64_t)e * chunks) * 4;
+  const int v = __ldg(dst + e);
+  const int lo = __ldg(rev_rowptr + e), hi = __ldg(rev_rowptr + e + 1);
+  const int4 nb = __ldg(src_ell + v);
+  const int slo = __ldg(src_rowptr + v), shi = __ldg(src_rowptr + v + 1);
+  const int id[4] = {nb.x, nb.y, nb.z, nb.w};
+  float4 row[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (id[u] >= 0) row[u] = ldg4(g_m + (int64_t)id[u] * d + c);
+  const float4 hv = ldg4_stream(h + (int64_t)e * d + c);
+  float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (id[u] >= 0) ga = add4(ga, row[u]);
+  for (int j = slo + 4; j < shi; ++j) ga = add4(ga, ldg4(g_m + (int64_t)__ldg(src_perm + j) * d + c));
+  if (mean) {
+    const float cnt = (float)max(__ldg(dst_rowptr + v + 1) - __ldg(dst_rowptr + v), 1);
+    ga = make_float4(ga.x / cnt, ga.y / cnt, ga.z / cnt, ga.w / cnt);
+  }
+  float4 sub = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = lo; j < hi; ++j) sub = add4(sub, ldg4(g_m + (int64_t)__ldg(rev_perm + j) * d + c));
+  float4 r = make_float4(seg_act_bwd<AK>(hv.x, act, act_param) * (ga.x - sub.x), seg_act_bwd<AK>(hv.y, act, act_param) * (ga.y - sub.y),
+                         seg_act_bwd<AK>(hv.z, act, act_param) * (ga.z - sub.z), seg_act_bwd<AK>(hv.w, act, act_param) * (ga.w - sub.w));
+  if (residual) r = add4(ldg4_stream(g + (int64_t)e * d + c), r);
+  stg4(g_h + (int64_t)e * d + c, r);
+}
+
 __global__ void __launch_bounds__(ROW_THREADS) dropout_mask_kernel(int64_t total, float p, uint64_t seed, uint64_t offset, float* __restrict__ mask) {
   int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
   if (t >= total) return;
@@ -407,6 +450,41 @@ extern "C" int nt_layer_backward_epilogue(const void* g, const void* h, const vo
                                                                                           (int)d, total, act, act_param, residual, mean, out);
   }
   NT_LAUNCH_CHECK("nt_layer_backward_epilogue", 1);
+  return NT_OK;
+}
+
+extern "C" int nt_layer_backward_epilogue_fused(const void* g, const void* h, const void* g_m, const int32_t* dst, const int32_t* src_rowptr,
+                                                const int32_t* src_perm, const int32_t* src_ell, const int32_t* rev_rowptr, const int32_t* rev_perm,
+                                                const int32_t* dst_rowptr, int64_t E, int64_t d, int act, float act_param, int residual, int mean,
+                                                void* g_h, int dtype, nt_stream_t stream) {
+  if (dtype != NT_F32) { set_error("nt_layer_backward_epilogue_fused: only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
+  NT_CHECK_ARG(d > 0 && d < (1 << 20) && E >= 0 && E < INT32_MAX, "nt_layer_backward_epilogue_fused: bad sizes");
+  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "nt_layer_backward_epilogue_fused: bad activation");
+  if (E == 0) return NT_OK;
+  NT_CHECK_ARG(h && g_m && dst && src_rowptr && src_perm && src_ell && rev_rowptr && rev_perm && g_h, "nt_layer_backward_epilogue_fused: null pointer");
+  NT_CHECK_ARG(!residual || g, "nt_layer_backward_epilogue_fused: residual needs g");
+  NT_CHECK_ARG(!mean || dst_rowptr, "nt_layer_backward_epilogue_fused: mean needs dst_rowptr");
+  if (!vec_ok(d, g, h, g_m, g_h, src_ell)) {
+    set_error("nt_layer_backward_epilogue_fused: needs d %% 4 == 0 and 16-byte aligned rows (use nt_seg_reduce + nt_layer_backward_epilogue)");
+    return NT_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = as_stream(stream);
+  const float *gf = static_cast<const float*>(g), *hf = static_cast<const float*>(h), *gm = static_cast<const float*>(g_m);
+  float* out = static_cast<float*>(g_h);
+  const int chunks = (int)(d / 4);
+  const int64_t total = E * chunks;
+  const unsigned grid = (unsigned)cdiv(total, ROW_THREADS);
+  const int4* ell4 = reinterpret_cast<const int4*>(src_ell);
+  if (act == NT_ACT_IDENTITY)
+    layer_bwd_epilogue_fused<0><<<grid, ROW_THREADS, 0, st>>>(gf, hf, gm, dst, src_rowptr, src_perm, ell4, rev_rowptr, rev_perm, dst_rowptr, (int)d, chunks,
+                                                              total, act, act_param, residual, mean, out);
+  else if (act == NT_ACT_RELU)
+    layer_bwd_epilogue_fused<1><<<grid, ROW_THREADS, 0, st>>>(gf, hf, gm, dst, src_rowptr, src_perm, ell4, rev_rowptr, rev_perm, dst_rowptr, (int)d, chunks,
+                                                              total, act, act_param, residual, mean, out);
+  else
+    layer_bwd_epilogue_fused<2><<<grid, ROW_THREADS, 0, st>>>(gf, hf, gm, dst, src_rowptr, src_perm, ell4, rev_rowptr, rev_perm, dst_rowptr, (int)d, chunks,
+                                                              total, act, act_param, residual, mean, out);
+  NT_LAUNCH_CHECK("nt_layer_backward_epilogue_fused", 1);
   return NT_OK;
 }
 

@@ -36,6 +36,7 @@ ACT_CODES = {
 _GEMM_MODES = {"tf32x3": GEMM_TF32X3, "fp32": GEMM_FP32, "tf32": GEMM_TF32, "bf16": GEMM_BF16}
 _gemm_mode = _GEMM_MODES[os.environ.get("NOTORCH_B200_GEMM", "tf32x3").lower()]
 _validate_mode = os.environ.get("NOTORCH_B200_VALIDATE", "sync").lower()  # "sync" | "deferred" | "off"
+_fuse_k5_k6 = os.environ.get("NOTORCH_B200_FUSE_K5K6", "1") != "0"  # backward epilogue sums the outgoing-edge gradients itself (no K5 launch)
 
 
 def set_gemm_mode(mode: str) -> None:
@@ -495,11 +496,17 @@ class _Layer(torch.autograd.Function):
                 g_m = torch.empty_like(h)
                 _run("K4a:nt_layer_backward_dgrad", L.nt_layer_backward_dgrad, _p(g), _p(W), _p(img_t), E, d, p, seed, offset, _p(g_m), NT_F32,
                      mode, _stream())
-                g_n = _seg_reduce_raw(g_m, csr.by_src, tag="K5")
                 gh = torch.empty_like(h)
-                _run("K6:nt_layer_backward_epilogue", L.nt_layer_backward_epilogue, _p(g), _p(h), _p(g_n), _p(g_m), _p(csr.dst),
-                     _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr), E, d, act, act_param, int(residual), int(mean), _p(gh),
-                     NT_F32, _stream())
+                ell = _ell_of(csr.by_src) if (_fuse_k5_k6 and d % 4 == 0) else None
+                if ell is not None:  # K5 + K6 in one kernel: g_n is never materialised
+                    _run("K6:nt_layer_backward_epilogue", L.nt_layer_backward_epilogue_fused, _p(g), _p(h), _p(g_m), _p(csr.dst),
+                         _p(csr.by_src.rowptr), _p(csr.by_src.perm), _p(ell), _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr),
+                         E, d, act, act_param, int(residual), int(mean), _p(gh), NT_F32, _stream())
+                else:
+                    g_n = _seg_reduce_raw(g_m, csr.by_src, tag="K5")
+                    _run("K6:nt_layer_backward_epilogue", L.nt_layer_backward_epilogue, _p(g), _p(h), _p(g_n), _p(g_m), _p(csr.dst),
+                         _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr), E, d, act, act_param, int(residual), int(mean),
+                         _p(gh), NT_F32, _stream())
         return gh, gW, gb, None, None, None, None, None, None, None, None, None
 
 
