@@ -451,16 +451,18 @@ def run_ours(args, wl, batch):
         g = torch.cuda.CUDAGraph()
         g2 = None
         n0 = _lib.lib().nt_kernel_launch_count()
+        # every graph of this process draws its intermediates from ONE memory pool (they are replayed one after the other and
+        # nothing but the pinned loss and the parameters outlives a replay): three private pools do not fit 180 GB at configs[4]
         if world == 1:
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, pool=graph_pool):
                 loss = step(src, from_host)
                 pinned_loss.copy_(loss.detach().reshape(1), non_blocking=True)
         else:
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, pool=graph_pool):
                 loss = fwd_bwd(src, from_host)
                 pinned_loss.copy_(loss.detach().reshape(1), non_blocking=True)
             g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2, pool=g.pool()):
+            with torch.cuda.graph(g2, pool=graph_pool):
                 opt.step()
         return g, pinned_loss, _lib.lib().nt_kernel_launch_count() - n0, g2
 
@@ -472,6 +474,7 @@ def run_ours(args, wl, batch):
 
     graphs: dict[bool, tuple] = {}
     launch_mode = "eager"
+    graph_pool = torch.cuda.graph_pool_handle() if use_graph else None
     if use_graph:
         try:
             graphs[False] = capture(resident, False)
@@ -487,7 +490,9 @@ def run_ours(args, wl, batch):
         except Exception as exc:  # capture is an optimisation, never a requirement
             print(f"bench.py: CUDA graph capture failed ({type(exc).__name__}: {exc}); launching eagerly", file=sys.stderr)
             graphs = {}
+            devbuf = None
             torch.cuda.synchronize()
+            torch.cuda.empty_cache()
             ops.set_index_validation("deferred")
 
     def timed(nsteps: int, src: dict, from_host: bool):
