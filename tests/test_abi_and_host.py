@@ -135,6 +135,36 @@ def test_cpu_tensors_raise_no_fallback():
         ChempropBlock(hidden_dim=8, depth=1)(G)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Sum()(G)
+    from notorch_b200.nn import AtomMessagePassing, GraphEmbedding, Norm
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        AtomMessagePassing(hidden_dim=8, depth=1)(G)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Norm()(G)
+
+
+def test_gemm_modes_and_new_entry_points_reject_bad_arguments():
+    """Argument validation of the entry points added for the atom variant, the ELL reductions and the bf16 mode (no GPU needed: every
+    call is rejected before a launch)."""
+    from notorch_b200 import _lib, ops
+
+    lib = _lib.lib()
+    assert lib.nt_seg_reduce_ell(None, 300, None, None, None, 10, 1, 0.0, 0, 1.0, None, None, None, _lib.NT_F32, None) != 0  # null ell
+    assert lib.nt_csr_to_ell(None, None, 10, None, None) != 0
+    assert lib.nt_dense_forward(None, None, None, None, 10, 300, 0.0, 0, 0, None, _lib.NT_F32, 7, None) != 0  # bad gemm_mode
+    assert lib.nt_dense_forward(None, None, None, None, 10, 300, 0.0, 0, 0, None, _lib.NT_F32, _lib.GEMM_TF32X3, None) != 0  # null pointers
+    assert lib.nt_layer_backward_epilogue_fused(None, None, None, None, None, None, None, None, None, None, 10, 300, 1, 0.0, 1, 0, None,
+                                                _lib.NT_F32, None) != 0
+    assert lib.nt_weight_prepare(None, 300, 0, None, 5, None) != 0  # bad dtype
+    old = ops.get_gemm_mode()
+    try:
+        for mode in ("tf32x3", "tf32", "bf16", "fp32"):
+            ops.set_gemm_mode(mode)
+            assert ops.get_gemm_mode() == mode
+        with pytest.raises(KeyError):
+            ops.set_gemm_mode("fp8")
+    finally:
+        ops.set_gemm_mode(old)
 
 
 def test_synth_generator_statistics_and_contract():
