@@ -146,3 +146,33 @@ def test_bf16_layer_is_deterministic_and_equals_the_product_of_rounded_operands(
     m = (n[src] - a[rev]).float()
     ref = h.double() + m.bfloat16().double() @ W.bfloat16().double().T + b.double()
     assert_close(out1, ref, "bf16-rounded operands, exact product", 1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d", [64, 300])
+def test_bf16_mode_with_dropout_uses_the_same_keep_mask_forward_and_backward(bf16_mode, d):
+    """Dropout in bf16 mode: K2's epilogue mask, K4a's operand mask and K4b's mask are the same function of (seed, offset); checked
+    against the fp64 oracle evaluated with the kernel's own keep-mask (smooth comparison: single layer, relative L2)."""
+    from notorch_b200 import ops
+    from oracle import dmpnn_oracle as O
+
+    p = oracle_inputs(32, d, 1, seed=4)
+    E, V, pr = p["E"], p["V"], 0.25
+    csr = ops.build_graph_csr(p["edge_index"].cuda(), p["rev_index"].cuda(), V)
+    gen = torch.Generator().manual_seed(1)
+    h, g = torch.randn(E, d, generator=gen), torch.randn(E, d, generator=gen)
+    W, b = p["weights"][0], p["biases"][0]
+    seed, offset = 7654321, 5
+    mask = ops.dropout_mask(E, d, pr, seed, offset, "cuda").cpu()
+    hc, Wc, bc = h.cuda().requires_grad_(True), W.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    out = ops._Layer.apply(hc, Wc, bc, csr, 1, 0.0, False, True, pr, seed, offset, ops._gemm_mode)
+    (out * g.cuda()).sum().backward()
+    h64, W64, b64 = h.double().requires_grad_(True), W.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref, _ = O.layer_forward(h64, V, p["edge_index"][0], p["edge_index"][1], p["rev_index"], W64, b64, keep_mask=mask.bool(), p=pr)
+    (ref * g.double()).sum().backward()
+    dropped = ~mask.bool()
+    assert torch.equal((out.cpu() - h)[dropped], torch.zeros(int(dropped.sum())))  # dropped entries are exactly the residual
+    _assert_l2(out, ref.detach(), "dropout out (bf16 mode)", REL_BF16_FWD)
+    _assert_l2(hc.grad, h64.grad, "dropout grad h (bf16 mode)", REL_BF16_BWD)
+    _assert_l2(Wc.grad, W64.grad, "dropout grad W (bf16 mode)", REL_BF16_BWD)
+    _assert_l2(bc.grad, b64.grad, "dropout grad b (bf16 mode)", REL_BF16_BWD)
