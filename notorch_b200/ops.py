@@ -441,6 +441,56 @@ class _GatherAdd(torch.autograd.Function):
 _dropout_calls = 0
 
 
+def _layer_forward_raw(h: Tensor, W: Tensor, b: Tensor | None, csr: GraphCSR, act: int, act_param: float, mean: bool, residual: bool,
+                       p: float, seed: int, offset: int, mode: int, save_m: bool) -> tuple[Tensor, Tensor | None, Tensor]:
+    """K1 + K2 of one depth on raw tensors (no autograd): returns (h', m or None, n)."""
+    E, d = h.shape
+    L = _lib.lib()
+    with torch.cuda.device(h.device):
+        n = _seg_reduce_raw(h, csr.by_dst, act, act_param, mean, tag="K1")
+        img = _weight_image(W, False) if mode != GEMM_FP32 else None
+        out = torch.empty_like(h)
+        m = torch.empty_like(h) if save_m else None
+        _run("K2:nt_layer_forward", L.nt_layer_forward, _p(h), _p(n), _p(csr.src), _p(csr.rev), _p(W), _p(img), _p(b), E, csr.V, d, act,
+             act_param, int(residual), p, seed, offset, _p(out), _p(m), NT_F32, mode, _stream())
+    return out, m, n
+
+
+def _layer_backward_raw(g: Tensor, h: Tensor, m: Tensor | None, n: Tensor | None, W: Tensor, has_bias: bool, csr: GraphCSR, act: int,
+                        act_param: float, mean: bool, residual: bool, p: float, seed: int, offset: int, mode: int, need_w: bool,
+                        need_h: bool) -> tuple[Tensor | None, Tensor | None, Tensor | None]:
+    """K4b, K4a, K5 + K6 of one depth on raw tensors: returns (g_h, g_W, g_b)."""
+    E, d = h.shape
+    g = g.contiguous()
+    L = _lib.lib()
+    gW = gb = gh = None
+    with torch.cuda.device(g.device):
+        if need_w:
+            gW = torch.empty_like(W)
+            gb = torch.empty(d, dtype=W.dtype, device=W.device) if has_bias else None
+            nbytes = L.nt_layer_backward_wgrad_workspace_bytes(E, d)
+            ws = _workspace(g.device, nbytes, slot=1)
+            _run("K4b:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(g), _p(m), _p(h), _p(n), _p(csr.src), _p(csr.rev), E, csr.V, d,
+                 act, act_param, p, seed, offset, _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream())
+        if need_h:
+            img_t = _weight_image(W, True) if mode != GEMM_FP32 else None
+            g_m = torch.empty_like(h)
+            _run("K4a:nt_layer_backward_dgrad", L.nt_layer_backward_dgrad, _p(g), _p(W), _p(img_t), E, d, p, seed, offset, _p(g_m), NT_F32,
+                 mode, _stream())
+            gh = torch.empty_like(h)
+            ell = _ell_of(csr.by_src) if (_fuse_k5_k6 and d % 4 == 0) else None
+            if ell is not None:  # K5 + K6 in one kernel: g_n is never materialised
+                _run("K6:nt_layer_backward_epilogue", L.nt_layer_backward_epilogue_fused, _p(g), _p(h), _p(g_m), _p(csr.dst),
+                     _p(csr.by_src.rowptr), _p(csr.by_src.perm), _p(ell), _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr),
+                     E, d, act, act_param, int(residual), int(mean), _p(gh), NT_F32, _stream())
+            else:
+                g_n = _seg_reduce_raw(g_m, csr.by_src, tag="K5")
+                _run("K6:nt_layer_backward_epilogue", L.nt_layer_backward_epilogue, _p(g), _p(h), _p(g_n), _p(g_m), _p(csr.dst),
+                     _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr), E, d, act, act_param, int(residual), int(mean),
+                     _p(gh), NT_F32, _stream())
+    return gh, gW, gb
+
+
 class _Layer(torch.autograd.Function):
     """One message-passing depth: K1 + K2 forward, K4a + K4b + K5 + K6 backward.
 
@@ -459,16 +509,9 @@ class _Layer(torch.autograd.Function):
             raise RuntimeError(f"notorch_b200: weight {tuple(W.shape)} does not match hidden size {d}")
         if b is not None:
             b = _require(b, "bias", torch.float32, 1)
-        L = _lib.lib()
-        # tensor-core path: K2 also writes the message tensor m, which K4b then streams with TMA
+        # tensor-core path: K2 also writes the message tensor m, which K4b then streams as dense tiles
         save_m = mode != GEMM_FP32 and d % 4 == 0 and (ctx.needs_input_grad[1] or (b is not None and ctx.needs_input_grad[2]))
-        with torch.cuda.device(h.device):
-            n = _seg_reduce_raw(h, csr.by_dst, act, act_param, mean, tag="K1")
-            img = _weight_image(W, False) if mode != GEMM_FP32 else None
-            out = torch.empty_like(h)
-            m = torch.empty_like(h) if save_m else None
-            _run("K2:nt_layer_forward", L.nt_layer_forward, _p(h), _p(n), _p(csr.src), _p(csr.rev), _p(W), _p(img), _p(b), E, csr.V, d, act,
-                 act_param, int(residual), p, seed, offset, _p(out), _p(m), NT_F32, mode, _stream())
+        out, m, n = _layer_forward_raw(h, W, b, csr, act, act_param, mean, residual, p, seed, offset, mode, save_m)
         ctx.save_for_backward(h, m if save_m else n, W)
         ctx.csr, ctx.cfg, ctx.has_bias, ctx.has_m = csr, (act, act_param, mean, residual, p, seed, offset, mode), b is not None, save_m
         return out
@@ -477,36 +520,8 @@ class _Layer(torch.autograd.Function):
     def backward(ctx, g: Tensor):
         h, n_or_m, W = ctx.saved_tensors
         m, n = (n_or_m, None) if ctx.has_m else (None, n_or_m)
-        csr = ctx.csr
-        act, act_param, mean, residual, p, seed, offset, mode = ctx.cfg
-        E, d = h.shape
-        g = g.contiguous()
-        L = _lib.lib()
-        gW = gb = gh = None
-        with torch.cuda.device(g.device):
-            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-                gW = torch.empty_like(W)
-                gb = torch.empty(d, dtype=W.dtype, device=W.device) if ctx.has_bias else None
-                nbytes = L.nt_layer_backward_wgrad_workspace_bytes(E, d)
-                ws = _workspace(g.device, nbytes, slot=1)
-                _run("K4b:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(g), _p(m), _p(h), _p(n), _p(csr.src), _p(csr.rev), E, csr.V, d,
-                     act, act_param, p, seed, offset, _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream())
-            if ctx.needs_input_grad[0]:
-                img_t = _weight_image(W, True) if mode != GEMM_FP32 else None
-                g_m = torch.empty_like(h)
-                _run("K4a:nt_layer_backward_dgrad", L.nt_layer_backward_dgrad, _p(g), _p(W), _p(img_t), E, d, p, seed, offset, _p(g_m), NT_F32,
-                     mode, _stream())
-                gh = torch.empty_like(h)
-                ell = _ell_of(csr.by_src) if (_fuse_k5_k6 and d % 4 == 0) else None
-                if ell is not None:  # K5 + K6 in one kernel: g_n is never materialised
-                    _run("K6:nt_layer_backward_epilogue", L.nt_layer_backward_epilogue_fused, _p(g), _p(h), _p(g_m), _p(csr.dst),
-                         _p(csr.by_src.rowptr), _p(csr.by_src.perm), _p(ell), _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr),
-                         E, d, act, act_param, int(residual), int(mean), _p(gh), NT_F32, _stream())
-                else:
-                    g_n = _seg_reduce_raw(g_m, csr.by_src, tag="K5")
-                    _run("K6:nt_layer_backward_epilogue", L.nt_layer_backward_epilogue, _p(g), _p(h), _p(g_n), _p(g_m), _p(csr.dst),
-                         _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr), E, d, act, act_param, int(residual), int(mean),
-                         _p(gh), NT_F32, _stream())
+        need_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        gh, gW, gb = _layer_backward_raw(g, h, m, n, W, ctx.has_bias, ctx.csr, *ctx.cfg, need_w, ctx.needs_input_grad[0])
         return gh, gW, gb, None, None, None, None, None, None, None, None, None
 
 
