@@ -218,6 +218,14 @@ int nt_layer_backward_epilogue(const void* g, const void* h, const void* g_n, co
                                int act, float act_param, int residual, int mean,
                                void* g_h, int dtype, nt_stream_t stream);
 
+/* K6 after a max / min forward reduction (chemprop.py:39 with reduce in {"max","min"}): torch_scatter routes the gradient of an
+ * arg-reduction to the argument row only, so g_a[e,c] = (arg[dst[e],c] == e ? g_n[dst[e],c] : 0) - sum_{j in revinv(e)} g_m[..];
+ * arg is the [V,d] int32 output of nt_seg_extreme. */
+int nt_layer_backward_epilogue_arg(const void* g, const void* h, const void* g_n, const void* g_m,
+                                   const int32_t* dst, const int32_t* arg, const int32_t* rev_rowptr,
+                                   const int32_t* rev_perm, int64_t E, int64_t d, int act, float act_param,
+                                   int residual, void* g_h, int dtype, nt_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K5 + K6 fused (same arithmetic as nt_seg_reduce over the by-source CSR followed by nt_layer_backward_epilogue, bit-identical):
  * every edge sums the g_m rows of the outgoing edges of its destination atom itself (src_ell / src_rowptr / src_perm: the CSR of
@@ -254,6 +262,11 @@ int nt_embedding_bag_backward(const void* g, const int64_t* idx, int64_t n, int6
  * ---------------------------------------------------------------------------------------------- */
 int nt_seg_max(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments,
                void* out, int32_t* arg, int dtype, nt_stream_t stream);
+/* nt_seg_extreme: scatter(act(x), index, reduce = is_min ? "min" : "max") with its argument (chemprop.py:39,86 for the block-level
+ * arg-reductions): out[s,c] = extreme over the segment of act(x[r,c]), arg[s,c] = the FIRST row attaining it; empty: 0 / -1.
+ * nt_seg_max_backward is the backward of both (g flows to the argument row). */
+int nt_seg_extreme(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments,
+                   int act, float act_param, int is_min, void* out, int32_t* arg, int dtype, nt_stream_t stream);
 int nt_seg_max_backward(const void* g, const int32_t* arg, const int32_t* seg_of_row, int64_t n, int64_t d,
                         void* gx, int dtype, nt_stream_t stream);
 int nt_row_dot(const void* x, const void* y, const int32_t* y_index, int64_t y_rows, int64_t n, int64_t d,

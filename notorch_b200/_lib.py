@@ -45,11 +45,13 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "nt_layer_backward_wgrad_workspace_bytes": (_sz, [_i64, _i64]),
     "nt_layer_backward_wgrad": (_int, [_vp, _vp, _vp, _vp, _i32p, _i32p, _i64, _i64, _i64, _int, _f32, _f32, _u64, _u64, _vp, _vp, _vp, _sz, _int, _int, _vp]),
     "nt_layer_backward_epilogue": (_int, [_vp, _vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _int, _vp, _int, _vp]),
+    "nt_layer_backward_epilogue_arg": (_int, [_vp, _vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _vp, _int, _vp]),
     "nt_layer_backward_epilogue_fused": (_int, [_vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _int, _vp, _int, _vp]),
     "nt_embedding_bag_sum": (_int, [_vp, _i64, _i64p, _i64, _i64, _i64, _vp, _i32p, _int, _vp]),
     "nt_embedding_bag_backward_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "nt_embedding_bag_backward": (_int, [_vp, _i64p, _i64, _i64, _i64, _i64, _vp, _vp, _sz, _int, _vp]),
     "nt_seg_max": (_int, [_vp, _i64, _i32p, _i32p, _i64, _vp, _i32p, _int, _vp]),
+    "nt_seg_extreme": (_int, [_vp, _i64, _i32p, _i32p, _i64, _int, _f32, _int, _vp, _i32p, _int, _vp]),
     "nt_seg_max_backward": (_int, [_vp, _i32p, _i32p, _i64, _i64, _vp, _int, _vp]),
     "nt_row_dot": (_int, [_vp, _vp, _i32p, _i64, _i64, _i64, _f32, _f32, _vp, _int, _vp]),
     "nt_seg_softmax": (_int, [_vp, _i32p, _i32p, _i64, _vp, _int, _vp]),

@@ -13,23 +13,42 @@ namespace nt {
 
 constexpr int RO_THREADS = 256;
 
-// out[s,c] = max_j x[perm[j],c], arg[s,c] = first row attaining it; empty segment -> 0 / -1 (torch_scatter: 0 / dim_size)
-__global__ void __launch_bounds__(RO_THREADS) seg_max_kernel(const float* __restrict__ x, int d, const int32_t* __restrict__ rowptr,
-                                                             const int32_t* __restrict__ perm, int64_t total, float* __restrict__ out,
-                                                             int32_t* __restrict__ arg) {
+// out[s,c] = max_j (sign * act(x[perm[j],c])) * sign, arg[s,c] = first row attaining it; empty segment -> 0 / -1 (torch_scatter: 0 / dim_size).
+// sign = +1: scatter_max, sign = -1: scatter_min (= -scatter_max(-x), sign flips are exact). VEC: four channels per thread (d % 4 == 0).
+template <bool VEC>
+__global__ void __launch_bounds__(RO_THREADS) seg_extreme_kernel(const float* __restrict__ x, int d, int chunks, const int32_t* __restrict__ rowptr,
+                                                                 const int32_t* __restrict__ perm, int64_t total, int act, float act_param,
+                                                                 float sign, float* __restrict__ out, int32_t* __restrict__ arg) {
   int64_t t = (int64_t)blockIdx.x * RO_THREADS + threadIdx.x;
   if (t >= total) return;
-  const int s = (int)(t / d), c = (int)(t - (int64_t)s * d);
+  const int s = (int)(t / chunks), c = (int)(t - (int64_t)s * chunks) * (VEC ? 4 : 1);
   const int lo = __ldg(rowptr + s), hi = __ldg(rowptr + s + 1);
-  float best = 0.f;
-  int where = -1;
+  constexpr int W = VEC ? 4 : 1;
+  float best[W];
+  int where[W];
+#pragma unroll
+  for (int u = 0; u < W; ++u) { best[u] = 0.f; where[u] = -1; }
   for (int j = lo; j < hi; ++j) {
     const int r = perm ? __ldg(perm + j) : j;
-    const float v = __ldg(x + (int64_t)r * d + c);
-    if (where < 0 || v > best) { best = v; where = r; }  // strict '>' : the first maximum wins, like torch_scatter's CPU kernel
+    float v[W];
+    if constexpr (VEC) {
+      const float4 q = ldg4(x + (int64_t)r * d + c);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      v[0] = __ldg(x + (int64_t)r * d + c);
+    }
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+      const float a = act_fwd(v[u], act, act_param) * sign;
+      if (where[u] < 0 || a > best[u]) { best[u] = a; where[u] = r; }  // strict '>' : the first extreme wins, like torch_scatter's CPU kernel
+    }
   }
-  out[t] = best;
-  arg[t] = where;
+  const int64_t o = (int64_t)s * d + c;
+#pragma unroll
+  for (int u = 0; u < W; ++u) {
+    out[o + u] = where[u] < 0 ? 0.f : best[u] * sign;
+    arg[o + u] = where[u];
+  }
 }
 
 // gx[r,c] = (arg[seg[r],c] == r) ? g[seg[r],c] : 0
@@ -144,17 +163,37 @@ using namespace nt;
 
 #define NT_RO_F32(fn) if (dtype != NT_F32) { set_error(fn ": only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
 
+static int seg_extreme_impl(const char* fn, const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int act,
+                            float act_param, int is_min, void* out, int32_t* arg, nt_stream_t stream) {
+  NT_CHECK_ARG(d > 0 && d < (1 << 20) && num_segments >= 0 && num_segments * d < ((int64_t)1 << 40), "%s: bad sizes", fn);
+  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "%s: bad activation", fn);
+  if (num_segments == 0) return NT_OK;
+  NT_CHECK_ARG(rowptr && out && arg, "%s: null pointer", fn);
+  const float sign = is_min ? -1.f : 1.f;
+  if (d % 4 == 0 && aligned16(x) && aligned16(out) && aligned16(arg)) {
+    const int chunks = (int)(d / 4);
+    const int64_t total = num_segments * chunks;
+    seg_extreme_kernel<true><<<(unsigned)cdiv(total, RO_THREADS), RO_THREADS, 0, as_stream(stream)>>>(
+        static_cast<const float*>(x), (int)d, chunks, rowptr, perm, total, act, act_param, sign, static_cast<float*>(out), arg);
+  } else {
+    const int64_t total = num_segments * d;
+    seg_extreme_kernel<false><<<(unsigned)cdiv(total, RO_THREADS), RO_THREADS, 0, as_stream(stream)>>>(
+        static_cast<const float*>(x), (int)d, (int)d, rowptr, perm, total, act, act_param, sign, static_cast<float*>(out), arg);
+  }
+  NT_LAUNCH_CHECK(fn, 1);
+  return NT_OK;
+}
+
 extern "C" int nt_seg_max(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, void* out, int32_t* arg, int dtype,
                           nt_stream_t stream) {
   NT_RO_F32("nt_seg_max");
-  NT_CHECK_ARG(d > 0 && num_segments >= 0 && num_segments * d < ((int64_t)1 << 40), "nt_seg_max: bad sizes");
-  if (num_segments == 0) return NT_OK;
-  NT_CHECK_ARG(rowptr && out && arg, "nt_seg_max: null pointer");
-  const int64_t total = num_segments * d;
-  seg_max_kernel<<<(unsigned)cdiv(total, RO_THREADS), RO_THREADS, 0, as_stream(stream)>>>(static_cast<const float*>(x), (int)d, rowptr, perm, total,
-                                                                                         static_cast<float*>(out), arg);
-  NT_LAUNCH_CHECK("nt_seg_max", 1);
-  return NT_OK;
+  return seg_extreme_impl("nt_seg_max", x, d, rowptr, perm, num_segments, NT_ACT_IDENTITY, 0.f, 0, out, arg, stream);
+}
+
+extern "C" int nt_seg_extreme(const void* x, int64_t d, const int32_t* rowptr, const int32_t* perm, int64_t num_segments, int act, float act_param,
+                              int is_min, void* out, int32_t* arg, int dtype, nt_stream_t stream) {
+  NT_RO_F32("nt_seg_extreme");
+  return seg_extreme_impl("nt_seg_extreme", x, d, rowptr, perm, num_segments, act, act_param, is_min, out, arg, stream);
 }
 
 extern "C" int nt_seg_max_backward(const void* g, const int32_t* arg, const int32_t* seg_of_row, int64_t n, int64_t d, void* gx, int dtype,

@@ -248,8 +248,10 @@ template <bool VEC>
 __global__ void __launch_bounds__(ROW_THREADS) layer_bwd_epilogue(const float* __restrict__ g, const float* __restrict__ h, const float* __restrict__ g_n,
                                                                    const float* __restrict__ g_m, const int32_t* __restrict__ dst,
                                                                    const int32_t* __restrict__ rev_rowptr, const int32_t* __restrict__ rev_perm,
-                                                                   const int32_t* __restrict__ dst_rowptr, int d, int chunks, int64_t total, int act,
-                                                                   float act_param, int residual, int mean, float* __restrict__ g_h) {
+                                                                   const int32_t* __restrict__ dst_rowptr, const int32_t* __restrict__ arg, int d,
+                                                                   int chunks, int64_t total, int act, float act_param, int residual, int mean,
+                                                                   float* __restrict__ g_h) {
+  // arg != NULL: the forward reduction was a max / min; only the edge that supplied the extreme of (atom, channel) receives g_n
   int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
   if (t >= total) return;
   int e = (int)(t / chunks);
@@ -261,6 +263,10 @@ __global__ void __launch_bounds__(ROW_THREADS) layer_bwd_epilogue(const float* _
   if (VEC) {
     float4 ga = ldg4(g_n + (int64_t)v * d + c);
     if (mean) ga = make_float4(ga.x / inv_cnt_div, ga.y / inv_cnt_div, ga.z / inv_cnt_div, ga.w / inv_cnt_div);
+    if (arg) {
+      const int4 w = __ldg(reinterpret_cast<const int4*>(arg + (int64_t)v * d + c));
+      ga = make_float4(w.x == e ? ga.x : 0.f, w.y == e ? ga.y : 0.f, w.z == e ? ga.z : 0.f, w.w == e ? ga.w : 0.f);
+    }
     float4 sub = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = lo; j < hi; ++j) sub = add4(sub, ldg4(g_m + (int64_t)__ldg(rev_perm + j) * d + c));
     float4 hv = ldg4_stream(h + (int64_t)e * d + c);
@@ -271,6 +277,7 @@ __global__ void __launch_bounds__(ROW_THREADS) layer_bwd_epilogue(const float* _
   } else {
     float ga = __ldg(g_n + (int64_t)v * d + c);
     if (mean) ga = ga / inv_cnt_div;
+    if (arg && __ldg(arg + (int64_t)v * d + c) != e) ga = 0.f;
     float sub = 0.f;
     for (int j = lo; j < hi; ++j) sub += __ldg(g_m + (int64_t)__ldg(rev_perm + j) * d + c);
     float r = act_bwd(__ldg(h + (int64_t)e * d + c), act, act_param) * (ga - sub);
@@ -425,32 +432,47 @@ extern "C" int nt_gather_add(const void* base, const void* x, const int32_t* idx
   return NT_OK;
 }
 
-extern "C" int nt_layer_backward_epilogue(const void* g, const void* h, const void* g_n, const void* g_m, const int32_t* dst,
-                                          const int32_t* rev_rowptr, const int32_t* rev_perm, const int32_t* dst_rowptr, int64_t E, int64_t d,
-                                          int act, float act_param, int residual, int mean, void* g_h, int dtype, nt_stream_t stream) {
-  if (dtype != NT_F32) { set_error("nt_layer_backward_epilogue: only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
-  NT_CHECK_ARG(d > 0 && d < (1 << 20) && E >= 0 && E < INT32_MAX, "nt_layer_backward_epilogue: bad sizes");
-  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "nt_layer_backward_epilogue: bad activation");
+static int bwd_epilogue_impl(const char* fn, const void* g, const void* h, const void* g_n, const void* g_m, const int32_t* dst,
+                             const int32_t* rev_rowptr, const int32_t* rev_perm, const int32_t* dst_rowptr, const int32_t* arg, int64_t E, int64_t d,
+                             int act, float act_param, int residual, int mean, void* g_h, int dtype, nt_stream_t stream) {
+  if (dtype != NT_F32) { set_error("%s: only NT_F32 is implemented", fn); return NT_ERR_UNSUPPORTED; }
+  NT_CHECK_ARG(d > 0 && d < (1 << 20) && E >= 0 && E < INT32_MAX, "%s: bad sizes", fn);
+  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "%s: bad activation", fn);
   if (E == 0) return NT_OK;
-  NT_CHECK_ARG(h && g_n && g_m && dst && rev_rowptr && rev_perm && g_h, "nt_layer_backward_epilogue: null pointer");
-  NT_CHECK_ARG(!residual || g, "nt_layer_backward_epilogue: residual needs g");
-  NT_CHECK_ARG(!mean || dst_rowptr, "nt_layer_backward_epilogue: mean needs dst_rowptr");
+  NT_CHECK_ARG(h && g_n && g_m && dst && rev_rowptr && rev_perm && g_h, "%s: null pointer", fn);
+  NT_CHECK_ARG(!residual || g, "%s: residual needs g", fn);
+  NT_CHECK_ARG(!mean || dst_rowptr, "%s: mean needs dst_rowptr", fn);
   cudaStream_t st = as_stream(stream);
   const float *gf = static_cast<const float*>(g), *hf = static_cast<const float*>(h), *gn = static_cast<const float*>(g_n),
               *gm = static_cast<const float*>(g_m);
   float* out = static_cast<float*>(g_h);
-  if (vec_ok(d, g, h, g_n, g_m, g_h)) {
+  if (vec_ok(d, g, h, g_n, g_m, g_h) && aligned16(arg)) {
     int chunks = (int)(d / 4);
     int64_t total = E * chunks;
-    layer_bwd_epilogue<true><<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(gf, hf, gn, gm, dst, rev_rowptr, rev_perm, dst_rowptr, (int)d,
-                                                                                         chunks, total, act, act_param, residual, mean, out);
+    layer_bwd_epilogue<true><<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(gf, hf, gn, gm, dst, rev_rowptr, rev_perm, dst_rowptr, arg,
+                                                                                         (int)d, chunks, total, act, act_param, residual, mean, out);
   } else {
     int64_t total = E * d;
-    layer_bwd_epilogue<false><<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(gf, hf, gn, gm, dst, rev_rowptr, rev_perm, dst_rowptr, (int)d,
-                                                                                          (int)d, total, act, act_param, residual, mean, out);
+    layer_bwd_epilogue<false><<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(gf, hf, gn, gm, dst, rev_rowptr, rev_perm, dst_rowptr, arg,
+                                                                                          (int)d, (int)d, total, act, act_param, residual, mean, out);
   }
-  NT_LAUNCH_CHECK("nt_layer_backward_epilogue", 1);
+  NT_LAUNCH_CHECK(fn, 1);
   return NT_OK;
+}
+
+extern "C" int nt_layer_backward_epilogue(const void* g, const void* h, const void* g_n, const void* g_m, const int32_t* dst,
+                                          const int32_t* rev_rowptr, const int32_t* rev_perm, const int32_t* dst_rowptr, int64_t E, int64_t d,
+                                          int act, float act_param, int residual, int mean, void* g_h, int dtype, nt_stream_t stream) {
+  return bwd_epilogue_impl("nt_layer_backward_epilogue", g, h, g_n, g_m, dst, rev_rowptr, rev_perm, dst_rowptr, nullptr, E, d, act, act_param, residual,
+                           mean, g_h, dtype, stream);
+}
+
+extern "C" int nt_layer_backward_epilogue_arg(const void* g, const void* h, const void* g_n, const void* g_m, const int32_t* dst, const int32_t* arg,
+                                              const int32_t* rev_rowptr, const int32_t* rev_perm, int64_t E, int64_t d, int act, float act_param,
+                                              int residual, void* g_h, int dtype, nt_stream_t stream) {
+  NT_CHECK_ARG(arg || E == 0, "nt_layer_backward_epilogue_arg: null pointer");
+  return bwd_epilogue_impl("nt_layer_backward_epilogue_arg", g, h, g_n, g_m, dst, rev_rowptr, rev_perm, nullptr, arg, E, d, act, act_param, residual, 0,
+                           g_h, dtype, stream);
 }
 
 extern "C" int nt_layer_backward_epilogue_fused(const void* g, const void* h, const void* g_m, const int32_t* dst, const int32_t* src_rowptr,

@@ -61,8 +61,6 @@ class ChempropBlock(nn.Module):
         return len(self.layers)
 
     def forward(self, G: Graph | BatchedGraph):
-        if self.reduce not in ("sum", "mean"):
-            raise NotImplementedError(f"notorch_b200: reduce='{self.reduce}' is not implemented (sum and mean are); no fallback")
         csr = ops.graph_csr(G)
         h = ops.edge_init(G.node_feats, G.edge_feats, csr)  # K0
         for entry in self.layers:

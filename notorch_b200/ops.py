@@ -370,6 +370,16 @@ def _seg_reduce_raw(x: Tensor, csr: SegmentCSR, act: int = 0, act_param: float =
     return out
 
 
+def _seg_extreme_raw(x: Tensor, csr: SegmentCSR, act: int, act_param: float, is_min: bool, tag: str = "K1x") -> tuple[Tensor, Tensor]:
+    """max / min of act(x) over every segment + the int32 argument rows (first extreme wins; empty segment: 0 / -1)."""
+    d = x.shape[1]
+    out = torch.empty((csr.num_segments, d), dtype=x.dtype, device=x.device)
+    arg = torch.empty((csr.num_segments, d), dtype=torch.int32, device=x.device)
+    _run(f"{tag}:nt_seg_extreme", _lib.lib().nt_seg_extreme, _p(x), d, _p(csr.rowptr), _p(csr.perm), csr.num_segments, act, act_param, int(is_min),
+         _p(out), _p(arg), NT_F32, _stream())
+    return out, arg
+
+
 def _gather_add_raw(base: Tensor | None, x: Tensor, idx32: Tensor, mean_rowptr: Tensor | None, scale: float = 1.0,
                     tag: str = "K0") -> Tensor:
     n, d = idx32.numel(), x.shape[1]
@@ -414,6 +424,33 @@ class _SegReduce(torch.autograd.Function):
         return gx, None, None, None, None
 
 
+class _SegExtreme(torch.autograd.Function):
+    """``scatter(x, index, reduce="max" | "min")`` (torch_scatter arg-reductions; chemprop.py:86 with reduce in {max, min}):
+    the gradient flows to the first row attaining the extreme, empty segments give 0."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, csr: SegmentCSR, is_min: bool, tag: str):
+        x = _require_float(x, "x")
+        if x.shape[0] != csr.keys32.numel():
+            raise RuntimeError(f"notorch_b200: {x.shape[0]} rows but the index has {csr.keys32.numel()} entries")
+        with torch.cuda.device(x.device):
+            out, arg = _seg_extreme_raw(x, csr, _lib.ACT_IDENTITY, 0.0, is_min, tag=tag)
+        ctx.save_for_backward(arg)
+        ctx.csr, ctx.n, ctx.tag = csr, x.shape[0], tag
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (arg,) = ctx.saved_tensors
+        g = g.contiguous()
+        d = g.shape[1]
+        with torch.cuda.device(g.device):
+            gx = torch.empty((ctx.n, d), dtype=g.dtype, device=g.device)
+            _run(f"{ctx.tag}bwd:nt_seg_max_backward", _lib.lib().nt_seg_max_backward, _p(g), _p(arg), _p(ctx.csr.keys32), ctx.n, d, _p(gx), NT_F32,
+                 _stream())
+        return gx, None, None, None
+
+
 class _GatherAdd(torch.autograd.Function):
     """K0: out[i] = base[i] + x[idx[i]]  (chemprop.py:83); backward of the gather is K5."""
 
@@ -442,24 +479,30 @@ _dropout_calls = 0
 
 
 def _layer_forward_raw(h: Tensor, W: Tensor, b: Tensor | None, csr: GraphCSR, act: int, act_param: float, mean: bool, residual: bool,
-                       p: float, seed: int, offset: int, mode: int, save_m: bool) -> tuple[Tensor, Tensor | None, Tensor]:
-    """K1 + K2 of one depth on raw tensors (no autograd): returns (h', m or None, n)."""
+                       p: float, seed: int, offset: int, mode: int, save_m: bool,
+                       extreme: int = 0) -> tuple[Tensor, Tensor | None, Tensor, Tensor | None]:
+    """K1 + K2 of one depth on raw tensors (no autograd): returns (h', m or None, n, arg or None).
+    ``extreme``: 0 = sum / mean (``mean``), 1 = max, 2 = min — K1 is then the arg-reduction and ``arg`` its [V, d] argument rows."""
     E, d = h.shape
     L = _lib.lib()
     with torch.cuda.device(h.device):
-        n = _seg_reduce_raw(h, csr.by_dst, act, act_param, mean, tag="K1")
+        arg = None
+        if extreme:
+            n, arg = _seg_extreme_raw(h, csr.by_dst, act, act_param, extreme == 2)
+        else:
+            n = _seg_reduce_raw(h, csr.by_dst, act, act_param, mean, tag="K1")
         img = _weight_image(W, False) if mode != GEMM_FP32 else None
         out = torch.empty_like(h)
         m = torch.empty_like(h) if save_m else None
         _run("K2:nt_layer_forward", L.nt_layer_forward, _p(h), _p(n), _p(csr.src), _p(csr.rev), _p(W), _p(img), _p(b), E, csr.V, d, act,
              act_param, int(residual), p, seed, offset, _p(out), _p(m), NT_F32, mode, _stream())
-    return out, m, n
+    return out, m, n, arg
 
 
 def _layer_backward_raw(g: Tensor, h: Tensor, m: Tensor | None, n: Tensor | None, W: Tensor, has_bias: bool, csr: GraphCSR, act: int,
                         act_param: float, mean: bool, residual: bool, p: float, seed: int, offset: int, mode: int, need_w: bool,
-                        need_h: bool) -> tuple[Tensor | None, Tensor | None, Tensor | None]:
-    """K4b, K4a, K5 + K6 of one depth on raw tensors: returns (g_h, g_W, g_b)."""
+                        need_h: bool, arg: Tensor | None = None) -> tuple[Tensor | None, Tensor | None, Tensor | None]:
+    """K4b, K4a, K5 + K6 of one depth on raw tensors: returns (g_h, g_W, g_b). ``arg``: argument rows of a max / min forward."""
     E, d = h.shape
     g = g.contiguous()
     L = _lib.lib()
@@ -478,8 +521,12 @@ def _layer_backward_raw(g: Tensor, h: Tensor, m: Tensor | None, n: Tensor | None
             _run("K4a:nt_layer_backward_dgrad", L.nt_layer_backward_dgrad, _p(g), _p(W), _p(img_t), E, d, p, seed, offset, _p(g_m), NT_F32,
                  mode, _stream())
             gh = torch.empty_like(h)
-            ell = _ell_of(csr.by_src) if (_fuse_k5_k6 and d % 4 == 0) else None
-            if ell is not None:  # K5 + K6 in one kernel: g_n is never materialised
+            ell = _ell_of(csr.by_src) if (_fuse_k5_k6 and d % 4 == 0 and arg is None) else None
+            if arg is not None:  # max / min: the atom gradient goes to the argument edge of every (atom, channel) only
+                g_n = _seg_reduce_raw(g_m, csr.by_src, tag="K5")
+                _run("K6:nt_layer_backward_epilogue_arg", L.nt_layer_backward_epilogue_arg, _p(g), _p(h), _p(g_n), _p(g_m), _p(csr.dst), _p(arg),
+                     _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), E, d, act, act_param, int(residual), _p(gh), NT_F32, _stream())
+            elif ell is not None:  # K5 + K6 in one kernel: g_n is never materialised
                 _run("K6:nt_layer_backward_epilogue", L.nt_layer_backward_epilogue_fused, _p(g), _p(h), _p(g_m), _p(csr.dst),
                      _p(csr.by_src.rowptr), _p(csr.by_src.perm), _p(ell), _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr),
                      E, d, act, act_param, int(residual), int(mean), _p(gh), NT_F32, _stream())
@@ -499,7 +546,7 @@ class _Layer(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h: Tensor, W: Tensor, b: Tensor | None, csr: GraphCSR, act: int, act_param: float, mean: bool,
-                residual: bool, p: float, seed: int, offset: int, mode: int):
+                residual: bool, p: float, seed: int, offset: int, mode: int, extreme: int = 0):
         h = _require_float(h, "edge_feats")
         W = _require_float(W, "weight")
         E, d = h.shape
@@ -511,27 +558,34 @@ class _Layer(torch.autograd.Function):
             b = _require(b, "bias", torch.float32, 1)
         # tensor-core path: K2 also writes the message tensor m, which K4b then streams as dense tiles
         save_m = mode != GEMM_FP32 and d % 4 == 0 and (ctx.needs_input_grad[1] or (b is not None and ctx.needs_input_grad[2]))
-        out, m, n = _layer_forward_raw(h, W, b, csr, act, act_param, mean, residual, p, seed, offset, mode, save_m)
-        ctx.save_for_backward(h, m if save_m else n, W)
+        out, m, n, arg = _layer_forward_raw(h, W, b, csr, act, act_param, mean, residual, p, seed, offset, mode, save_m, extreme)
+        ctx.save_for_backward(h, m if save_m else n, W, arg)
         ctx.csr, ctx.cfg, ctx.has_bias, ctx.has_m = csr, (act, act_param, mean, residual, p, seed, offset, mode), b is not None, save_m
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
-        h, n_or_m, W = ctx.saved_tensors
+        h, n_or_m, W, arg = ctx.saved_tensors
         m, n = (n_or_m, None) if ctx.has_m else (None, n_or_m)
         need_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
-        gh, gW, gb = _layer_backward_raw(g, h, m, n, W, ctx.has_bias, ctx.csr, *ctx.cfg, need_w, ctx.needs_input_grad[0])
-        return gh, gW, gb, None, None, None, None, None, None, None, None, None
+        gh, gW, gb = _layer_backward_raw(g, h, m, n, W, ctx.has_bias, ctx.csr, *ctx.cfg, need_w, ctx.needs_input_grad[0], arg)
+        return gh, gW, gb, None, None, None, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
 # public functional API
 # ------------------------------------------------------------------------------------------------
 
+_REDUCTIONS = ("sum", "mean", "max", "min")  # notorch/types.py: Reduction
+
+
 def seg_reduce(x: Tensor, csr: SegmentCSR, reduce: str = "sum", scale: float = 1.0, tag: str = "K1") -> Tensor:
-    if reduce not in ("sum", "mean"):
-        raise NotImplementedError(f"notorch_b200: reduce='{reduce}' is not implemented (sum and mean are); no fallback")
+    if reduce not in _REDUCTIONS:
+        raise ValueError(f"notorch_b200: unknown reduce '{reduce}' (one of {_REDUCTIONS})")
+    if reduce in ("max", "min"):
+        if scale != 1.0:
+            raise ValueError("notorch_b200: a scale factor only applies to sum / mean reductions")
+        return _SegExtreme.apply(x, csr, reduce == "min", tag + "x")
     return _SegReduce.apply(x, csr, reduce == "mean", float(scale), tag)
 
 
@@ -560,8 +614,8 @@ def layer(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, *, act:
           reduce: str = "sum", residual: bool = True, dropout: float = 0.0, training: bool = False) -> Tensor:
     """One fused message-passing depth (K1+K2; hand-written backward K4-K6)."""
     global _dropout_calls
-    if reduce not in ("sum", "mean"):
-        raise NotImplementedError(f"notorch_b200: reduce='{reduce}' is not implemented (sum and mean are); no fallback")
+    if reduce not in _REDUCTIONS:
+        raise ValueError(f"notorch_b200: unknown reduce '{reduce}' (one of {_REDUCTIONS})")
     p = float(dropout) if training else 0.0
     if not 0.0 <= p < 1.0:
         if p == 1.0:
@@ -572,7 +626,8 @@ def layer(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, *, act:
         seed = int(torch.empty((), dtype=torch.int64).random_().item())  # CPU generator: follows torch.manual_seed, no device sync
         _dropout_calls += 1
         offset = _dropout_calls
-    return _Layer.apply(h, weight, bias, csr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)
+    extreme = {"max": 1, "min": 2}.get(reduce, 0)
+    return _Layer.apply(h, weight, bias, csr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode, extreme)
 
 
 # ------------------------------------------------------------------------------------------------

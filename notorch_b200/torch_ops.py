@@ -85,7 +85,7 @@ def chemprop_layer(h: Tensor, W: Tensor, b: Optional[Tensor], src: Tensor, dst: 
     csr = _graph(V, src, dst, rev, dst_rowptr, dst_perm, src_rowptr, src_perm, rev_rowptr, rev_perm)
     h, W = ops._require_float(h, "edge_feats"), ops._require_float(W, "weight")
     save_m = gemm_mode != GEMM_FP32 and h.shape[1] % 4 == 0
-    out, m, n = ops._layer_forward_raw(h, W, b, csr, act, act_param, mean, residual, p, seed, offset, gemm_mode, save_m)
+    out, m, n, _ = ops._layer_forward_raw(h, W, b, csr, act, act_param, mean, residual, p, seed, offset, gemm_mode, save_m)
     return out, (m if save_m else n)
 
 

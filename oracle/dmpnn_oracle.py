@@ -109,8 +109,26 @@ def apply_act(x: Tensor, act: str = "relu", param: float | None = None) -> Tenso
     return fn(x, **kw)
 
 
+def seg_extreme(x: Tensor, index: Tensor, size: int, reduce: str = "max") -> tuple[Tensor, Tensor]:
+    """``torch_scatter.scatter_max`` / ``scatter_min`` along dim 0 (published semantics of torch-scatter 2.1: the FIRST row attaining
+    the extreme is the argument, an empty segment yields value 0 and argument ``len(x)``; ``scatter(..., reduce="max")`` returns the
+    value only and autograd routes the gradient to the argument row). Returns (value ``[size, d]``, arg ``[size, d]`` int64)."""
+    n, d = x.shape
+    sign = 1.0 if reduce == "max" else -1.0
+    xs = x * sign  # exact
+    idx = index.view(-1, 1).expand(n, d)
+    best = torch.full((size, d), float("-inf"), dtype=x.dtype).scatter_reduce_(0, idx, xs, "amax", include_self=True)
+    rows = torch.arange(n).view(-1, 1).expand(n, d)
+    cand = torch.where(xs == best[index], rows, torch.full_like(rows, n))
+    arg = torch.full((size, d), n, dtype=torch.long).scatter_reduce_(0, idx, cand, "amin", include_self=True)
+    empty = arg == n
+    return torch.where(empty, torch.zeros_like(best), best * sign), arg
+
+
 def seg_reduce(x: Tensor, index: Tensor, size: int, reduce: str = "sum") -> Tensor:
-    """``torch_scatter.scatter(x, index, dim=0, dim_size=size, reduce=...)`` for sum / mean."""
+    """``torch_scatter.scatter(x, index, dim=0, dim_size=size, reduce=...)`` for sum / mean / max / min."""
+    if reduce in ("max", "min"):
+        return seg_extreme(x, index, size, reduce)[0]
     idx = index.view(-1, 1).expand_as(x)
     out = torch.zeros((size, x.shape[1]), dtype=x.dtype).scatter_add_(0, idx, x)
     if reduce == "sum":
@@ -269,11 +287,20 @@ def block_backward(
                              keep_masks=keep_masks, p=p)
     indeg = torch.zeros(V, dtype=dt).index_add_(0, dst, torch.ones(E, dtype=dt)).clamp(min=1)
     g = torch.zeros((E, x_e.shape[1]), dtype=dt)
+    eids = torch.arange(E).view(-1, 1)
+    extreme = reduce in ("max", "min")
+
+    def through_reduce(g_atoms: Tensor, reduced: Tensor) -> Tensor:
+        """Gradient of ``scatter(reduced, dst, V, reduce)`` w.r.t. its [E, d] input, given the [V, d] cotangent."""
+        if extreme:  # only the argument row of every (atom, channel) receives the gradient
+            arg = seg_extreme(reduced, dst, V, reduce)[1]
+            return torch.where(arg[dst] == eids, g_atoms[dst], torch.zeros((), dtype=dt))
+        return (g_atoms / indeg.view(-1, 1) if reduce == "mean" else g_atoms)[dst]
+
     if g_edge is not None:
         g = g + g_edge
     if g_node is not None:
-        gn = g_node / indeg.view(-1, 1) if reduce == "mean" else g_node
-        g = g + gn[dst]
+        g = g + through_reduce(g_node, hs[-1])
     gWs, gbs = [], []
     for l in reversed(range(len(weights))):
         W, h = weights[l], hs[l]
@@ -287,9 +314,7 @@ def block_backward(
         gbs.append(g_u.sum(0) if biases[l] is not None else None)
         g_m = g_u @ W
         g_n = torch.zeros((V, W.shape[1]), dtype=dt).index_add_(0, src, g_m)
-        if reduce == "mean":
-            g_n = g_n / indeg.view(-1, 1)
-        g_a = g_n[dst] - torch.zeros_like(g_m).index_add_(0, rev_index, g_m)
+        g_a = through_reduce(g_n, a) - torch.zeros_like(g_m).index_add_(0, rev_index, g_m)
         h_for_mask = act_grad_at[l].to(dt) if act_grad_at is not None else h
         g = (g if residual else 0) + _act_grad(h_for_mask, act, act_param) * g_a
     g_xv = torch.zeros_like(x_v).index_add_(0, src, g)

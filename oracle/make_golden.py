@@ -54,6 +54,10 @@ CASES = {
     "act_gelu": dict(batch=3, d=16, depth=2, act="gelu"),
     "act_leaky": dict(batch=3, d=16, depth=2, act="leaky_relu"),
     "odd_d37": dict(batch=4, d=37, depth=2),
+    # torch_scatter's arg-reductions inside the block (chemprop.py:39,86 with reduce in {"max","min"}); bondless molecules give
+    # empty segments (value 0, no gradient)
+    "max_reduce": dict(batch=5, d=16, depth=2, reduce="max", bondless_every=3),
+    "min_reduce": dict(batch=5, d=20, depth=2, reduce="min", act="tanh", bondless_every=4),
 }
 
 
@@ -165,13 +169,18 @@ def main() -> None:
         raise SystemExit("reference tree not found; golden fixtures can only be made in the authoring container")
     os.makedirs(OUT, exist_ok=True)
     total = 0
+    only = set(sys.argv[1:])  # optional: regenerate just the named cases (seeds depend on the position in CASES, not on the selection)
     for i, (name, cfg) in enumerate(CASES.items()):
+        if only and name not in only:
+            continue
         data = run_case(name, cfg, seed=4242 + i)
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **data)
         total += os.path.getsize(path)
         print(f"{name:18s} V={int(data['num_atoms'].sum()):4d} E={int(data['num_edges'].sum()):4d} "
               f"{os.path.getsize(path) / 1024:.0f} KiB")
+    if only:
+        return
     extra = run_readout_max(seed=9001)
     path = os.path.join(OUT, "..", "golden_readouts", "readout_max.npz")
     os.makedirs(os.path.dirname(path), exist_ok=True)

@@ -100,6 +100,73 @@ def test_segmented_reductions_bit_exact(d, reduce):
     assert torch.equal(h0, O.edge_init(p["x_v"], p["x_e"], p["edge_index"][0]))  # K0 (chemprop.py:83)
 
 
+@pytest.mark.parametrize("d", [300, 37, 8])
+@pytest.mark.parametrize("reduce", ["max", "min"])
+def test_arg_reductions_bit_exact(d, reduce):
+    """scatter(..., reduce="max"|"min") (chemprop.py:39,86): values, tie-breaking (first row wins), empty segments -> 0, and the gradient
+    routed to the argument row, all bit-exact against the oracle's restatement of torch_scatter."""
+    from notorch_b200 import _lib, ops
+
+    p = oracle_inputs(48, d, 0, config=1, seed=13)
+    E, V, dst = p["E"], p["V"], p["edge_index"][1]
+    x = p["x_e"].clone()
+    x[:, : min(4, d)] = torch.randint(-1, 2, (E, min(4, d))).float()  # plenty of exact ties
+    csr = ops.build_graph_csr(p["edge_index"].cuda(), p["rev_index"].cuda(), V)
+    xc = x.cuda().requires_grad_(True)
+    got = ops.edge_to_atom(xc, csr, reduce)
+    want, arg = O.seg_extreme(x, dst, V, reduce)
+    assert torch.equal(got.detach().cpu(), want)
+    g = torch.randn(V, d)
+    got.backward(g.cuda())
+    want_g = torch.where(arg[dst] == torch.arange(E).view(-1, 1), g[dst], torch.zeros(()))
+    assert torch.equal(xc.grad.cpu(), want_g)
+    # with an activation prologue (K1 of a max / min layer)
+    n, a = ops._seg_extreme_raw(x.cuda(), csr.by_dst, _lib.ACT_RELU, 0.0, reduce == "min")
+    w, wa = O.seg_extreme(torch.relu(x), dst, V, reduce)
+    assert torch.equal(n.cpu(), w)
+    assert torch.equal(torch.where(a < 0, E, a).long().cpu(), wa)  # empty segment: -1 here, len(x) in torch_scatter
+
+
+@pytest.mark.parametrize("reduce,act", [("max", "relu"), ("min", "silu"), ("max", "tanh")])
+@pytest.mark.parametrize("mode", ["tf32x3", "fp32"])
+@pytest.mark.parametrize("d", [64, 37])
+def test_block_arg_reductions_vs_oracle(reduce, act, mode, d):
+    """ChempropBlock with reduce in {max, min}: forward and all gradients vs the oracle (pinned to the reference's own max / min
+    goldens in tests/golden/{max,min}_reduce.npz) on a larger seeded batch."""
+    from notorch_b200 import BatchedGraph, ops
+    from notorch_b200.nn import ChempropBlock
+
+    depth = 3
+    p = oracle_inputs(40, d, depth, config=1, seed=21)
+    blk = ChempropBlock(hidden_dim=d, act=ACT_MODULES[act], depth=depth, reduce=reduce).cuda()
+    with torch.no_grad():
+        for l, layer in enumerate(blk.layers):
+            layer.module.update[0].weight.copy_(p["weights"][l])
+            layer.module.update[0].bias.copy_(p["biases"][l])
+    xv, xe = p["x_v"].cuda().requires_grad_(True), p["x_e"].cuda().requires_grad_(True)
+    G = BatchedGraph(xv, xe, p["edge_index"].cuda(), p["rev_index"].cuda(), batch_node_index=p["batch_node_index"].cuda(),
+                     batch_edge_index=p["batch_edge_index"].cuda(), size=p["B"])
+    gN, gE = torch.randn(p["V"], d), torch.randn(p["E"], d)
+    old = ops.get_gemm_mode()
+    ops.set_gemm_mode(mode)
+    try:
+        G1 = blk(G)
+        ((G1.node_feats * gN.cuda()).sum() + (G1.edge_feats * gE.cuda()).sum()).backward()
+    finally:
+        ops.set_gemm_mode(old)
+    f64 = lambda t: t.double()
+    Ws, bs = [f64(w) for w in p["weights"]], [f64(b) for b in p["biases"]]
+    node, edge, _ = O.block_forward(f64(p["x_v"]), f64(p["x_e"]), p["edge_index"], p["rev_index"], Ws, bs, act=act, reduce=reduce)
+    ref = O.block_backward(f64(p["x_v"]), f64(p["x_e"]), p["edge_index"], p["rev_index"], Ws, bs, f64(gN), f64(gE), act=act, reduce=reduce)
+    assert_close(G1.node_feats.detach().cpu().double(), node, "node_out")
+    assert_close(G1.edge_feats.detach().cpu().double(), edge, "edge_out")
+    assert_close(xv.grad.cpu().double(), ref["x_v"], "grad x_v")
+    assert_close(xe.grad.cpu().double(), ref["x_e"], "grad x_e")
+    for l, layer in enumerate(blk.layers):
+        assert_close(layer.module.update[0].weight.grad.cpu().double(), ref["weights"][l], f"grad W{l}")
+        assert_close(layer.module.update[0].bias.grad.cpu().double(), ref["biases"][l], f"grad b{l}")
+
+
 def test_norm_readout_extension():
     from notorch_b200 import ops
 
@@ -346,8 +413,8 @@ def test_unsupported_inputs_raise():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Sum()(G_cpu)
     G = G_cpu.to("cuda")
-    with pytest.raises(NotImplementedError):
-        ChempropBlock(hidden_dim=16, depth=1, reduce="max").cuda()(G)
+    with pytest.raises(ValueError, match="unknown reduce"):
+        ChempropBlock(hidden_dim=16, depth=1, reduce="prod").cuda()(G)
     with pytest.raises(NotImplementedError):
         ChempropBlock(hidden_dim=16, depth=1, act=torch.nn.Softplus).cuda()(G)
     with pytest.raises(RuntimeError, match="float32 only"):
