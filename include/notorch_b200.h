@@ -238,6 +238,22 @@ int nt_layer_backward_epilogue_fused(const void* g, const void* h, const void* g
                                      void* g_h, int dtype, nt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Prediction head (row N3): the nn.Linear layers of notorch/nn/mlp.py:58-62 on the [B, d] molecule vectors, strict fp32 (FFMA),
+ * rectangular: W is [out_features, in_features] row-major like nn.Linear.weight.
+ *   nt_linear_forward          out = x W^T + bias                      (bias may be NULL)
+ *   nt_linear_backward_input   gx  = g W
+ *   nt_linear_backward_weight  gW  = g^T x, gb = column sums of g      (gb may be NULL; split over rows, fixed-order reduction)
+ * With rows == 0, nt_linear_backward_weight writes zeros.
+ * ---------------------------------------------------------------------------------------------- */
+int nt_linear_forward(const void* x, const void* W, const void* bias, int64_t rows, int64_t out_features,
+                      int64_t in_features, void* out, int dtype, nt_stream_t stream);
+int nt_linear_backward_input(const void* g, const void* W, int64_t rows, int64_t out_features, int64_t in_features,
+                             void* gx, int dtype, nt_stream_t stream);
+size_t nt_linear_backward_weight_workspace_bytes(int64_t rows, int64_t out_features, int64_t in_features);
+int nt_linear_backward_weight(const void* g, const void* x, int64_t rows, int64_t out_features, int64_t in_features,
+                              void* gW, void* gb, void* workspace, size_t workspace_bytes, int dtype, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * GraphEmbedding (row N1, the step before the block) — replaces the two nn.EmbeddingBag(mode="sum") of
  * notorch/nn/gnn/embed.py:20-24 on 2-D index input: out[i,:] = sum_{j<bag} table[idx[i,j],:]  (idx int64 [n,bag]).
  * *status bit 0 is set if an index is outside [0, num_types). Backward: g_table[t,:] = sum over all (i,j) with

@@ -47,6 +47,10 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "nt_layer_backward_epilogue": (_int, [_vp, _vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _int, _vp, _int, _vp]),
     "nt_layer_backward_epilogue_arg": (_int, [_vp, _vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _vp, _int, _vp]),
     "nt_layer_backward_epilogue_fused": (_int, [_vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _int, _vp, _int, _vp]),
+    "nt_linear_forward": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
+    "nt_linear_backward_input": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
+    "nt_linear_backward_weight_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "nt_linear_backward_weight": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _int, _vp]),
     "nt_embedding_bag_sum": (_int, [_vp, _i64, _i64p, _i64, _i64, _i64, _vp, _i32p, _int, _vp]),
     "nt_embedding_bag_backward_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "nt_embedding_bag_backward": (_int, [_vp, _i64p, _i64, _i64, _i64, _i64, _vp, _vp, _sz, _int, _vp]),

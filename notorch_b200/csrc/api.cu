@@ -46,6 +46,10 @@ int simt_layer_forward(const float*, const float*, const int32_t*, const int32_t
 int simt_layer_dgrad(const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, cudaStream_t);
 int simt_layer_wgrad(const float*, const float*, const float*, const int32_t*, const int32_t*, int64_t, int64_t, int, float, float, uint64_t, uint64_t,
                      float*, float*, float*, cudaStream_t);
+size_t simt_linear_wgrad_workspace_bytes(int64_t rows, int64_t n_out, int64_t k_in);
+int simt_linear_forward(const float*, const float*, const float*, int64_t, int64_t, int64_t, float*, cudaStream_t);
+int simt_linear_dgrad(const float*, const float*, int64_t, int64_t, int64_t, float*, cudaStream_t);
+int simt_linear_wgrad(const float*, const float*, int64_t, int64_t, int64_t, float*, float*, float*, cudaStream_t);
 // gemm_tc.cu
 void tc_set_trace_buffer(void* ptr);
 size_t tc_weight_image_bytes(int64_t d);
@@ -176,6 +180,48 @@ extern "C" int nt_dense_forward(const void* x, const void* weight_image, const v
   }
   return pair_dense_forward(static_cast<const float*>(x), weight_image, static_cast<const float*>(bias), static_cast<const float*>(resid), R, d,
                             dropout_p, seed, offset, static_cast<float*>(out), products_of(gemm_mode), as_stream(stream));
+}
+
+// ---- prediction head: rectangular fp32 Linear on [rows, in_features] molecule vectors (notorch/nn/mlp.py:58-62) ----
+#define NT_LINEAR_CHECKS(fn)                                                                                              \
+  if (dtype != NT_F32) { set_error(fn ": only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }                        \
+  NT_CHECK_ARG(rows >= 0 && rows < INT32_MAX && out_features > 0 && in_features > 0 && out_features < (1 << 20) && in_features < (1 << 20), \
+               fn ": bad sizes")
+
+extern "C" int nt_linear_forward(const void* x, const void* W, const void* bias, int64_t rows, int64_t out_features, int64_t in_features, void* out,
+                                 int dtype, nt_stream_t stream) {
+  NT_LINEAR_CHECKS("nt_linear_forward");
+  if (rows == 0) return NT_OK;
+  NT_CHECK_ARG(x && W && out, "nt_linear_forward: null pointer");
+  return simt_linear_forward(static_cast<const float*>(x), static_cast<const float*>(W), static_cast<const float*>(bias), rows, out_features,
+                             in_features, static_cast<float*>(out), as_stream(stream));
+}
+
+extern "C" int nt_linear_backward_input(const void* g, const void* W, int64_t rows, int64_t out_features, int64_t in_features, void* gx, int dtype,
+                                        nt_stream_t stream) {
+  NT_LINEAR_CHECKS("nt_linear_backward_input");
+  if (rows == 0) return NT_OK;
+  NT_CHECK_ARG(g && W && gx, "nt_linear_backward_input: null pointer");
+  return simt_linear_dgrad(static_cast<const float*>(g), static_cast<const float*>(W), rows, out_features, in_features, static_cast<float*>(gx),
+                           as_stream(stream));
+}
+
+extern "C" size_t nt_linear_backward_weight_workspace_bytes(int64_t rows, int64_t out_features, int64_t in_features) {
+  if (rows < 0 || out_features <= 0 || in_features <= 0) return 0;
+  return simt_linear_wgrad_workspace_bytes(rows, out_features, in_features);
+}
+
+extern "C" int nt_linear_backward_weight(const void* g, const void* x, int64_t rows, int64_t out_features, int64_t in_features, void* gW, void* gb,
+                                         void* workspace, size_t workspace_bytes, int dtype, nt_stream_t stream) {
+  NT_LINEAR_CHECKS("nt_linear_backward_weight");
+  NT_CHECK_ARG(gW, "nt_linear_backward_weight: null pointer");
+  NT_CHECK_ARG(rows == 0 || (g && x), "nt_linear_backward_weight: null pointer");
+  if (workspace_bytes < simt_linear_wgrad_workspace_bytes(rows, out_features, in_features) || !workspace) {
+    set_error("nt_linear_backward_weight: workspace too small (nt_linear_backward_weight_workspace_bytes)");
+    return NT_ERR_WORKSPACE;
+  }
+  return simt_linear_wgrad(static_cast<const float*>(g), static_cast<const float*>(x), rows, out_features, in_features, static_cast<float*>(gW),
+                           static_cast<float*>(gb), static_cast<float*>(workspace), as_stream(stream));
 }
 
 extern "C" int nt_layer_backward_dgrad(const void* g, const void* W, const void* weight_image, int64_t E, int64_t d, float dropout_p, uint64_t seed,

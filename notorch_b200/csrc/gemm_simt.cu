@@ -215,4 +215,104 @@ int simt_layer_wgrad(const float* g, const float* h, const float* n, const int32
   return NT_OK;
 }
 
+// ---- rectangular Linear of the prediction head (notorch/nn/mlp.py:58-62: nn.Linear(d1, d2) on [B, d1] molecule vectors) ----
+struct LinearForwardProblem {  // out[m,n] = sum_k x[m,k] W[n,k] + bias[n]
+  static constexpr bool SPLIT_K = false, A_K_CONTIG = true, B_K_CONTIG = true;
+  int64_t M, K, k_chunk;
+  int N;
+  const float* __restrict__ x;
+  const float* __restrict__ W;
+  const float* __restrict__ bias;
+  float* __restrict__ out;
+  __device__ __forceinline__ float a(int64_t m, int64_t k) const { return __ldg(x + m * K + k); }
+  __device__ __forceinline__ float b(int n, int64_t k) const { return __ldg(W + (int64_t)n * K + k); }
+  __device__ __forceinline__ void store(int64_t m, int n, float acc, int) const { out[m * N + n] = acc + (bias ? __ldg(bias + n) : 0.f); }
+};
+
+struct LinearDgradProblem {  // gx[m,k] = sum_n g[m,n] W[n,k]        (GEMM "N" = K_in, reduction over N_out)
+  static constexpr bool SPLIT_K = false, A_K_CONTIG = true, B_K_CONTIG = false;
+  int64_t M, K, k_chunk;  // K = N_out
+  int N;                  // K_in
+  const float* __restrict__ g;
+  const float* __restrict__ W;
+  float* __restrict__ gx;
+  __device__ __forceinline__ float a(int64_t m, int64_t n_out) const { return __ldg(g + m * K + n_out); }
+  __device__ __forceinline__ float b(int k_in, int64_t n_out) const { return __ldg(W + n_out * N + k_in); }
+  __device__ __forceinline__ void store(int64_t m, int k_in, float acc, int) const { gx[m * N + k_in] = acc; }
+};
+
+struct LinearWgradProblem {  // partial[z][n][k] = sum_{m in chunk z} g[m,n] x[m,k]; column k == K_in carries the bias gradient
+  static constexpr bool SPLIT_K = true, A_K_CONTIG = false, B_K_CONTIG = false;
+  int64_t M, K, k_chunk;  // M = N_out, K = rows
+  int N;                  // K_in + 1
+  int n_out, k_in;
+  const float* __restrict__ g;
+  const float* __restrict__ x;
+  float* __restrict__ partial;
+  __device__ __forceinline__ float a(int64_t n, int64_t m) const { return __ldg(g + m * n_out + n); }
+  __device__ __forceinline__ float b(int k, int64_t m) const { return k < k_in ? __ldg(x + m * k_in + k) : 1.f; }
+  __device__ __forceinline__ void store(int64_t n, int k, float acc, int z) const { partial[((int64_t)z * n_out + n) * N + k] = acc; }
+};
+
+__global__ void __launch_bounds__(256) linear_wgrad_reduce(const float* __restrict__ partial, int splits, int n_out, int k_in, float* __restrict__ gW,
+                                                           float* __restrict__ gb) {
+  int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int N = k_in + 1;
+  if (t >= (int64_t)n_out * N) return;
+  const int n = (int)(t / N), k = (int)(t - (int64_t)n * N);
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += __ldg(partial + ((int64_t)z * n_out + n) * N + k);  // ascending z: deterministic
+  if (k < k_in) gW[(int64_t)n * k_in + k] = s;
+  else if (gb) gb[n] = s;
+}
+
+static int linear_wgrad_splits(int64_t rows, int64_t n_out, int64_t k_in) {
+  int64_t tiles = cdiv(n_out, BM) * cdiv(k_in + 1, BN);
+  int64_t s = (4 * (int64_t)148) / tiles;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  int64_t max_s = cdiv(rows > 0 ? rows : 1, 4 * BK);
+  if (s > max_s) s = max_s;
+  return (int)s;
+}
+
+size_t simt_linear_wgrad_workspace_bytes(int64_t rows, int64_t n_out, int64_t k_in) {
+  return (size_t)linear_wgrad_splits(rows, n_out, k_in) * n_out * (k_in + 1) * sizeof(float);
+}
+
+int simt_linear_forward(const float* x, const float* W, const float* bias, int64_t rows, int64_t n_out, int64_t k_in, float* out, cudaStream_t st) {
+  LinearForwardProblem pr;
+  pr.M = rows; pr.K = k_in; pr.k_chunk = k_in; pr.N = (int)n_out;
+  pr.x = x; pr.W = W; pr.bias = bias; pr.out = out;
+  dim3 grid((unsigned)cdiv(rows, BM), (unsigned)cdiv(n_out, BN), 1);
+  simt_gemm_kernel<LinearForwardProblem><<<grid, GEMM_THREADS, 0, st>>>(pr);
+  NT_LAUNCH_CHECK("simt_linear_forward", 1);
+  return NT_OK;
+}
+
+int simt_linear_dgrad(const float* g, const float* W, int64_t rows, int64_t n_out, int64_t k_in, float* gx, cudaStream_t st) {
+  LinearDgradProblem pr;
+  pr.M = rows; pr.K = n_out; pr.k_chunk = n_out; pr.N = (int)k_in;
+  pr.g = g; pr.W = W; pr.gx = gx;
+  dim3 grid((unsigned)cdiv(rows, BM), (unsigned)cdiv(k_in, BN), 1);
+  simt_gemm_kernel<LinearDgradProblem><<<grid, GEMM_THREADS, 0, st>>>(pr);
+  NT_LAUNCH_CHECK("simt_linear_dgrad", 1);
+  return NT_OK;
+}
+
+int simt_linear_wgrad(const float* g, const float* x, int64_t rows, int64_t n_out, int64_t k_in, float* gW, float* gb, float* partial, cudaStream_t st) {
+  const int splits = linear_wgrad_splits(rows, n_out, k_in);
+  LinearWgradProblem pr;
+  pr.M = n_out; pr.K = rows; pr.N = (int)k_in + 1; pr.n_out = (int)n_out; pr.k_in = (int)k_in;
+  pr.k_chunk = cdiv(cdiv(rows, splits), BK) * BK;
+  if (pr.k_chunk == 0) pr.k_chunk = BK;
+  pr.g = g; pr.x = x; pr.partial = partial;
+  dim3 grid((unsigned)cdiv(n_out, BM), (unsigned)cdiv(k_in + 1, BN), (unsigned)splits);
+  simt_gemm_kernel<LinearWgradProblem><<<grid, GEMM_THREADS, 0, st>>>(pr);
+  const int64_t total = n_out * (k_in + 1);
+  linear_wgrad_reduce<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(partial, splits, (int)n_out, (int)k_in, gW, gb);
+  NT_LAUNCH_CHECK("simt_linear_wgrad", 2);
+  return NT_OK;
+}
+
 }  // namespace nt

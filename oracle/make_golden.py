@@ -164,6 +164,39 @@ def run_readout_max(seed: int) -> dict[str, np.ndarray]:
             "gH": gH.numpy(), "H": H.detach().numpy(), "g_x": xr.grad.numpy()}
 
 
+def run_mlp_head(seed: int) -> dict[str, np.ndarray]:
+    """The reference's ``MLP`` factory (nn/mlp.py:9-68) on molecule vectors: two hidden layers, SiLU, unflattened ``(2, 3)`` output;
+    forward + all gradients in fp32 and fp64."""
+    import importlib
+
+    reference_loader.load()
+    RefMLP = importlib.import_module("notorch.nn.mlp").MLP
+    g = torch.Generator().manual_seed(seed)
+    B, d = 37, 52
+    kw = dict(input_dim=d, output_size=(2, 3), hidden_dim=24, num_layers=2, dropout=0.0)
+    torch.manual_seed(seed)
+    mlp = RefMLP(activation=nn.SiLU, **kw)
+    x = torch.randn(B, d, generator=g)
+    gY = torch.randn(B, 2, 3, generator=g)
+    out = {"meta": np.frombuffer(json.dumps(dict(kw, output_size=[2, 3], activation="silu", seed=seed)).encode(), dtype=np.uint8),
+           "x": x.numpy(), "gY": gY.numpy()}
+    for k, v in mlp.state_dict().items():
+        out["param/" + k] = v.numpy().copy()
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        m = RefMLP(activation=nn.SiLU, **kw).to(dt)
+        m.load_state_dict({k: v.to(dt) for k, v in mlp.state_dict().items()})
+        xr = x.detach().clone().to(dt).requires_grad_(True)
+        y = m(xr)
+        (y * gY.to(dt)).sum().backward()
+        out[f"{tag}/y"], out[f"{tag}/g_x"] = y.detach().numpy(), xr.grad.numpy()
+        for k, p_ in m.named_parameters():
+            out[f"{tag}/grad/" + k] = p_.grad.numpy()
+    return out
+
+
+EXTRAS = {"readout_max": (run_readout_max, 9001), "mlp_head": (run_mlp_head, 9002)}
+
+
 def main() -> None:
     if not reference_loader.available():
         raise SystemExit("reference tree not found; golden fixtures can only be made in the authoring container")
@@ -179,12 +212,12 @@ def main() -> None:
         total += os.path.getsize(path)
         print(f"{name:18s} V={int(data['num_atoms'].sum()):4d} E={int(data['num_edges'].sum()):4d} "
               f"{os.path.getsize(path) / 1024:.0f} KiB")
-    if only:
-        return
-    extra = run_readout_max(seed=9001)
-    path = os.path.join(OUT, "..", "golden_readouts", "readout_max.npz")
-    os.makedirs(os.path.dirname(path), exist_ok=True)
-    np.savez_compressed(path, **extra)
+    os.makedirs(os.path.join(OUT, "..", "golden_readouts"), exist_ok=True)
+    for name, (fn, seed) in EXTRAS.items():
+        if only and name not in only:
+            continue
+        np.savez_compressed(os.path.join(OUT, "..", "golden_readouts", f"{name}.npz"), **fn(seed=seed))
+        print(f"{name:18s} -> tests/golden_readouts/{name}.npz")
     print(f"total {total / 1024:.0f} KiB -> {OUT}")
 
 
