@@ -137,6 +137,9 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
+// what kind::tf32 makes of an fp32 word left as is in shared memory: the low 13 mantissa bits are ignored
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version = 1 at bit 46,
 // layout type 2 at bits 61-63, SBO = 1024 B between 8-row groups, LBO unused for swizzled K-major).
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {

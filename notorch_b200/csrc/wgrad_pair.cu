@@ -262,9 +262,18 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
               v[k] = make_float4(v[k].x * sc.x, v[k].y * sc.y, v[k].z * sc.z, v[k].w * sc.w);
             }
           }
-          const float4 h4 = make_float4(tf32_rna(v[k].x), tf32_rna(v[k].y), tf32_rna(v[k].z), tf32_rna(v[k].w));
+          // Unmodified fp32 data stays in place as the "hi" operand: kind::tf32 reads the upper 19 bits of the word, i.e. the value
+          // TRUNCATED to TF32, so lo = v - trunc(v) (exact, < 2^-10 |v|) is all that has to be computed and stored. Units that were
+          // changed in registers (dropout scale, the all-ones row) are written back rounded.
+          const bool rewritten = (k == ones_chunk) || (DROP && k >= A_CHUNKS);
+          float4 h4;
+          if (rewritten) {
+            h4 = make_float4(tf32_rna(v[k].x), tf32_rna(v[k].y), tf32_rna(v[k].z), tf32_rna(v[k].w));
+            *reinterpret_cast<float4*>(hi + k * CHUNK_BYTES) = h4;
+          } else {
+            h4 = make_float4(tf32_trunc(v[k].x), tf32_trunc(v[k].y), tf32_trunc(v[k].z), tf32_trunc(v[k].w));
+          }
           const float4 l4 = make_float4(tf32_rna(v[k].x - h4.x), tf32_rna(v[k].y - h4.y), tf32_rna(v[k].z - h4.z), tf32_rna(v[k].w - h4.w));
-          *reinterpret_cast<float4*>(hi + k * CHUNK_BYTES) = h4;
           *reinterpret_cast<float4*>(lo + k * CHUNK_BYTES) = l4;
         }
       }
