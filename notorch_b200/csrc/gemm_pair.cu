@@ -534,18 +534,13 @@ layer_gemm_pair(const Params p) {
             m = make_float4(m.x * sc.x, m.y * sc.y, m.z * sc.z, m.w * sc.w);
           }
           if (!BF16) {
-            if (MODE != 0 && !(MODE == 1 && DROP)) {
-              // the rows are used as they are: the fp32 words stay in place as the hi operand (kind::tf32 reads them truncated
-              // to TF32), only lo = v - trunc(v) is computed and stored
-              const float4 hi = make_float4(tf32_trunc(m.x), tf32_trunc(m.y), tf32_trunc(m.z), tf32_trunc(m.w));
-              const float4 lo = make_float4(tf32_rna(m.x - hi.x), tf32_rna(m.y - hi.y), tf32_rna(m.z - hi.z), tf32_rna(m.w - hi.w));
-              *reinterpret_cast<float4*>(a1 + u * 16) = lo;
-            } else {
-              const float4 hi = make_float4(tf32_rna(m.x), tf32_rna(m.y), tf32_rna(m.z), tf32_rna(m.w));
-              const float4 lo = make_float4(tf32_rna(m.x - hi.x), tf32_rna(m.y - hi.y), tf32_rna(m.z - hi.z), tf32_rna(m.w - hi.w));
-              *reinterpret_cast<float4*>(a0 + u * 16) = hi;
-              *reinterpret_cast<float4*>(a1 + u * 16) = lo;
-            }
+            // K2 forms m in registers and has to write it anyway: fully rounded split. Rows used as they are (dgrad without dropout,
+            // dense forward) stay in place as the hi operand and only lo is stored (tc_common.cuh).
+            constexpr bool IN_PLACE = MODE == 2 || (MODE == 1 && !DROP);
+            float4 hi, lo;
+            tf32_split4<IN_PLACE ? SPLIT_INPLACE : SPLIT_RNA>(m, hi, lo);
+            if (!IN_PLACE) *reinterpret_cast<float4*>(a0 + u * 16) = hi;
+            *reinterpret_cast<float4*>(a1 + u * 16) = lo;
           }
           raw0[i] = m;
         }

@@ -140,6 +140,27 @@ __device__ __forceinline__ float tf32_rna(float x) {
 // what kind::tf32 makes of an fp32 word left as is in shared memory: the low 13 mantissa bits are ignored
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+// hi / lo split of a streamed operand for the three-product TF32 scheme. kind::tf32 reads the upper 19 bits of a shared-memory word,
+// i.e. the fp32 value TRUNCATED to TF32, so a value can also be left as it is and serve as its own hi part.
+//   SPLIT_RNA      hi = rna(v), lo = rna(v - hi): two conversions per value, hi has to be written; smallest error (K2: not ALU-bound)
+//   SPLIT_INPLACE  hi = v as it is (never written when the tile holds the raw rows), lo = rna(v - trunc(v)): one conversion (K4a)
+//   SPLIT_NOCVT    hi = v as it is, lo = v - trunc(v) left to the tensor core's truncation: no conversion. cvt.rna.tf32 issues at a
+//                  fraction of the FP32 rate and K4b's producers are ALU / shared-memory bound: 267 -> 241 us at d = 300, with the
+//                  weight-gradient error unchanged to two digits (4.1e-6 -> 4.2e-6 at d = 1024, measured)
+enum { SPLIT_RNA = 0, SPLIT_INPLACE = 1, SPLIT_NOCVT = 2 };
+template <int KIND>
+__device__ __forceinline__ void tf32_split4(const float4& v, float4& hi, float4& lo) {
+  if constexpr (KIND == SPLIT_RNA) {
+    hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+    lo = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
+  } else {
+    const float4 t = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
+    hi = v;
+    if constexpr (KIND == SPLIT_INPLACE) lo = make_float4(tf32_rna(v.x - t.x), tf32_rna(v.y - t.y), tf32_rna(v.z - t.z), tf32_rna(v.w - t.w));
+    else lo = make_float4(v.x - t.x, v.y - t.y, v.z - t.z, v.w - t.w);
+  }
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version = 1 at bit 46,
 // layout type 2 at bits 61-63, SBO = 1024 B between 8-row groups, LBO unused for swizzled K-major).
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {

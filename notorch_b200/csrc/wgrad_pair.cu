@@ -40,9 +40,22 @@ constexpr int SMEM_BYTES = OFF_BAR + 128;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 
 struct Geometry {
-  int d, m_units, n_tiles, n_tile, n_a, n_b, ones_row, splits, ld_partial;
-  int64_t kb_total, kb_per_split;
+  int d, m_units, n_tiles, n_tile, n_a, n_b, ones_row, ld_partial;
+  // The last unit of feature rows runs at HALF height (M = 128: 64 rows per CTA) when at most 128 rows of it are real
+  // (d = 300: rows 256..300 incl. the all-ones bias row): half the MMA work and half the m columns to stage. Such units get
+  // fewer edge splits than the full-height ones, in proportion to their cost per edge.
+  int half_last, full_units, half_units, splits, splits_last, planes;
+  int64_t kb_total, kb_per_split, kb_per_split_last;
 };
+
+static float half_unit_cost() {
+  static const float w = [] {
+    const char* e = getenv("NOTORCH_B200_WGRAD_HALF_COST");
+    const float v = e ? (float)atof(e) : 0.78f;
+    return v > 0.05f && v <= 1.f ? v : 0.78f;
+  }();
+  return w;
+}
 
 static Geometry make_geometry(int64_t E, int d, int sms) {
   Geometry g;
@@ -56,12 +69,28 @@ static Geometry make_geometry(int64_t E, int d, int sms) {
   else { g.n_a = 128; g.n_b = g.n_tile - 128; }
   g.ld_partial = g.n_tiles * g.n_tile;
   g.kb_total = (E + BLOCK_E - 1) / BLOCK_E;
-  int64_t units = (int64_t)g.m_units * g.n_tiles;
-  int64_t s = (sms / 2) / units;
-  if (s < 1) s = 1;
-  if (s > g.kb_total) s = g.kb_total > 0 ? g.kb_total : 1;
-  g.splits = (int)s;
-  g.kb_per_split = (g.kb_total + s - 1) / s;
+  static const bool allow_half = [] { const char* e = getenv("NOTORCH_B200_WGRAD_HALF"); return !(e && e[0] == '0'); }();
+  const int last_rows = d + g.ones_row - (g.m_units - 1) * 2 * TILE_M;
+  g.half_last = (allow_half && last_rows <= TILE_M) ? 1 : 0;
+  g.full_units = (g.m_units - g.half_last) * g.n_tiles;
+  g.half_units = g.half_last * g.n_tiles;
+  const int clusters = sms / 2 > 0 ? sms / 2 : 1;
+  int64_t sf = 0, sl = 0;
+  if (g.full_units > 0) {
+    sf = (int64_t)((float)clusters / ((float)g.full_units + half_unit_cost() * (float)g.half_units));
+    if (sf < 1) sf = 1;
+    if (sf > g.kb_total) sf = g.kb_total > 0 ? g.kb_total : 1;
+  }
+  if (g.half_units > 0) {
+    sl = (clusters - g.full_units * sf) / g.half_units;
+    if (sl < 1) sl = 1;
+    if (sl > g.kb_total) sl = g.kb_total > 0 ? g.kb_total : 1;
+  }
+  g.splits = (int)sf;
+  g.splits_last = (int)sl;
+  g.planes = (int)(sf > sl ? sf : sl);
+  g.kb_per_split = sf > 0 ? (g.kb_total + sf - 1) / sf : 0;
+  g.kb_per_split_last = sl > 0 ? (g.kb_total + sl - 1) / sl : 0;
   return g;
 }
 
@@ -77,9 +106,9 @@ struct Params {
   int products;
 };
 
-// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both MN-major, M = 256 (pair)
-__device__ __forceinline__ uint32_t make_idesc_pair_mn(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (3u << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both MN-major, M = 256 or 128 over the CTA pair
+__device__ __forceinline__ uint32_t make_idesc_pair_mn(int n, int m) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (3u << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 template <bool DROP>
@@ -101,17 +130,31 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
 
   const Geometry& geo = p.geo;
   const int d = geo.d;
-  const int units = geo.m_units * geo.n_tiles;
   const int pair_id = blockIdx.x >> 1;
-  const int unit = pair_id % units;  // pairs of one edge range are adjacent: the g tiles they share hit in L2
-  const int split = pair_id / units;
-  const int mu = unit % geo.m_units, nt = unit / geo.m_units;
-  const int i0 = mu * 2 * TILE_M + (int)rank * TILE_M;      // this CTA's 128 feature rows of m
+  // full-height units first (pairs of one edge range are adjacent: the g tiles they share hit in L2), then the half-height ones
+  const int n_full = geo.full_units * geo.splits;
+  const bool half = pair_id >= n_full;
+  int mu, nt, split;
+  if (!half) {
+    const int unit = pair_id % geo.full_units, mf = geo.m_units - geo.half_last;
+    split = pair_id / geo.full_units;
+    mu = unit % mf;
+    nt = unit / mf;
+  } else {
+    const int q = pair_id - n_full;
+    split = q / geo.half_units;
+    mu = geo.m_units - 1;
+    nt = q % geo.half_units;
+  }
+  const int rows_cta = half ? TILE_M / 2 : TILE_M;          // feature rows of m this CTA stages and accumulates
+  const int a_chunks = rows_cta / 32;
+  const int i0 = mu * 2 * TILE_M + (int)rank * rows_cta;
   const int o0 = nt * geo.n_tile;
   const int ha = geo.n_a / 2, hb = geo.n_b / 2;             // this CTA's share of the two MMAs' N (multiples of 32)
   const int b_chunks = (ha + hb) / 32;
-  const int64_t kb_lo = (int64_t)split * geo.kb_per_split;
-  int64_t kb_hi = kb_lo + geo.kb_per_split;
+  const int64_t per_split = half ? geo.kb_per_split_last : geo.kb_per_split;
+  const int64_t kb_lo = (int64_t)split * per_split;
+  int64_t kb_hi = kb_lo + per_split;
   if (kb_hi > geo.kb_total) kb_hi = geo.kb_total;
   const int64_t nkb = kb_hi > kb_lo ? kb_hi - kb_lo : 0;
 
@@ -135,27 +178,41 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
 
   if (warp < NUM_EPI_WARPS) {
     // ===================================== EPILOGUE (once) =====================================
-    const int i = i0 + warp * 32 + lane;
-    float* dst = p.partial + ((int64_t)split * geo.m_units * 2 * TILE_M + i) * geo.ld_partial + o0;
+    // Accumulator layout in tensor memory. M = 256: lane = feature row (128 per CTA), column = output column. M = 128 (half-height
+    // unit, 64 rows per CTA): lanes 0-63 hold the rows for the first half of each MMA's N, lanes 64-127 the same rows for the
+    // second half, so an MMA of width N occupies N / 2 columns.
+    const int row = half ? (warp & 1) * 32 + lane : warp * 32 + lane;
+    float* dst = p.partial + ((int64_t)split * geo.m_units * 2 * TILE_M + i0 + row) * geo.ld_partial + o0;
     if (nkb > 0) {
       mbar_wait_relaxed(bar_tmem_full, 0);
       tc_fence_after();
-      for (int cc = 0; cc < geo.n_tile / 16; ++cc) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 16), v);
-        tmem_ld_wait();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+      auto drain = [&](uint32_t col0, int ncols, float* out) {
+        for (int cc = 0; cc < ncols / 16; ++cc) {
+          uint32_t v[16];
+          tmem_ld16(lane_base + col0 + (uint32_t)(cc * 16), v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(dst + cc * 16 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(out + cc * 16 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      };
+      if (!half) {
+        drain(0u, geo.n_tile, dst);
+      } else {
+        const int hi_half = warp >> 1;
+        drain(0u, geo.n_a / 2, dst + hi_half * (geo.n_a / 2));
+        if (geo.n_b > 0) drain((uint32_t)geo.n_a, geo.n_b / 2, dst + geo.n_a + hi_half * (geo.n_b / 2));
       }
-    } else {
+    } else if (!half || warp < 2) {
       for (int c = 0; c < geo.n_tile; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else if (warp == MMA_WARP) {
     // ===================================== MMA ISSUER (leader CTA only) =====================================
     if (leader) {
-      const uint32_t idesc_a = make_idesc_pair_mn(geo.n_a);
-      const uint32_t idesc_b = make_idesc_pair_mn(geo.n_b > 0 ? geo.n_b : 64);
+      const int mma_m = half ? TILE_M : 2 * TILE_M;
+      const uint32_t idesc_a = make_idesc_pair_mn(geo.n_a, mma_m);
+      const uint32_t idesc_b = make_idesc_pair_mn(geo.n_b > 0 ? geo.n_b : 64, mma_m);
       int s = 0;
       uint32_t ph = 0;
 #pragma unroll 1
@@ -205,7 +262,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
     const int E_i = (int)p.E;
     const uint32_t ready_leader = map_to_cta(bar_ready, 0);
     // the all-ones feature row of m (bias gradient) lives in this CTA's A tile iff i0 <= d < i0 + 128
-    const bool ones_here = geo.ones_row && d >= i0 && d < i0 + TILE_M;
+    const bool ones_here = geo.ones_row && d >= i0 && d < i0 + rows_cta;
     const int ones_chunk = ones_here ? (d - i0) / 32 : -1, ones_c16 = ones_here ? ((d - i0) % 32) / 4 : -1;
 
     auto feature_of = [&](int chunk) {  // first feature of this thread's unit in chunk `chunk`
@@ -218,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
       const uint32_t dst = sbase + s * STAGE_BYTES + pt * 16;
 #pragma unroll
       for (int k = 0; k < MAX_UNITS; ++k) {
-        if (k < n_chunks) {
+        if (k < n_chunks && (k < a_chunks || k >= A_CHUNKS)) {
           const int f = feature_of(k);
           const bool ok = e < E_i && f < d;
           const float* src = (k < A_CHUNKS ? p.m : p.g) + (ok ? (int64_t)e * d + f : 0);
@@ -249,10 +306,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
       float4 v[MAX_UNITS];
 #pragma unroll
       for (int k = 0; k < MAX_UNITS; ++k)  // all reads first: the in-place stores below must not serialise the units
-        if (k < n_chunks) v[k] = *reinterpret_cast<const float4*>(hi + k * CHUNK_BYTES);
+        if (k < n_chunks && (k < a_chunks || k >= A_CHUNKS)) v[k] = *reinterpret_cast<const float4*>(hi + k * CHUNK_BYTES);
 #pragma unroll
       for (int k = 0; k < MAX_UNITS; ++k) {
-        if (k < n_chunks) {
+        if (k < n_chunks && (k < a_chunks || k >= A_CHUNKS)) {
           if (k == ones_chunk) {
             if (c16 == ones_c16 && e < E_i) v[k].x = 1.f;
           } else if (DROP && k >= A_CHUNKS) {
@@ -262,18 +319,13 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
               v[k] = make_float4(v[k].x * sc.x, v[k].y * sc.y, v[k].z * sc.z, v[k].w * sc.w);
             }
           }
-          // Unmodified fp32 data stays in place as the "hi" operand: kind::tf32 reads the upper 19 bits of the word, i.e. the value
-          // TRUNCATED to TF32, so lo = v - trunc(v) (exact, < 2^-10 |v|) is all that has to be computed and stored. Units that were
-          // changed in registers (dropout scale, the all-ones row) are written back rounded.
+          // hi / lo split without conversions (tc_common.cuh, SPLIT_NOCVT): the fp32 data stays in place as the hi operand and only
+          // lo = v - trunc(v) is computed and stored. Units that were changed in registers (dropout scale, the all-ones row) are
+          // written back.
           const bool rewritten = (k == ones_chunk) || (DROP && k >= A_CHUNKS);
-          float4 h4;
-          if (rewritten) {
-            h4 = make_float4(tf32_rna(v[k].x), tf32_rna(v[k].y), tf32_rna(v[k].z), tf32_rna(v[k].w));
-            *reinterpret_cast<float4*>(hi + k * CHUNK_BYTES) = h4;
-          } else {
-            h4 = make_float4(tf32_trunc(v[k].x), tf32_trunc(v[k].y), tf32_trunc(v[k].z), tf32_trunc(v[k].w));
-          }
-          const float4 l4 = make_float4(tf32_rna(v[k].x - h4.x), tf32_rna(v[k].y - h4.y), tf32_rna(v[k].z - h4.z), tf32_rna(v[k].w - h4.w));
+          float4 h4, l4;
+          tf32_split4<SPLIT_NOCVT>(v[k], h4, l4);
+          if (rewritten) *reinterpret_cast<float4*>(hi + k * CHUNK_BYTES) = h4;
           *reinterpret_cast<float4*>(lo + k * CHUNK_BYTES) = l4;
         }
       }
@@ -307,8 +359,9 @@ __global__ void __launch_bounds__(256) wgrad_pair_reduce(const float* __restrict
   const int i = (int)(t / d), o = (int)(t - (int64_t)i * d);  // o fastest: coalesced reads of the partial planes
   const int64_t plane = (int64_t)geo.m_units * 2 * TILE_M * geo.ld_partial;
   const float* src = partial + (int64_t)i * geo.ld_partial + o;
+  const int nz = (geo.half_last && i >= (geo.m_units - 1) * 2 * TILE_M) ? geo.splits_last : geo.splits;
   float s = 0.f;
-  for (int z = 0; z < geo.splits; ++z) s += __ldg(src + z * plane);
+  for (int z = 0; z < nz; ++z) s += __ldg(src + z * plane);
   if (i < d) gW[(int64_t)o * d + i] = s;
   else if (gb) gb[o] = s;
 }
@@ -320,7 +373,7 @@ size_t pair_wgrad_workspace_bytes(int64_t E, int64_t d) {
   int sms = num_sms();
   if (sms <= 0) sms = 148;
   wgp::Geometry geo = wgp::make_geometry(E, (int)d, sms);
-  return (size_t)geo.splits * geo.m_units * 2 * tc::TILE_M * geo.ld_partial * sizeof(float) + 1024;
+  return (size_t)geo.planes * geo.m_units * 2 * tc::TILE_M * geo.ld_partial * sizeof(float) + 1024;
 }
 
 // returns NT_ERR_UNSUPPORTED when the bias gradient cannot ride along (d % 256 == 0) and gb is requested
@@ -355,7 +408,7 @@ int pair_layer_wgrad(const float* g, const float* m, int64_t E, int64_t d, float
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_pair_kernel)");
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * p.geo.splits * p.geo.m_units * p.geo.n_tiles));
+  cfg.gridDim = dim3((unsigned)(2 * (p.geo.full_units * p.geo.splits + p.geo.half_units * p.geo.splits_last)));
   cfg.blockDim = dim3(wgp::THREADS);
   cfg.dynamicSmemBytes = wgp::SMEM_BYTES;
   cfg.stream = st;
