@@ -104,6 +104,7 @@ struct Params {
   uint32_t drop_thr;
   uint64_t seed, offset;
   int products;
+  int ablate;  // debug (NOTORCH_B200_WGRAD_ABLATE): 1 = no MMAs, 2 = no hi / lo split, 4 = no loads; results are then meaningless
 };
 
 // kind::tf32 instruction descriptor: D = F32, A = B = TF32, both MN-major, M = 256 or 128 over the CTA pair
@@ -229,7 +230,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
           for (int j = 0; j < BLOCK_E / 8; ++j) {
             const uint32_t k16 = j * (1024u >> 4);  // next 8 edges = the next two 4-row swizzle atoms of every chunk
             const uint32_t acc = (kb | j) != 0 ? 1u : 0u;
-            if (p.products == 3) {
+            if (p.ablate & 1) {
+            } else if (p.products == 3) {
               umma2_tf32_lo(tmem_base, a_lo + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, acc);
               umma2_tf32_lo(tmem_base, a_hi + k16, b_lo + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, 1u);
               umma2_tf32_lo(tmem_base, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, 1u);
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
     auto load_step = [&]() {
       if (lkb < nkb) {
         mbar_wait(bar_empty + 8 * ls, lph ^ 1);
-        issue(lkb, ls);
+        if (!(p.ablate & 4)) issue(lkb, ls);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       ++lkb;
@@ -304,6 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
       uint8_t* lo = hi + PART_BYTES;
       asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
       float4 v[MAX_UNITS];
+      if (!(p.ablate & 2)) {
 #pragma unroll
       for (int k = 0; k < MAX_UNITS; ++k)  // all reads first: the in-place stores below must not serialise the units
         if (k < n_chunks && (k < a_chunks || k >= A_CHUNKS)) v[k] = *reinterpret_cast<const float4*>(hi + k * CHUNK_BYTES);
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
           if (rewritten) *reinterpret_cast<float4*>(hi + k * CHUNK_BYTES) = h4;
           *reinterpret_cast<float4*>(lo + k * CHUNK_BYTES) = l4;
         }
+      }
       }
       fence_proxy_async();
       __syncwarp();
@@ -393,6 +397,8 @@ int pair_layer_wgrad(const float* g, const float* m, int64_t E, int64_t d, float
   p.partial = static_cast<float*>(workspace);
   p.E = E;
   p.products = products;
+  static const int ablate = [] { const char* e = getenv("NOTORCH_B200_WGRAD_ABLATE"); return e ? atoi(e) : 0; }();
+  p.ablate = ablate;
   p.drop_p = drop_p;
   p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   double t = (double)drop_p * 4294967296.0;
