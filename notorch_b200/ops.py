@@ -36,6 +36,7 @@ ACT_CODES = {
 _GEMM_MODES = {"tf32x3": GEMM_TF32X3, "fp32": GEMM_FP32, "tf32": GEMM_TF32, "bf16": GEMM_BF16}
 _gemm_mode = _GEMM_MODES[os.environ.get("NOTORCH_B200_GEMM", "tf32x3").lower()]
 _validate_mode = os.environ.get("NOTORCH_B200_VALIDATE", "sync").lower()  # "sync" | "deferred" | "off"
+_parallel_csr = os.environ.get("NOTORCH_B200_PARALLEL_CSR", "1") != "0"  # by_src / by_dst / by_rev built on three streams
 _fuse_k5_k6 = os.environ.get("NOTORCH_B200_FUSE_K5K6", "1") != "0"  # backward epilogue sums the outgoing-edge gradients itself (no K5 launch)
 
 
@@ -235,25 +236,42 @@ def _check_status(status: Tensor, what: str) -> None:
     _drain_status()
 
 
+def _csr_outputs(n: int, num_segments: int, dev: torch.device) -> tuple[Tensor, Tensor, Tensor]:
+    return (torch.empty(num_segments + 1, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.int32, device=dev),
+            torch.empty(n, dtype=torch.int32, device=dev))
+
+
+def _launch_build_csr(keys: Tensor, num_segments: int, outs: tuple[Tensor, Tensor, Tensor], status: Tensor, slot: int) -> None:
+    rowptr, perm, keys32 = outs
+    n = keys.numel()
+    L = _lib.lib()
+    ws = _workspace(keys.device, L.nt_build_csr_workspace_bytes(n, num_segments), slot=slot)
+    _run("csr:nt_build_csr", L.nt_build_csr, _p(keys), n, num_segments, _p(keys32), _p(rowptr), _p(perm), _p(status), _p(ws), ws.numel(), _stream())
+
+
 def build_segment_csr(keys: Tensor, num_segments: int, what: str = "index", status: Tensor | None = None,
                       validate: bool = True) -> SegmentCSR:
     keys = _require(keys, what, torch.int64, 1)
-    n = keys.numel()
     dev = keys.device
     with torch.cuda.device(dev):
-        L = _lib.lib()
-        rowptr = torch.empty(num_segments + 1, dtype=torch.int32, device=dev)
-        perm = torch.empty(n, dtype=torch.int32, device=dev)
-        keys32 = torch.empty(n, dtype=torch.int32, device=dev)
+        outs = _csr_outputs(keys.numel(), num_segments, dev)
         if status is None:
             status = torch.zeros(1, dtype=torch.int32, device=dev)
-        nbytes = L.nt_build_csr_workspace_bytes(n, num_segments)
-        ws = _workspace(dev, nbytes)
-        _run("csr:nt_build_csr", L.nt_build_csr, _p(keys), n, num_segments, _p(keys32), _p(rowptr), _p(perm), _p(status), _p(ws), ws.numel(),
-             _stream())
+        _launch_build_csr(keys, num_segments, outs, status, slot=0)
     if validate:
         _check_status(status, what)
-    return SegmentCSR(rowptr, perm, keys32, num_segments, status)
+    return SegmentCSR(outs[0], outs[1], outs[2], num_segments, status)
+
+
+_side_streams: dict[tuple[int, int], torch.cuda.Stream] = {}
+
+
+def _side_stream(device: torch.device, which: int) -> torch.cuda.Stream:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _side_streams.get((idx, which))
+    if st is None:
+        st = _side_streams[(idx, which)] = torch.cuda.Stream(device=idx)
+    return st
 
 
 @dataclass
@@ -292,10 +310,30 @@ def build_graph_csr(edge_index: Tensor, rev_index: Tensor, num_nodes: int) -> Gr
     E = edge_index.shape[1]
     if rev_index.shape[0] != E:
         raise RuntimeError(f"notorch_b200: rev_index has {rev_index.shape[0]} entries for {E} edges")
-    status = torch.zeros(1, dtype=torch.int32, device=edge_index.device)
-    by_src = build_segment_csr(edge_index[0], num_nodes, "edge_index[0]", status, validate=False)
-    by_dst = build_segment_csr(edge_index[1], num_nodes, "edge_index[1]", status, validate=False)
-    by_rev = build_segment_csr(rev_index, E, "rev_index", status, validate=False)
+    dev = edge_index.device
+    keys = (edge_index[0], edge_index[1], rev_index)
+    sizes = (num_nodes, num_nodes, E)
+    with torch.cuda.device(dev):
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        outs = [_csr_outputs(E, S, dev) for S in sizes]  # allocated on the caller's stream, whichever stream fills them
+        if _parallel_csr and _timer is None and E > 0:
+            # the three CSRs are independent chains of small, latency-bound kernels: build two of them on side streams
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            _launch_build_csr(keys[0], sizes[0], outs[0], status, slot=0)
+            for which in (1, 2):
+                side = _side_stream(dev, which)
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    _launch_build_csr(keys[which], sizes[which], outs[which], status, slot=4 + which)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                main.wait_event(done)
+        else:
+            for which in range(3):
+                _launch_build_csr(keys[which], sizes[which], outs[which], status, slot=0)
+    by_src, by_dst, by_rev = (SegmentCSR(o[0], o[1], o[2], S, status) for o, S in zip(outs, sizes))
     _check_status(status, "edge_index / rev_index")
     return GraphCSR(num_nodes, E, by_dst, by_src, by_rev)
 
