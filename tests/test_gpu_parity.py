@@ -260,7 +260,7 @@ def test_block_vs_oracle_fresh_inputs(mode, batch, d, depth, config):
 
 
 @pytest.mark.parametrize("mode", GEMM_MODES)
-@pytest.mark.parametrize("E,d", [(1, 16), (127, 64), (128, 300), (129, 304), (1000, 256), (777, 512), (300, 1024), (5000, 300), (2500, 100), (200, 320), (260, 2048), (513, 8)])
+@pytest.mark.parametrize("E,d", [(1, 16), (127, 64), (128, 300), (129, 304), (1000, 256), (777, 512), (300, 1024), (5000, 300), (2500, 100), (200, 320), (260, 2048), (513, 8), (700, 332), (400, 576)])
 def test_layer_kernels_vs_fp64(mode, E, d):
     """K2 / K4a / K4b in isolation on random (adversarial: arbitrary src / rev) indices vs an fp64 restatement."""
     from notorch_b200 import ops
