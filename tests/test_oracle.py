@@ -167,3 +167,25 @@ def test_readout_max_matches_reference_golden():
     H = O.readout_max(torch.from_numpy(z["x"]), torch.from_numpy(z["batch_node_index"]), 7)
     assert torch.equal(H, torch.from_numpy(z["H"]))
     assert (H[2] == 0).all() and (H[5] == 0).all()  # empty molecules give 0 (torch_scatter.scatter_max)
+
+
+@pytest.mark.parametrize("reduce", ["max", "min"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_seg_extreme_restatement_vs_bruteforce(reduce, seed):
+    """The vectorised arg-reduction of the oracle against a literal loop over rows in ascending order (torch-scatter's CPU kernel:
+    strict comparison, so the first extreme wins; untouched outputs become 0 with argument len(x))."""
+    gen = torch.Generator().manual_seed(seed)
+    n, S, d = 57, 9, 5
+    index = torch.randint(0, S - 2, (n,), generator=gen)  # segments S-2, S-1 stay empty
+    x = torch.randint(-2, 3, (n, d), generator=gen).double()  # many ties
+    x[:, -1] = torch.randn(n, generator=gen, dtype=torch.float64)
+    val, arg = O.seg_extreme(x, index, S, reduce)
+    want_v, want_a = torch.zeros(S, d, dtype=torch.float64), torch.full((S, d), n, dtype=torch.long)
+    better = (lambda a, b: a > b) if reduce == "max" else (lambda a, b: a < b)
+    for r in range(n):
+        s = int(index[r])
+        for c in range(d):
+            if want_a[s, c] == n or better(float(x[r, c]), float(want_v[s, c])):
+                want_v[s, c], want_a[s, c] = x[r, c], r
+    assert torch.equal(val, want_v) and torch.equal(arg, want_a)
+    assert torch.equal(O.seg_reduce(x, index, S, reduce), want_v)
