@@ -22,51 +22,56 @@ from ..residual import Residual
 
 
 class ChempropLayer(nn.Module):
+    """One message-passing depth. Parameters live in ``update = Sequential(Linear(d, d), Dropout(p))`` so that a reference
+    checkpoint loads with ``strict=True``; the modules in ``update`` are containers only — K1 + K2 compute the layer."""
+
     def __init__(self, hidden_dim: int, act: type[nn.Module] = nn.ReLU, bias: bool = True, dropout: float = 0.0,
                  reduce: Reduction = "sum"):
         super().__init__()
-        self.act = act()
-        self.reduce = reduce
-        self.update = nn.Sequential(nn.Linear(hidden_dim, hidden_dim, bias), nn.Dropout(dropout))
+        w_h = nn.Linear(hidden_dim, hidden_dim, bias=bias)
+        self.act, self.reduce = act(), reduce
+        self.update = nn.Sequential(w_h, nn.Dropout(p=dropout))
 
     def forward(self, edge_feats: Tensor, node_feats: Tensor, edge_index: Tensor, rev_index: Tensor, *,
                 _residual: bool = False, _csr: ops.GraphCSR | None = None) -> Tensor:
-        # node_feats is used only for its length, exactly like the reference (chemprop.py:39)
-        csr = _csr if _csr is not None else ops.graph_csr_from_tensors(edge_index, rev_index, len(node_feats))
-        linear, drop = self.update[0], self.update[1]
-        return ops.layer(edge_feats, linear.weight, linear.bias, csr, act=ops.act_code(self.act), reduce=self.reduce,
-                         residual=_residual, dropout=drop.p, training=self.training and drop.training)
+        # only len(node_feats) matters, as in the reference (chemprop.py:39); a block passes its cached CSR bundle and asks for the
+        # residual to be added inside K2
+        if _csr is None:
+            _csr = ops.graph_csr_from_tensors(edge_index, rev_index, len(node_feats))
+        w_h, drop = self.update
+        return ops.layer(edge_feats, w_h.weight, w_h.bias, _csr, act=ops.act_code(self.act), reduce=self.reduce, residual=_residual,
+                         dropout=drop.p, training=self.training and drop.training)
 
     def extra_repr(self):
         return f"(reduce): {self.reduce}"
 
 
 class ChempropBlock(nn.Module):
+    """``depth`` message-passing layers between the edge initialisation and the final edge -> atom reduction. With ``shared=True``
+    every depth holds the SAME layer object (chemprop.py:65-66), each wrapped in its own ``Residual`` when ``residual=True``."""
+
     def __init__(self, hidden_dim: int = 256, act: type[nn.Module] = nn.ReLU, bias: bool = True, dropout: float = 0.0,
                  depth: int = 3, residual: bool = True, shared: bool = False, reduce: Reduction = "sum"):
         super().__init__()
-        if shared:
-            one = ChempropLayer(hidden_dim, act, bias, dropout, reduce)
-            layers = [one for _ in range(depth)]  # the same module object at every depth (chemprop.py:65-66)
-        else:
-            layers = [ChempropLayer(hidden_dim, act, bias, dropout, reduce) for _ in range(depth)]
-        if residual:
-            layers = [Residual(layer) for layer in layers]
-        self.layers = nn.ModuleList(layers)
-        self.hidden_dim = hidden_dim
-        self.reduce = reduce
+        stack: list[nn.Module] = []
+        core = None
+        for _ in range(depth):  # created in depth order: the same RNG consumption as the reference under torch.manual_seed
+            if core is None or not shared:
+                core = ChempropLayer(hidden_dim, act=act, bias=bias, dropout=dropout, reduce=reduce)
+            stack.append(Residual(core) if residual else core)
+        self.layers = nn.ModuleList(stack)
+        self.hidden_dim, self.reduce = hidden_dim, reduce
 
     @property
     def depth(self) -> int:
         return len(self.layers)
 
     def forward(self, G: Graph | BatchedGraph):
-        csr = ops.graph_csr(G)
+        csr = ops.graph_csr(G)  # int32 CSR bundle, built once per batch and cached on the graph object
         h = ops.edge_init(G.node_feats, G.edge_feats, csr)  # K0
         for entry in self.layers:
-            if isinstance(entry, Residual):
-                h = entry.module(h, G.node_feats, G.edge_index, G.rev_index, _residual=True, _csr=csr)
-            else:
-                h = entry(h, G.node_feats, G.edge_index, G.rev_index, _csr=csr)
-        node_hiddens = ops.edge_to_atom(h, csr, self.reduce)  # K1, no activation (chemprop.py:86)
-        return G.update(node_feats=node_hiddens, edge_feats=h)
+            fused_residual = isinstance(entry, Residual)
+            layer = entry.module if fused_residual else entry
+            h = layer(h, G.node_feats, G.edge_index, G.rev_index, _residual=fused_residual, _csr=csr)
+        atoms = ops.edge_to_atom(h, csr, self.reduce)  # K1 without activation (chemprop.py:86)
+        return G.update(node_feats=atoms, edge_feats=h)
