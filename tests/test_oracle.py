@@ -189,3 +189,27 @@ def test_seg_extreme_restatement_vs_bruteforce(reduce, seed):
                 want_v[s, c], want_a[s, c] = x[r, c], r
     assert torch.equal(val, want_v) and torch.equal(arg, want_a)
     assert torch.equal(O.seg_reduce(x, index, S, reduce), want_v)
+
+
+def test_constructor_surface_matches_live_reference():
+    """hydra builds the reference's modules from constructor kwargs (cli/train.py:24-26), so the drop-in classes must take exactly the
+    same arguments with the same defaults. Compared against the live reference when it is mounted (authoring container only)."""
+    import importlib
+    import inspect
+
+    from oracle import reference_loader
+
+    if not reference_loader.available():
+        pytest.skip("reference tree not mounted")
+    reference_loader.load()
+    ours = importlib.import_module("notorch_b200.nn")
+
+    def surface(fn):
+        return [(n, p.default) for n, p in inspect.signature(fn).parameters.items() if n != "self"]
+
+    for module, names in (("notorch.nn.gnn.chemprop", ["ChempropLayer", "ChempropBlock"]),
+                          ("notorch.nn.gnn.agg", ["Sum", "Mean", "Max", "Gated", "SDPAttention"]), ("notorch.nn.residual", ["Residual"])):
+        ref = importlib.import_module(module)
+        for name in names:
+            assert surface(getattr(ref, name).__init__) == surface(getattr(ours, name).__init__), name
+    assert surface(importlib.import_module("notorch.nn.mlp").MLP) == surface(ours.MLP)
