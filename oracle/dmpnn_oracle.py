@@ -20,6 +20,9 @@ What each function follows (paths relative to ``/root/reference``):
 * ``edge_init``      — ``notorch/nn/gnn/chemprop.py:83``.
 * ``seg_reduce``     — ``torch_scatter.scatter`` as called at ``chemprop.py:39,86`` and
                        ``nn/gnn/agg.py:27,36`` (sum = ``zeros.scatter_add_``; mean = sum / clamp(count, 1)).
+* ``seg_extreme``    — ``torch_scatter.scatter_max`` / ``scatter_min`` (``reduce="max" | "min"`` at ``chemprop.py:39,86``,
+                       ``agg.py:45``): published torch-scatter 2.1 semantics, pinned by ``tests/golden/{max,min}_reduce.npz`` and
+                       ``tests/golden_readouts/readout_max.npz`` (reference run on the ``torch_scatter`` shim) and by a brute-force loop.
 * ``layer_forward``  — ``notorch/nn/gnn/chemprop.py:28-43`` + ``notorch/nn/residual.py:27-28``.
 * ``block_forward``  — ``notorch/nn/gnn/chemprop.py:81-88``.
 * ``readout``        — ``notorch/nn/gnn/agg.py:23-38``.
