@@ -73,6 +73,10 @@ long long nt_kernel_launch_count(void);
 /* Debug only: device buffer of >= 65001 uint64 (word 0 = counter, zeroed by the caller) into which CTA 0 of the fused
  * tensor-core kernel appends role/time records; NULL switches tracing off. Not part of the data path. */
 void nt_debug_set_trace_buffer(void* device_u64_buffer);
+/* Host-only (no CUDA call): the work decomposition nt_layer_backward_wgrad (CTA-pair kernel) would use for E edges, hidden size d
+ * and num_sms SMs. out12 = {m_units, n_tiles, n_tile, n_a, n_b, half_last, full_units, half_units, splits, splits_last,
+ * k_blocks_per_split, k_blocks_per_split_last}; a K-block is 32 edges. For tests of the split logic. */
+int nt_debug_wgrad_geometry(int64_t E, int64_t d, int num_sms, int64_t* out12);
 /* 1 if the current device is compute capability 10.x (tcgen05 available), else 0; <0 on error. */
 int nt_device_supported(void);
 

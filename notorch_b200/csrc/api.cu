@@ -69,6 +69,7 @@ size_t tma_wgrad_workspace_bytes(int64_t E, int64_t d);
 int tma_layer_wgrad(const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, float*, void*, size_t, int, cudaStream_t);
 // wgrad_pair.cu (K4b on a CTA pair)
 size_t pair_wgrad_workspace_bytes(int64_t E, int64_t d);
+void pair_wgrad_geometry(int64_t E, int64_t d, int sms, int64_t out[12]);
 int pair_layer_wgrad(const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, float*, void*, size_t, int, cudaStream_t);
 // wgrad_tc.cu
 int tc_bias_grad(const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, void*, size_t, cudaStream_t);
@@ -111,6 +112,12 @@ using namespace nt;
 extern "C" const char* nt_last_error_string(void) { return g_err; }
 extern "C" int nt_version(void) { return 100; }
 extern "C" long long nt_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int nt_debug_wgrad_geometry(int64_t E, int64_t d, int num_sms_, int64_t* out12) {
+  NT_CHECK_ARG(E >= 0 && E < INT32_MAX && d > 0 && d % 4 == 0 && d < (1 << 20) && num_sms_ > 0 && out12, "nt_debug_wgrad_geometry: bad arguments");
+  pair_wgrad_geometry(E, d, num_sms_, out12);
+  return NT_OK;
+}
 
 extern "C" void nt_debug_set_trace_buffer(void* device_u64_buffer) {
   tc_set_trace_buffer(device_u64_buffer);

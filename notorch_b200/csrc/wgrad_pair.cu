@@ -372,6 +372,14 @@ __global__ void __launch_bounds__(256) wgrad_pair_reduce(const float* __restrict
 
 }  // namespace wgp
 
+// host-only view of the work decomposition (no CUDA call): lets the CPU test suite check its invariants for any (E, d, #SMs)
+void pair_wgrad_geometry(int64_t E, int64_t d, int sms, int64_t out[12]) {
+  const wgp::Geometry g = wgp::make_geometry(E, (int)d, sms);
+  const int64_t v[12] = {g.m_units, g.n_tiles, g.n_tile, g.n_a, g.n_b, g.half_last, g.full_units, g.half_units, g.splits, g.splits_last,
+                         g.kb_per_split, g.kb_per_split_last};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
+}
+
 size_t pair_wgrad_workspace_bytes(int64_t E, int64_t d) {
   if (d % 4 != 0 || E <= 0) return 0;
   int sms = num_sms();

@@ -180,3 +180,37 @@ def test_synth_generator_statistics_and_contract():
     assert np.array_equal(again.edge_index, mols.edge_index)
     sh = [mols.shard(r, 4) for r in range(4)]
     assert sum(len(s) for s in sh) == 512 and sum(s.total_edges for s in sh) == mols.total_edges
+
+
+def test_wgrad_pair_geometry_invariants():
+    """Host-side work decomposition of the CTA-pair weight-gradient kernel (wgrad_pair.cu: make_geometry), no GPU needed: every unit
+    covers all K-blocks, the grid never exceeds the SM count unless there are more units than CTA pairs, the half-height unit is
+    used exactly when at most 128 feature rows (incl. the all-ones bias row) remain, and the two MMAs tile the N tile."""
+    import ctypes
+
+    from notorch_b200 import _lib
+
+    L = _lib.lib()
+    out = (ctypes.c_int64 * 12)()
+    for sms in (148, 132, 2):
+        for d in (4, 8, 64, 100, 128, 252, 256, 260, 300, 304, 320, 332, 384, 512, 576, 1024, 2048, 2348, 4096):
+            for E in (0, 1, 31, 32, 33, 1000, 205166, 819000):
+                assert L.nt_debug_wgrad_geometry(E, d, sms, out) == 0
+                m_units, n_tiles, n_tile, n_a, n_b, half, full_u, half_u, sf, sl, per, per_l = list(out)
+                kb_total = (E + 31) // 32
+                ones = 1 if d % 256 else 0
+                assert m_units == (d + 255) // 256 and n_tiles * n_tile >= d and n_tile % 64 == 0 and n_tile <= 320
+                assert n_a + n_b == n_tile and n_a % 64 == 0 and n_b % 64 == 0 and 0 < n_a <= 256 and 0 <= n_b <= 256
+                last_rows = d + ones - (m_units - 1) * 256
+                assert half == (1 if last_rows <= 128 else 0)
+                assert full_u == (m_units - half) * n_tiles and half_u == half * n_tiles
+                clusters = max(sms // 2, 1)
+                if full_u:
+                    assert sf >= 1 and per * sf >= kb_total and (kb_total == 0 or sf <= kb_total)
+                if half_u:
+                    assert sl >= 1 and per_l * sl >= kb_total and (kb_total == 0 or sl <= kb_total)
+                pairs = full_u * sf + half_u * sl
+                assert pairs >= full_u + half_u
+                if full_u + half_u <= clusters and kb_total >= clusters:
+                    assert pairs <= clusters, (sms, d, E, list(out))
+    assert L.nt_debug_wgrad_geometry(10, 6, 148, out) != 0  # d % 4 != 0 is not the tensor-core path
