@@ -66,17 +66,14 @@ enum nt_gemm_mode {
                          rel-to-max 2e-2 on embeddings, 5e-2 on gradients (tests/test_bf16_mode.py) */
 };
 
+/* Bumped whenever an entry point's argument list changes; the ctypes binding (notorch_b200/_lib.py) refuses a library whose
+ * nt_version() differs, so a stale .so can never be called with a newer signature table. */
+#define NT_ABI_VERSION 200
+
 const char* nt_last_error_string(void);
-int nt_version(void);
+int nt_version(void); /* = NT_ABI_VERSION of the build */
 /* Number of kernels this library has launched in this process so far (all threads). */
 long long nt_kernel_launch_count(void);
-/* Debug only: device buffer of >= 65001 uint64 (word 0 = counter, zeroed by the caller) into which CTA 0 of the fused
- * tensor-core kernel appends role/time records; NULL switches tracing off. Not part of the data path. */
-void nt_debug_set_trace_buffer(void* device_u64_buffer);
-/* Host-only (no CUDA call): the work decomposition nt_layer_backward_wgrad (CTA-pair kernel) would use for E edges, hidden size d
- * and num_sms SMs. out12 = {m_units, n_tiles, n_tile, n_a, n_b, half_last, full_units, half_units, splits, splits_last,
- * k_blocks_per_split, k_blocks_per_split_last}; a K-block is 32 edges. For tests of the split logic. */
-int nt_debug_wgrad_geometry(int64_t E, int64_t d, int num_sms, int64_t* out12);
 /* 1 if the current device is compute capability 10.x (tcgen05 available), else 0; <0 on error. */
 int nt_device_supported(void);
 

@@ -13,6 +13,8 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnotorch_b200.so")
 
+ABI_VERSION = 200  # = NT_ABI_VERSION of include/notorch_b200.h; a library reporting another value is refused
+
 # enums of include/notorch_b200.h
 NT_F32, NT_BF16 = 0, 1
 GEMM_TF32X3, GEMM_FP32, GEMM_TF32, GEMM_BF16 = 0, 1, 2, 3
@@ -77,18 +79,26 @@ def _load() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            # in-tree build (nvcc cross-compiles for sm_100a without a GPU); loud failure otherwise
-            from . import build as _build
+        # in-tree build (nvcc cross-compiles for sm_100a without a GPU). build() is a no-op while the digest of csrc/ + the headers
+        # matches the stamp written beside the objects, so an edited source never runs under a stale library.
+        from . import build as _build
 
-            try:
-                _build.build()
-            except Exception as exc:  # pragma: no cover - depends on the toolchain
+        try:
+            _build.build()
+        except Exception as exc:  # pragma: no cover - depends on the toolchain
+            if not os.path.exists(LIB_PATH):
                 raise RuntimeError(
                     f"notorch_b200: {LIB_PATH} is missing and could not be built ({exc}). "
                     "There is no CPU or PyTorch fallback; run `python -m notorch_b200.build`."
                 ) from exc
+            import warnings
+
+            warnings.warn(f"notorch_b200: {LIB_PATH} is older than its sources and could not be rebuilt ({exc}); loading it as is", stacklevel=3)
         lib = C.CDLL(LIB_PATH)
+        lib.nt_version.restype = C.c_int
+        if lib.nt_version() != ABI_VERSION:
+            raise RuntimeError(f"notorch_b200: {LIB_PATH} reports ABI version {lib.nt_version()}, this binding needs {ABI_VERSION}; "
+                               "rebuild with `python -m notorch_b200.build --force`")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError here = header / library mismatch
             fn.restype = res

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "../../include/notorch_b200_debug.h"
 
 namespace nt {
 
@@ -50,23 +51,14 @@ size_t simt_linear_wgrad_workspace_bytes(int64_t rows, int64_t n_out, int64_t k_
 int simt_linear_forward(const float*, const float*, const float*, int64_t, int64_t, int64_t, float*, cudaStream_t);
 int simt_linear_dgrad(const float*, const float*, int64_t, int64_t, int64_t, float*, cudaStream_t);
 int simt_linear_wgrad(const float*, const float*, int64_t, int64_t, int64_t, float*, float*, float*, cudaStream_t);
-// gemm_tc.cu
-void tc_set_trace_buffer(void* ptr);
-size_t tc_weight_image_bytes(int64_t d);
-int tc_weight_prepare(const float*, int64_t, int, void*, cudaStream_t);
-int tc_layer_forward(const float*, const float*, const int32_t*, const int32_t*, const void*, const float*, int64_t, int64_t, int, float, int, float,
-                     uint64_t, uint64_t, float*, float*, int, cudaStream_t);
-int tc_layer_dgrad(const float*, const void*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
-// gemm_pair.cu (second-generation K2 / K4a: CTA pairs, copy-engine gathers)
+// gemm_pair.cu (K2 / K4a / dense forward on CTA pairs)
 void pair_set_trace_buffer(void* ptr);
+size_t pair_weight_image_bytes(int64_t d);
 int pair_weight_prepare(const float*, int64_t, int, void*, int, cudaStream_t);
 int pair_layer_forward(const float*, const float*, const int32_t*, const int32_t*, const void*, const float*, int64_t, int64_t, int64_t, int, float, int,
                        float, uint64_t, uint64_t, float*, float*, int, cudaStream_t);
 int pair_layer_dgrad(const float*, const void*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
 int pair_dense_forward(const float*, const void*, const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, int, cudaStream_t);
-// wgrad_tma.cu
-size_t tma_wgrad_workspace_bytes(int64_t E, int64_t d);
-int tma_layer_wgrad(const float*, const float*, int64_t, int64_t, float, uint64_t, uint64_t, float*, float*, void*, size_t, int, cudaStream_t);
 // wgrad_pair.cu (K4b on a CTA pair)
 size_t pair_wgrad_workspace_bytes(int64_t E, int64_t d);
 void pair_wgrad_geometry(int64_t E, int64_t d, int sms, int64_t out[12]);
@@ -76,25 +68,6 @@ int tc_bias_grad(const float*, int64_t, int64_t, float, uint64_t, uint64_t, floa
 size_t tc_wgrad_workspace_bytes(int64_t E, int64_t d);
 int tc_layer_wgrad(const float*, const float*, const float*, const int32_t*, const int32_t*, int64_t, int64_t, int, float, float, uint64_t, uint64_t,
                    float*, float*, void*, size_t, int, cudaStream_t);
-
-// NOTORCH_B200_GEMM_V1=1 selects the first-generation single-CTA kernels of gemm_tc.cu (A/B timing only; the weight
-// image layouts differ, so the switch is process-wide and read once).
-static bool use_pair_kernels() {
-  static const bool v1 = getenv("NOTORCH_B200_GEMM_V1") != nullptr && atoi(getenv("NOTORCH_B200_GEMM_V1")) != 0;
-  return !v1;
-}
-
-// NOTORCH_B200_PAIR_DGRAD=0 routes K4a through the single-CTA kernel of gemm_tc.cu (timing experiments)
-static bool pair_dgrad_enabled() {
-  static const bool off = getenv("NOTORCH_B200_PAIR_DGRAD") != nullptr && atoi(getenv("NOTORCH_B200_PAIR_DGRAD")) == 0;
-  return !off && use_pair_kernels();
-}
-
-// NOTORCH_B200_WGRAD_V1=1 keeps K4b on the single-CTA kernel of wgrad_tma.cu (timing experiments)
-static bool pair_wgrad_enabled() {
-  static const bool v1 = getenv("NOTORCH_B200_WGRAD_V1") != nullptr && atoi(getenv("NOTORCH_B200_WGRAD_V1")) != 0;
-  return !v1 && use_pair_kernels();
-}
 
 // MMA passes per product: 3 = 3xTF32, 1 = single TF32 pass, 0 = bf16 operands (one kind::f16 pass)
 static int products_of(int gemm_mode) { return gemm_mode == NT_GEMM_TF32 ? 1 : gemm_mode == NT_GEMM_BF16 ? 0 : 3; }
@@ -110,7 +83,7 @@ static bool tc_shape_ok(int64_t d, const void* a, const void* b, const void* c, 
 using namespace nt;
 
 extern "C" const char* nt_last_error_string(void) { return g_err; }
-extern "C" int nt_version(void) { return 100; }
+extern "C" int nt_version(void) { return NT_ABI_VERSION; }
 extern "C" long long nt_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int nt_debug_wgrad_geometry(int64_t E, int64_t d, int num_sms_, int64_t* out12) {
@@ -119,10 +92,7 @@ extern "C" int nt_debug_wgrad_geometry(int64_t E, int64_t d, int num_sms_, int64
   return NT_OK;
 }
 
-extern "C" void nt_debug_set_trace_buffer(void* device_u64_buffer) {
-  tc_set_trace_buffer(device_u64_buffer);
-  pair_set_trace_buffer(device_u64_buffer);
-}
+extern "C" void nt_debug_set_trace_buffer(void* device_u64_buffer) { pair_set_trace_buffer(device_u64_buffer); }
 
 extern "C" int nt_device_supported(void) {
   int dev = 0;
@@ -138,16 +108,13 @@ extern "C" int nt_device_supported(void) {
   NT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, fn ": dropout_p must be in [0, 1)");                  \
   NT_CHECK_ARG(gemm_mode == NT_GEMM_TF32X3 || gemm_mode == NT_GEMM_FP32 || gemm_mode == NT_GEMM_TF32 || gemm_mode == NT_GEMM_BF16, fn ": bad gemm_mode")
 
-extern "C" size_t nt_weight_image_bytes(int64_t d) { return d > 0 ? tc_weight_image_bytes(d) : 0; }
+extern "C" size_t nt_weight_image_bytes(int64_t d) { return d > 0 ? pair_weight_image_bytes(d) : 0; }
 
 extern "C" int nt_weight_prepare(const void* W, int64_t d, int transpose, void* image, int dtype, nt_stream_t stream) {
   NT_CHECK_ARG(dtype == NT_F32 || dtype == NT_BF16, "nt_weight_prepare: bad dtype");
   NT_CHECK_ARG(W && image && d > 0 && d < (1 << 20), "nt_weight_prepare: bad arguments");
-  if (dtype == NT_BF16 && !use_pair_kernels()) { set_error("nt_weight_prepare: the bf16 image needs the CTA-pair kernels"); return NT_ERR_UNSUPPORTED; }
   if (!aligned16(image)) { set_error("nt_weight_prepare: image must be 16-byte aligned"); return NT_ERR_ALIGN; }
-  // forward image (transpose = 0): CTA-pair layout of gemm_pair.cu; dgrad image (transpose = 1): single-CTA layout of gemm_tc.cu
-  if (use_pair_kernels() && (!transpose || pair_dgrad_enabled() || dtype == NT_BF16)) return pair_weight_prepare(static_cast<const float*>(W), d, transpose != 0, image, dtype == NT_BF16, as_stream(stream));
-  return tc_weight_prepare(static_cast<const float*>(W), d, transpose != 0, image, as_stream(stream));
+  return pair_weight_prepare(static_cast<const float*>(W), d, transpose != 0, image, dtype == NT_BF16, as_stream(stream));
 }
 
 extern "C" int nt_layer_forward(const void* h, const void* n, const int32_t* src, const int32_t* rev, const void* W, const void* weight_image,
@@ -161,14 +128,9 @@ extern "C" int nt_layer_forward(const void* h, const void* n, const int32_t* src
   cudaStream_t st = as_stream(stream);
   if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, h, n, out, bias) && aligned16(m_out)) {
     NT_CHECK_ARG(weight_image, "nt_layer_forward: tensor-core path needs weight_image (nt_weight_prepare)");
-    if (use_pair_kernels())
-      return pair_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, weight_image, static_cast<const float*>(bias), E,
-                                V, d, act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), static_cast<float*>(m_out),
-                                products_of(gemm_mode), st);
-    if (gemm_mode == NT_GEMM_BF16) { set_error("nt_layer_forward: NT_GEMM_BF16 needs the CTA-pair kernels"); return NT_ERR_UNSUPPORTED; }
-    return tc_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, weight_image, static_cast<const float*>(bias), E, d,
-                            act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), static_cast<float*>(m_out),
-                            gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+    return pair_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, weight_image, static_cast<const float*>(bias), E,
+                              V, d, act, act_param, residual, dropout_p, seed, offset, static_cast<float*>(out), static_cast<float*>(m_out),
+                              products_of(gemm_mode), st);
   }
   if (m_out) { set_error("nt_layer_forward: m_out is only produced by the tensor-core path"); return NT_ERR_UNSUPPORTED; }
   return simt_layer_forward(static_cast<const float*>(h), static_cast<const float*>(n), src, rev, static_cast<const float*>(W),
@@ -181,7 +143,7 @@ extern "C" int nt_dense_forward(const void* x, const void* weight_image, const v
   NT_COMMON_LAYER_CHECKS("nt_dense_forward");
   if (R == 0) return NT_OK;
   NT_CHECK_ARG(x && out && weight_image, "nt_dense_forward: null pointer");
-  if (gemm_mode == NT_GEMM_FP32 || !use_pair_kernels() || !tc_shape_ok(d, x, out, bias, resid)) {
+  if (gemm_mode == NT_GEMM_FP32 || !tc_shape_ok(d, x, out, bias, resid)) {
     set_error("nt_dense_forward: needs the tensor-core path (gemm_mode tf32x3 / tf32, d %% 4 == 0, 16-byte aligned rows)");
     return NT_ERR_UNSUPPORTED;
   }
@@ -239,12 +201,8 @@ extern "C" int nt_layer_backward_dgrad(const void* g, const void* W, const void*
   cudaStream_t st = as_stream(stream);
   if (gemm_mode != NT_GEMM_FP32 && tc_shape_ok(d, g, g_m, nullptr, nullptr)) {
     NT_CHECK_ARG(weight_image, "nt_layer_backward_dgrad: tensor-core path needs weight_image (nt_weight_prepare, transpose=1)");
-    if (pair_dgrad_enabled())
-      return pair_layer_dgrad(static_cast<const float*>(g), weight_image, E, d, dropout_p, seed, offset, static_cast<float*>(g_m),
-                              products_of(gemm_mode), st);
-    if (gemm_mode == NT_GEMM_BF16) { set_error("nt_layer_backward_dgrad: NT_GEMM_BF16 needs the CTA-pair kernels"); return NT_ERR_UNSUPPORTED; }
-    return tc_layer_dgrad(static_cast<const float*>(g), weight_image, E, d, dropout_p, seed, offset, static_cast<float*>(g_m),
-                          gemm_mode == NT_GEMM_TF32 ? 1 : 3, st);
+    return pair_layer_dgrad(static_cast<const float*>(g), weight_image, E, d, dropout_p, seed, offset, static_cast<float*>(g_m),
+                            products_of(gemm_mode), st);
   }
   return simt_layer_dgrad(static_cast<const float*>(g), static_cast<const float*>(W), E, d, dropout_p, seed, offset, static_cast<float*>(g_m), st);
 }
@@ -253,8 +211,6 @@ extern "C" size_t nt_layer_backward_wgrad_workspace_bytes(int64_t E, int64_t d) 
   if (d <= 0) return 0;
   size_t simt = (size_t)simt_wgrad_splits(E, d) * (size_t)d * (size_t)(d + 1) * sizeof(float);
   size_t tcb = tc_wgrad_workspace_bytes(E, d);
-  size_t tmab = tma_wgrad_workspace_bytes(E, d);
-  if (tmab > tcb) tcb = tmab;
   size_t pairb = pair_wgrad_workspace_bytes(E, d);
   if (pairb > tcb) tcb = pairb;
   return (simt > tcb ? simt : tcb) + 256;
@@ -277,12 +233,12 @@ extern "C" int nt_layer_backward_wgrad(const void* g, const void* m, const void*
     set_error("nt_layer_backward_wgrad: workspace too small");
     return NT_ERR_WORKSPACE;
   }
-  if (m) {  // both operands dense: TMA-streamed tensor-core kernel
+  if (m) {  // both operands dense (m saved by K2): the CTA-pair kernel
     if (gemm_mode == NT_GEMM_FP32 || !tc_shape_ok(d, g, m, workspace, nullptr)) {
       set_error("nt_layer_backward_wgrad: a saved m needs the tensor-core path (d %% 4 == 0, 16-byte aligned)");
       return NT_ERR_UNSUPPORTED;
     }
-    auto wgrad = pair_wgrad_enabled() ? pair_layer_wgrad : tma_layer_wgrad;
+    auto wgrad = pair_layer_wgrad;
     int rc = wgrad(static_cast<const float*>(g), static_cast<const float*>(m), E, d, dropout_p, seed, offset, static_cast<float*>(gW),
                    static_cast<float*>(gb), workspace, workspace_bytes, wgrad_products_of(gemm_mode), st);
     if (rc != NT_ERR_UNSUPPORTED) return rc;

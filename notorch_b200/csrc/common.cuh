@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/notorch_b200.h"
 
 namespace nt {
@@ -41,6 +43,22 @@ static inline cudaStream_t as_stream(nt_stream_t s) { return reinterpret_cast<cu
 
 int num_sms();
 void count_launches(int n);
+
+// Function attributes (the > 48 KiB dynamic shared-memory opt-in) are PER DEVICE: a process-wide once-flag would leave every
+// GPU but the first without it. One bit per device ordinal; devices >= 64 simply repeat the (cheap) call.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> done{0};
+  template <typename F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+    e = f();
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+    return e;
+  }
+};
 
 // ---- activations (closed set compiled into every kernel; chemprop.py:17,24,37) -------------
 __device__ __forceinline__ float act_fwd(float x, int act, float p) {

@@ -310,11 +310,8 @@ extern "C" int nt_embedding_bag_sum(const void* table, int64_t num_types, const 
   const bool vec = d % 4 == 0 && aligned16(table) && aligned16(out);
   const size_t smem_need = (size_t)num_types * d * sizeof(float) + (size_t)EMBF_ROWS * bag * sizeof(int);
   if (vec && smem_need <= 200 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      NT_CUDA(cudaFuncSetAttribute(embedding_bag_sum_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
+    static PerDeviceOnce once;
+    NT_CUDA(once.run([] { return cudaFuncSetAttribute(embedding_bag_sum_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
     int sms = num_sms();
     if (sms <= 0) sms = 148;
     int per_sm = (int)((220 * 1024) / (smem_need + 1024));
@@ -366,11 +363,8 @@ extern "C" int nt_embedding_bag_backward(const void* g, const int64_t* idx, int6
   int64_t nblk = 0;
   EmbbPlan plan;
   if (aligned16(g) && embb_plan(n, bag, num_types, d, &plan)) {
-    static bool attr_v = false;
-    if (!attr_v) {
-      NT_CUDA(cudaFuncSetAttribute(embedding_bag_bwd_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, EMBB_SMEM_BUDGET));
-      attr_v = true;
-    }
+    static PerDeviceOnce once_v;
+    NT_CUDA(once_v.run([] { return cudaFuncSetAttribute(embedding_bag_bwd_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, EMBB_SMEM_BUDGET); }));
     nblk = plan.nblk;
     for (int64_t col0 = 0; col0 < d; col0 += plan.cols) {
       const int64_t w = col0 + plan.cols <= d ? plan.cols : d - col0;
@@ -384,11 +378,8 @@ extern "C" int nt_embedding_bag_backward(const void* g, const int64_t* idx, int6
     int64_t cols = (EMB_SMEM_BUDGET - idx_bytes) / (int64_t)(num_types * sizeof(float));
     if (cols < 1) { set_error("nt_embedding_bag_backward: vocabulary too large (%lld types)", (long long)num_types); return NT_ERR_UNSUPPORTED; }
     if (cols > d) cols = d;
-    static bool attr_set = false;
-    if (!attr_set) {
-      NT_CUDA(cudaFuncSetAttribute(embedding_bag_bwd_partial_s, cudaFuncAttributeMaxDynamicSharedMemorySize, EMB_SMEM_BUDGET));
-      attr_set = true;
-    }
+    static PerDeviceOnce once_s;
+    NT_CUDA(once_s.run([] { return cudaFuncSetAttribute(embedding_bag_bwd_partial_s, cudaFuncAttributeMaxDynamicSharedMemorySize, EMB_SMEM_BUDGET); }));
     nblk = cdiv(n, EMB_ROWS_PER_CTA);
     for (int64_t col0 = 0; col0 < d; col0 += cols) {
       const int64_t w = col0 + cols <= d ? cols : d - col0;

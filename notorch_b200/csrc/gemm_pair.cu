@@ -648,10 +648,9 @@ __global__ void __launch_bounds__(256) pair_weight_prepare_bf16_kernel(const flo
 
 template <int MODE, bool DROP, bool RELU, bool TRACE, bool BF16, bool SPLIT>
 static int launch_variant(const Params& p, cudaStream_t st) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(layer_gemm_pair<MODE, DROP, RELU, TRACE, BF16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  static PerDeviceOnce once;  // one per kernel instantiation
+  const cudaError_t attr_err = once.run([] {
+    return cudaFuncSetAttribute(layer_gemm_pair<MODE, DROP, RELU, TRACE, BF16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(layer_gemm_pair)");
   const int64_t pair_tiles = (p.E + 2 * TILE_M - 1) / (2 * TILE_M);
@@ -713,6 +712,8 @@ static void fill_dropout(Params& p, float drop_p, uint64_t seed, uint64_t offset
 }  // namespace pair
 
 void pair_set_trace_buffer(void* ptr) { pair::g_trace_buffer = static_cast<unsigned long long*>(ptr); }
+
+size_t pair_weight_image_bytes(int64_t d) { return 2 * pair::make_geometry((int)d).part_bytes; }
 
 int pair_weight_prepare(const float* W, int64_t d, int transpose, void* image, int bf16, cudaStream_t st) {
   pair::Geometry geo = pair::make_geometry((int)d);

@@ -414,11 +414,11 @@ int pair_layer_wgrad(const float* g, const float* m, int64_t E, int64_t d, float
   p.seed = seed;
   p.offset = offset;
 
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(wgp::wgrad_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgp::SMEM_BYTES);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(wgp::wgrad_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgp::SMEM_BYTES);
+  static PerDeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(wgp::wgrad_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgp::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgp::wgrad_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgp::SMEM_BYTES);
+    return e;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_pair_kernel)");
   cudaLaunchConfig_t cfg = {};

@@ -368,9 +368,8 @@ int tc_layer_wgrad(const float* g, const float* h, const float* n, const int32_t
   p.drop_thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
   p.seed = seed; p.offset = offset;
 
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(wg::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES); });
+  static PerDeviceOnce once;
+  const cudaError_t attr_err = once.run([] { return cudaFuncSetAttribute(wg::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES); });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_tc_kernel)");
   const int grid = p.geo.splits * p.geo.m_blocks * p.geo.n_tiles;
   wg::wgrad_tc_kernel<<<grid, wg::THREADS, wg::SMEM_BYTES, st>>>(p);

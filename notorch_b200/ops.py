@@ -8,7 +8,6 @@ K4 dgrad/wgrad, K5 gather backward (segmented sum by src), K6 layer backward epi
 from __future__ import annotations
 
 import os
-import threading
 from dataclasses import dataclass, field
 
 import torch
@@ -149,19 +148,12 @@ def _run(tag: str, fn, *args) -> None:
     _lib.check(rc, tag)
 
 
-_ws_lock = threading.Lock()
-_workspaces: dict[tuple[int, int], Tensor] = {}
-
-
 def _workspace(device: torch.device, nbytes: int, slot: int = 0) -> Tensor:
-    """Grow-only scratch buffer per (device, slot); kernels on one stream serialise their use of it."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
-    with _ws_lock:
-        ws = _workspaces.get(key)
-        if ws is None or ws.numel() < nbytes:
-            ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-            _workspaces[key] = ws
-        return ws
+    """Scratch bytes for ONE kernel call, drawn from the caching allocator on the calling stream: two streams or threads running
+    backward on one device never share a buffer (a process-wide scratch tensor would let their split-K partials overwrite each
+    other), and after warm-up the allocation is a free-list hit. ``slot`` is kept for call-site readability only."""
+    del slot
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -284,6 +276,9 @@ class GraphCSR:
     by_src: SegmentCSR  # K5: outgoing edges of each atom (keys32 = src)
     by_rev: SegmentCSR  # K6: inverse map of the (arbitrary) gather index rev (keys32 = rev)
     key: tuple = field(default_factory=tuple)
+    # the index tensors the bundle was built from: holding them keeps their storage alive, so the (address, shape, version) key
+    # above can never match a NEW tensor that the caching allocator placed at a recycled address
+    source: tuple = field(default_factory=tuple, repr=False)
 
     @property
     def src(self) -> Tensor:
@@ -347,7 +342,7 @@ def graph_csr(G, num_nodes: int | None = None) -> GraphCSR:
     if cached is not None and cached.key == key:
         return cached
     csr = build_graph_csr(G.edge_index, G.rev_index, V)
-    csr.key = key
+    csr.key, csr.source = key, (G.edge_index, G.rev_index)
     try:
         G._nt_csr = csr
     except AttributeError:  # pragma: no cover - slotted foreign object
@@ -365,7 +360,7 @@ def graph_csr_from_tensors(edge_index: Tensor, rev_index: Tensor, num_nodes: int
         if k == key:
             return c
     csr = build_graph_csr(edge_index, rev_index, num_nodes)
-    csr.key = key
+    csr.key, csr.source = key, (edge_index, rev_index)  # the entry owns its key tensors: their addresses cannot be recycled while it lives
     _layer_csr_cache.insert(0, (key, csr))
     del _layer_csr_cache[4:]
     return csr
@@ -386,7 +381,7 @@ def segment_csr_for(G, attr: str, num_segments: int) -> SegmentCSR:
     if hit is not None and hit[0] == key:
         return hit[1]
     csr = build_segment_csr(t, num_segments, attr)
-    cache[attr] = (key, csr)
+    cache[attr] = (key, csr, t)  # `t` is kept so that its address cannot be handed to another index tensor while the entry lives
     return csr
 
 

@@ -16,8 +16,8 @@ from oracle import reference_loader
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_symbols() -> set[str]:
-    text = open(os.path.join(ROOT, "include", "notorch_b200.h")).read()
+def _header_symbols(name: str = "notorch_b200.h") -> set[str]:
+    text = open(os.path.join(ROOT, "include", name)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return set(re.findall(r"\b(nt_[a-z0-9_]+)\s*\(", text))
 
@@ -28,10 +28,14 @@ def test_library_exports_every_header_symbol():
     lib = _lib.lib()
     declared = _header_symbols()
     assert declared, "no symbols parsed from the header"
-    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
-    for name in declared:
+    assert not any(n.startswith("nt_debug_") for n in declared), "debug entry points belong in notorch_b200_debug.h"
+    debug = _header_symbols("notorch_b200_debug.h")
+    assert debug and all(n.startswith("nt_debug_") for n in debug)
+    assert declared | debug == set(_lib.SIGNATURES), ((declared | debug) ^ set(_lib.SIGNATURES))
+    for name in declared | debug:
         assert hasattr(lib, name), name
-    assert lib.nt_version() >= 100
+    header = open(os.path.join(ROOT, "include", "notorch_b200.h")).read()
+    assert int(re.search(r"#define NT_ABI_VERSION (\d+)", header).group(1)) == _lib.ABI_VERSION == lib.nt_version()
 
 
 def test_argument_errors_are_status_codes_not_crashes():

@@ -43,7 +43,44 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         H.square().mean().backward()
         local = flat.flat.clone()
         flat.all_reduce_mean()
-        torch.save({"local": local, "reduced": flat.flat.clone(), "views_ok": all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in flat.params)},
+        reduced = flat.flat.clone()
+
+        # bucketed + overlapped form (what bench.py uses for N > 1): one bucket per parameter group, each all-reduce issued from the
+        # post-accumulate-grad hooks as soon as the bucket is complete, joined by finish(); same numbers as the single collective
+        torch.manual_seed(0)
+        model2 = O.CpuPort(hidden_dim=d, depth=2)
+        ps = list(model2.parameters())
+        flat2 = FlatGradients([ps[:2], ps[2:]], overlap=True)
+        assert len(flat2.buckets) == 2 and flat2.slices[0][1] == flat2.slices[1][0]
+        for _ in range(2):  # two steps: the per-step hook state resets in finish()
+            flat2.zero()
+            H2, _, _ = model2(xv, xe, torch.from_numpy(c["edge_index"]), torch.from_numpy(c["rev_index"]),
+                              torch.from_numpy(c["batch_node_index"]), len(mine))
+            H2.square().mean().backward()
+            flat2.finish()
+        overlapped = flat2.flat.clone()
+
+        # the default zero_grad() (set_to_none=True) detaches the views: the exchange must refuse, rebind() must repair
+        for p in ps:
+            p.grad = None
+        H2, _, _ = model2(xv, xe, torch.from_numpy(c["edge_index"]), torch.from_numpy(c["rev_index"]), torch.from_numpy(c["batch_node_index"]), len(mine))
+        try:
+            H2.square().mean().backward()  # the bucket hook refuses before anything is exchanged
+            refused = False
+        except RuntimeError as exc:
+            refused = "no longer aliases" in str(exc)
+        flat2.reset()
+        for p in ps:
+            p.grad = None
+        H2, _, _ = model2(xv, xe, torch.from_numpy(c["edge_index"]), torch.from_numpy(c["rev_index"]), torch.from_numpy(c["batch_node_index"]), len(mine))
+        for h in flat2._hooks:
+            h.remove()
+        H2.square().mean().backward()
+        moved = flat2.rebind()
+        flat2.overlap = False
+        flat2.all_reduce_mean()
+        torch.save({"local": local, "reduced": reduced, "overlapped": overlapped, "rebound": flat2.flat.clone(), "refused": refused, "moved": moved,
+                    "views_ok": all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in flat.params)},
                    os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -58,6 +95,9 @@ def test_flat_gradient_allreduce_world2(tmp_path):
     for i in range(world):
         assert r[i]["views_ok"]
         assert torch.allclose(r[i]["reduced"], want, rtol=0, atol=1e-7)
+        assert torch.allclose(r[i]["overlapped"], want, rtol=0, atol=1e-7)
+        assert r[i]["refused"] and r[i]["moved"] == 4
+        assert torch.allclose(r[i]["rebound"], want, rtol=0, atol=1e-7)
     assert not torch.equal(r[0]["local"], r[1]["local"])  # ranks really saw different molecules
 
 
