@@ -267,6 +267,24 @@ int nt_embedding_bag_backward(const void* g, const int64_t* idx, int64_t n, int6
                               void* g_table, void* workspace, size_t workspace_bytes, int dtype, nt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * GraphEmbedding FUSED into the edge initialisation (row N1 as SURVEY.md §8f words it) — replaces
+ * notorch/nn/gnn/embed.py:20-24 followed by notorch/nn/gnn/chemprop.py:83 in one kernel:
+ *   h0[e,:] = (sum_j table_v[node_types[src[e], j], :]) + (sum_k table_e[edge_types[e, k], :])
+ * node_types int64 [V, bag_v], edge_types int64 [E, bag_e], src int32 [E]; both tables are staged in shared memory, x_v / x_e
+ * are never written. Bit-identical to nt_embedding_bag_sum (twice) + nt_gather_add. *status bit 0: a type id or src out of range.
+ * Backward: ONE pass over g = dL/dh0 [E, d] yields both table gradients (per-thread column ownership over private
+ * shared-memory tables, fixed-order sums: deterministic, no atomics). NT_ERR_UNSUPPORTED when d % 4 != 0 or the combined
+ * vocabulary does not fit shared memory (callers then use the unfused entry points above). bag_v + bag_e <= 32.
+ * ---------------------------------------------------------------------------------------------- */
+int nt_embed_edge_init(const void* table_v, int64_t num_node_types, const void* table_e, int64_t num_edge_types,
+                       const int64_t* node_types, int64_t bag_v, const int64_t* edge_types, int64_t bag_e, const int32_t* src,
+                       int64_t E, int64_t V, int64_t d, void* h0, int32_t* status, int dtype, nt_stream_t stream);
+size_t nt_embed_edge_init_backward_workspace_bytes(int64_t E, int64_t num_node_types, int64_t num_edge_types, int64_t d);
+int nt_embed_edge_init_backward(const void* g, const int64_t* node_types, int64_t bag_v, const int64_t* edge_types, int64_t bag_e,
+                                const int32_t* src, int64_t E, int64_t V, int64_t num_node_types, int64_t num_edge_types, int64_t d,
+                                void* g_table_v, void* g_table_e, void* workspace, size_t workspace_bytes, int dtype, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Remaining read-outs of notorch/nn/gnn/agg.py (row N2). Segments are given as a CSR (rowptr, perm; perm NULL =
  * contiguous rows); every loop is sequential in ascending row order (deterministic).
  *  nt_seg_max            agg.Max (agg.py:45, torch_scatter.scatter_max): out[s,c] = max, arg = first row attaining it

@@ -57,6 +57,9 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "nt_embedding_bag_sum": (_int, [_vp, _i64, _i64p, _i64, _i64, _i64, _vp, _i32p, _int, _vp]),
     "nt_embedding_bag_backward_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "nt_embedding_bag_backward": (_int, [_vp, _i64p, _i64, _i64, _i64, _i64, _vp, _vp, _sz, _int, _vp]),
+    "nt_embed_edge_init": (_int, [_vp, _i64, _vp, _i64, _i64p, _i64, _i64p, _i64, _i32p, _i64, _i64, _i64, _vp, _i32p, _int, _vp]),
+    "nt_embed_edge_init_backward_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
+    "nt_embed_edge_init_backward": (_int, [_vp, _i64p, _i64, _i64p, _i64, _i32p, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _int, _vp]),
     "nt_seg_max": (_int, [_vp, _i64, _i32p, _i32p, _i64, _vp, _i32p, _int, _vp]),
     "nt_seg_extreme": (_int, [_vp, _i64, _i32p, _i32p, _i64, _int, _f32, _int, _vp, _i32p, _int, _vp]),
     "nt_seg_max_backward": (_int, [_vp, _i32p, _i32p, _i64, _i64, _vp, _int, _vp]),

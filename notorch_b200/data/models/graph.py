@@ -25,6 +25,48 @@ from torch import Tensor
 from ...utils.utils import UpdateMixin
 
 
+class PendingFeats:
+    """A float feature matrix that has been *described* but not computed yet.
+
+    ``GraphEmbedding`` stores one of these in ``node_feats`` / ``edge_feats`` so that the message-passing block can fuse the
+    embedding-table look-ups into its edge initialisation (``nt_embed_edge_init``: neither ``[V, d]`` nor ``[E, d]`` is ever
+    written). Anything else that READS ``G.node_feats`` / ``G.edge_feats`` gets a real tensor: the attribute access computes it
+    through the unfused kernel (same bits, autograd-connected), caches it here and returns it — so the graph stays a drop-in for
+    consumers that know nothing about this class. ``Graph.peek(name)`` returns the placeholder without computing."""
+
+    __slots__ = ("_compute", "shape", "dtype", "device", "origin", "_value")
+
+    def __init__(self, compute, shape: tuple[int, int], dtype: torch.dtype, device: torch.device, origin):
+        self._compute, self.shape, self.dtype, self.device, self.origin = compute, tuple(shape), dtype, device, origin
+        self._value: Tensor | None = None
+
+    def __len__(self) -> int:
+        return self.shape[0]
+
+    @property
+    def materialized(self) -> bool:
+        return self._value is not None
+
+    def materialize(self) -> Tensor:
+        if self._value is None:
+            self._value = self._compute()
+        return self._value
+
+
+def _feats_property(name: str) -> property:
+    def getter(self):
+        v = self.__dict__[name]
+        if isinstance(v, PendingFeats):
+            v = v.materialize()
+            self.__dict__[name] = v
+        return v
+
+    def setter(self, value):
+        self.__dict__[name] = value
+
+    return property(getter, setter)
+
+
 @dataclass(repr=False, eq=False)
 class Graph(UpdateMixin):
     node_feats: Tensor  # [V, t_v] integer types before embedding, [V, d] float after
@@ -37,13 +79,17 @@ class Graph(UpdateMixin):
         self._device = device_
         self.to(device_)
 
+    def peek(self, name: str):
+        """``node_feats`` / ``edge_feats`` WITHOUT materialising a :class:`PendingFeats` placeholder."""
+        return self.__dict__[name]
+
     @property
     def num_nodes(self) -> int:
-        return len(self.node_feats)
+        return len(self.peek("node_feats"))
 
     @property
     def num_edges(self) -> int:
-        return len(self.edge_feats)
+        return len(self.peek("edge_feats"))
 
     @property
     def device(self):
@@ -51,27 +97,41 @@ class Graph(UpdateMixin):
 
     _TENSOR_FIELDS = ("node_feats", "edge_feats", "edge_index", "rev_index")
 
-    def to(self, device) -> Self:
+    _CACHE_ATTRS = ("_nt_csr", "_nt_seg_csr", "_nt_mol_ptr", "_nt_mol_csr")
+
+    def to(self, device, non_blocking: bool = False) -> Self:
+        """Move the tensors (graph.py:45-53 / :229-239 of the reference) AND whatever the kernels cached on this object: the
+        int32 CSR bundle, the molecule row pointers and the read-out CSR follow the graph to another CUDA device (small int32
+        copies instead of a rebuild) and survive a no-op move untouched, so ``transfer_batch_to_device`` of a Lightning loop
+        does not throw the per-batch preprocessing away. Moving to the CPU drops them (they only serve the CUDA kernels)."""
         self._device = device
-        for name in self._TENSOR_FIELDS:
-            setattr(self, name, getattr(self, name).to(device))
-        # caches hold tensors of the old device: drop them, they are rebuilt lazily
-        self.__dict__.pop("_nt_csr", None)
-        self.__dict__.pop("_nt_seg_csr", None)
-        self.__dict__.pop("_nt_mol_ptr", None)
-        self.__dict__.pop("_nt_mol_csr", None)
+        before = {name: getattr(self, name) for name in self._TENSOR_FIELDS}
+        for name, t in before.items():
+            setattr(self, name, t.to(device, non_blocking=non_blocking))
+        if all(getattr(self, name) is t for name, t in before.items()):
+            return self  # nothing moved: every cache key is still valid
+        caches = {a: self.__dict__.pop(a) for a in self._CACHE_ATTRS if a in self.__dict__}
+        if caches and self.edge_index.is_cuda:
+            from ... import ops
+
+            ops.carry_graph_caches(self, caches, before)
         return self
 
     def _field_lines(self) -> list[str]:
         return [
-            f"node_feats: Tensor(shape={tuple(self.node_feats.shape)})",
-            f"edge_feats: Tensor(shape={tuple(self.edge_feats.shape)})",
+            f"node_feats: Tensor(shape={tuple(self.peek('node_feats').shape)})",
+            f"edge_feats: Tensor(shape={tuple(self.peek('edge_feats').shape)})",
             f"device={self._device}",
         ]
 
     def __repr__(self) -> str:
         body = "\n".join("  " + line for line in self._field_lines())
         return f"{type(self).__name__}(\n{body}\n)"
+
+
+# installed after @dataclass has read the field list (a property in the class body would be taken for a default value)
+Graph.node_feats = _feats_property("node_feats")
+Graph.edge_feats = _feats_property("edge_feats")
 
 
 @dataclass(repr=False, eq=False, kw_only=True)

@@ -16,7 +16,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from ... import ops
-from ...data.models.graph import BatchedGraph, Graph
+from ...data.models.graph import BatchedGraph, Graph, PendingFeats
 from ...types import Reduction
 from ..residual import Residual
 
@@ -68,10 +68,17 @@ class ChempropBlock(nn.Module):
 
     def forward(self, G: Graph | BatchedGraph):
         csr = ops.graph_csr(G)  # int32 CSR bundle, built once per batch and cached on the graph object
-        h = ops.edge_init(G.node_feats, G.edge_feats, csr)  # K0
+        xv, xe = ops.peek_feats(G, "node_feats"), ops.peek_feats(G, "edge_feats")
+        if (isinstance(xv, PendingFeats) and isinstance(xe, PendingFeats) and xv.origin[0] is xe.origin[0]
+                and not (xv.materialized or xe.materialized)):
+            # the features are a GraphEmbedding that has not been computed: table look-ups + K0 in one kernel (row N1)
+            h = ops.embed_edge_init(xv.origin[1], xe.origin[1], xv.origin[2], xe.origin[2], csr)
+        else:
+            xv = G.node_feats
+            h = ops.edge_init(xv, G.edge_feats, csr)  # K0
         for entry in self.layers:
             fused_residual = isinstance(entry, Residual)
             layer = entry.module if fused_residual else entry
-            h = layer(h, G.node_feats, G.edge_index, G.rev_index, _residual=fused_residual, _csr=csr)
+            h = layer(h, xv, G.edge_index, G.rev_index, _residual=fused_residual, _csr=csr)  # xv: only its length is used
         atoms = ops.edge_to_atom(h, csr, self.reduce)  # K1 without activation (chemprop.py:86)
         return G.update(node_feats=atoms, edge_feats=h)

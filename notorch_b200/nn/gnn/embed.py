@@ -12,7 +12,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from ... import _lib, ops
-from ...data.models.graph import Graph
+from ...data.models.graph import Graph, PendingFeats
 
 # notorch/transforms/conf.py:35-44 (needs RDKit to import, so restated): 45 atom types, 13 bond types
 DEFAULT_NUM_ATOM_TYPES = 45
@@ -61,8 +61,17 @@ class GraphEmbedding(nn.Module):
         self.edge = nn.EmbeddingBag(num_edge_types, hidden_dim, mode="sum")
 
     def forward(self, G: Graph) -> Graph:
-        return G.update(node_feats=_EmbeddingBagSum.apply(self.node.weight, G.node_feats),
-                        edge_feats=_EmbeddingBagSum.apply(self.edge.weight, G.edge_feats))
+        node_types, edge_types = G.node_feats, G.edge_feats
+        wv, we = self.node.weight, self.edge.weight
+        if isinstance(G, Graph) and ops.embed_edge_init_supported(wv, we, node_types, edge_types):
+            # deferred: ChempropBlock fuses both look-ups into its edge initialisation (nt_embed_edge_init) and never needs
+            # x_v / x_e; any other reader of G.node_feats / G.edge_feats triggers the unfused kernel below (same bits)
+            call = object()  # the two placeholders of ONE forward call recognise each other by this token
+            d, dev = wv.shape[1], wv.device
+            return G.update(
+                node_feats=PendingFeats(lambda: _EmbeddingBagSum.apply(wv, node_types), (node_types.shape[0], d), wv.dtype, dev, (call, wv, node_types)),
+                edge_feats=PendingFeats(lambda: _EmbeddingBagSum.apply(we, edge_types), (edge_types.shape[0], d), we.dtype, dev, (call, we, edge_types)))
+        return G.update(node_feats=_EmbeddingBagSum.apply(wv, node_types), edge_feats=_EmbeddingBagSum.apply(we, edge_types))
 
     @property
     def num_node_types(self) -> int:

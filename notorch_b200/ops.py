@@ -19,7 +19,8 @@ from ._lib import GEMM_BF16, GEMM_FP32, GEMM_TF32, GEMM_TF32X3, NT_BF16, NT_F32
 __all__ = [
     "GraphCSR", "SegmentCSR", "build_segment_csr", "graph_csr", "segment_csr_for", "seg_reduce", "gather_add",
     "edge_init", "edge_to_atom", "readout", "layer", "set_gemm_mode", "get_gemm_mode", "collate_packed",
-    "dropout_mask", "set_index_validation", "KernelTimer",
+    "dropout_mask", "set_index_validation", "KernelTimer", "embed_edge_init", "embed_edge_init_supported", "carry_graph_caches",
+    "set_save_messages",
 ]
 
 ACT_CODES = {
@@ -37,6 +38,18 @@ _gemm_mode = _GEMM_MODES[os.environ.get("NOTORCH_B200_GEMM", "tf32x3").lower()]
 _validate_mode = os.environ.get("NOTORCH_B200_VALIDATE", "sync").lower()  # "sync" | "deferred" | "off"
 _parallel_csr = os.environ.get("NOTORCH_B200_PARALLEL_CSR", "1") != "0"  # by_src / by_dst / by_rev built on three streams
 _fuse_k5_k6 = os.environ.get("NOTORCH_B200_FUSE_K5K6", "1") != "0"  # backward epilogue sums the outgoing-edge gradients itself (no K5 launch)
+
+
+_save_messages = os.environ.get("NOTORCH_B200_SAVE_M", "1") != "0"
+
+
+def set_save_messages(flag: bool) -> None:
+    """``True`` (default): K2 also writes the message tensor ``m_l`` and the weight gradient streams it as dense tiles (fastest).
+    ``False``: nothing but ``h_l`` and the small ``n_l`` [V, d] is kept per depth — the weight gradient re-gathers
+    ``m = n[src] - act(h)[rev]`` itself (``wgrad_tc.cu``), halving the activation memory saved for backward (SURVEY.md §7:
+    17 GB at BASELINE configs[2]) for a slower K4b."""
+    global _save_messages
+    _save_messages = bool(flag)
 
 
 def set_gemm_mode(mode: str) -> None:
@@ -172,6 +185,10 @@ class SegmentCSR:
     status: Tensor | None = None  # [1] int32 device flag, bit 0 = key out of range
     ell: Tensor | None = None  # [S, 4] int32: first four item ids of every segment (-1 padded), see nt_csr_to_ell
 
+    def to(self, device, non_blocking: bool = False) -> "SegmentCSR":
+        mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
+        return SegmentCSR(mv(self.rowptr), mv(self.perm), mv(self.keys32), self.num_segments, mv(self.status), mv(self.ell))
+
 
 def _ell_of(csr: "SegmentCSR") -> Tensor | None:
     """ELL copy of a permuted CSR (built once per batch, cached on the CSR object); contiguous segments keep the plain kernel."""
@@ -280,6 +297,11 @@ class GraphCSR:
     # above can never match a NEW tensor that the caching allocator placed at a recycled address
     source: tuple = field(default_factory=tuple, repr=False)
 
+    def to(self, device, non_blocking: bool = False) -> "GraphCSR":
+        """The bundle on another device (int32 copies; nothing is rebuilt). ``key`` / ``source`` are set by the caller."""
+        return GraphCSR(self.V, self.E, self.by_dst.to(device, non_blocking), self.by_src.to(device, non_blocking),
+                        self.by_rev.to(device, non_blocking))
+
     @property
     def src(self) -> Tensor:
         return self.by_src.keys32
@@ -333,10 +355,16 @@ def build_graph_csr(edge_index: Tensor, rev_index: Tensor, num_nodes: int) -> Gr
     return GraphCSR(num_nodes, E, by_dst, by_src, by_rev)
 
 
+def peek_feats(G, name: str):
+    """``G.node_feats`` / ``G.edge_feats`` without computing a pending embedding (``Graph.peek``); plain attribute on foreign graphs."""
+    peek = getattr(G, "peek", None)
+    return peek(name) if peek is not None else getattr(G, name)
+
+
 def graph_csr(G, num_nodes: int | None = None) -> GraphCSR:
     """CSR bundle of a ``Graph``/``BatchedGraph``, cached on the object (``Graph.update`` makes
     shallow copies, so the cache rides along GraphEmbedding -> ChempropBlock -> Aggregation)."""
-    V = len(G.node_feats) if num_nodes is None else num_nodes
+    V = len(peek_feats(G, "node_feats")) if num_nodes is None else num_nodes
     key = (_tensor_key(G.edge_index), _tensor_key(G.rev_index), V)
     cached = getattr(G, "_nt_csr", None)
     if cached is not None and cached.key == key:
@@ -348,6 +376,33 @@ def graph_csr(G, num_nodes: int | None = None) -> GraphCSR:
     except AttributeError:  # pragma: no cover - slotted foreign object
         pass
     return csr
+
+
+def carry_graph_caches(G, caches: dict, before: dict) -> None:
+    """``Graph.to(cuda device)``: re-attach the per-batch preprocessing that was cached on ``G`` (CSR bundle, molecule row
+    pointers, read-out CSR) after its index tensors moved — copied to the new device when the device changed, re-keyed to the
+    new tensors either way. ``before`` maps field name -> the tensor it held before the move."""
+    dev = G.edge_index.device
+    csr = caches.get("_nt_csr")
+    if csr is not None and csr.key == (_tensor_key(before["edge_index"]), _tensor_key(before["rev_index"]), csr.V):
+        moved = csr if csr.by_dst.rowptr.device == dev else csr.to(dev, non_blocking=True)
+        if moved is not csr and getattr(csr, "_atom_csr", None) is not None:
+            pass  # the atom neighbour lists are derived lazily from the moved bundle
+        moved.key = (_tensor_key(G.edge_index), _tensor_key(G.rev_index), csr.V)
+        moved.source = (G.edge_index, G.rev_index)
+        G._nt_csr = moved
+    ptr = caches.get("_nt_mol_ptr")
+    if ptr is not None:
+        G._nt_mol_ptr = ptr.to(dev, non_blocking=True)
+    seg = caches.get("_nt_seg_csr")
+    if seg:
+        kept = {}
+        for attr, (key, c, t_old) in seg.items():
+            if attr in before and before[attr] is t_old:
+                t_new = getattr(G, attr)
+                kept[attr] = ((_tensor_key(t_new), key[1]), c if c.rowptr.device == dev else c.to(dev, non_blocking=True), t_new)
+        if kept:
+            G._nt_seg_csr = kept
 
 
 _layer_csr_cache: list[tuple[tuple, GraphCSR]] = []
@@ -508,6 +563,66 @@ class _GatherAdd(torch.autograd.Function):
         return (g if ctx.needs_input_grad[0] else None), gx, None
 
 
+class _EmbedEdgeInit(torch.autograd.Function):
+    """GraphEmbedding fused into K0: h0 = bag(Tv, node_types)[src] + bag(Te, edge_types)
+    (embed.py:20-24 + chemprop.py:83) in one kernel, both tables in shared memory; backward = one pass over g_{h0}."""
+
+    @staticmethod
+    def forward(ctx, table_v: Tensor, table_e: Tensor, node_types: Tensor, edge_types: Tensor, csr: "GraphCSR"):
+        table_v, table_e = _require_float(table_v, "node embedding table"), _require_float(table_e, "edge embedding table")
+        node_types = _require(node_types, "node type indices", torch.int64, 2)
+        edge_types = _require(edge_types, "edge type indices", torch.int64, 2)
+        V, E, d = node_types.shape[0], edge_types.shape[0], table_v.shape[1]
+        if table_e.shape[1] != d or E != csr.E or V != csr.V:
+            raise RuntimeError(f"notorch_b200: fused embedding shape mismatch: tables {tuple(table_v.shape)} / {tuple(table_e.shape)}, "
+                               f"ids {tuple(node_types.shape)} / {tuple(edge_types.shape)}, graph V={csr.V} E={csr.E}")
+        with torch.cuda.device(table_v.device):
+            h0 = torch.empty((E, d), dtype=table_v.dtype, device=table_v.device)
+            status = torch.zeros(1, dtype=torch.int32, device=table_v.device)
+            _run("K0e:nt_embed_edge_init", _lib.lib().nt_embed_edge_init, _p(table_v), table_v.shape[0], _p(table_e), table_e.shape[0],
+                 _p(node_types), node_types.shape[1], _p(edge_types), edge_types.shape[1], _p(csr.src), E, V, d, _p(h0), _p(status), NT_F32,
+                 _stream())
+        _check_status(status, "GraphEmbedding type indices")
+        ctx.save_for_backward(node_types, edge_types)
+        ctx.csr, ctx.shapes = csr, (table_v.shape, table_e.shape)
+        return h0
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        node_types, edge_types = ctx.saved_tensors
+        (Tv, d), (Te, _) = ctx.shapes
+        csr = ctx.csr
+        g = g.contiguous()
+        L = _lib.lib()
+        with torch.cuda.device(g.device):
+            gv = torch.empty((Tv, d), dtype=g.dtype, device=g.device)
+            ge = torch.empty((Te, d), dtype=g.dtype, device=g.device)
+            ws = _workspace(g.device, L.nt_embed_edge_init_backward_workspace_bytes(csr.E, Tv, Te, d))
+            _run("K0ebwd:nt_embed_edge_init_backward", L.nt_embed_edge_init_backward, _p(g), _p(node_types), node_types.shape[1], _p(edge_types),
+                 edge_types.shape[1], _p(csr.src), csr.E, csr.V, Tv, Te, d, _p(gv), _p(ge), _p(ws), ws.numel(), NT_F32, _stream())
+        return gv, ge, None, None, None
+
+
+_fuse_embedding = os.environ.get("NOTORCH_B200_FUSE_EMBED", "1") != "0"
+
+
+def embed_edge_init_supported(table_v: Tensor, table_e: Tensor, node_types: Tensor, edge_types: Tensor) -> bool:
+    """Whether ``nt_embed_edge_init`` (+ backward) takes this problem; otherwise the caller materialises x_v / x_e and runs K0."""
+    if not _fuse_embedding or not (table_v.is_cuda and table_v.dtype == torch.float32 and table_e.dtype == torch.float32):
+        return False
+    d, T = table_v.shape[1], table_v.shape[0] + table_e.shape[0]
+    if d % 4 != 0 or table_e.shape[1] != d or node_types.dim() != 2 or edge_types.dim() != 2:
+        return False
+    if node_types.shape[1] + edge_types.shape[1] > 32 or edge_types.shape[0] == 0:
+        return False
+    return T * 16 + 128 * 32 * 4 <= 200 * 1024 and _lib.lib().nt_embed_edge_init_backward_workspace_bytes(max(edge_types.shape[0], 1), table_v.shape[0],
+                                                                                                         table_e.shape[0], d) > 0
+
+
+def embed_edge_init(table_v: Tensor, table_e: Tensor, node_types: Tensor, edge_types: Tensor, csr: "GraphCSR") -> Tensor:
+    return _EmbedEdgeInit.apply(table_v, table_e, node_types, edge_types, csr)
+
+
 _dropout_calls = 0
 
 
@@ -590,7 +705,7 @@ class _Layer(torch.autograd.Function):
         if b is not None:
             b = _require(b, "bias", torch.float32, 1)
         # tensor-core path: K2 also writes the message tensor m, which K4b then streams as dense tiles
-        save_m = mode != GEMM_FP32 and d % 4 == 0 and (ctx.needs_input_grad[1] or (b is not None and ctx.needs_input_grad[2]))
+        save_m = _save_messages and mode != GEMM_FP32 and d % 4 == 0 and (ctx.needs_input_grad[1] or (b is not None and ctx.needs_input_grad[2]))
         out, m, n, arg = _layer_forward_raw(h, W, b, csr, act, act_param, mean, residual, p, seed, offset, mode, save_m, extreme)
         ctx.save_for_backward(h, m if save_m else n, W, arg)
         ctx.csr, ctx.cfg, ctx.has_bias, ctx.has_m = csr, (act, act_param, mean, residual, p, seed, offset, mode), b is not None, save_m

@@ -86,7 +86,9 @@ def test_graph_update_is_shallow_copy_and_carries_cache():
     assert G.node_feats.sum() == 0 and G2.node_feats.sum() == 6 and len(G2) == 1
     assert G.update(in_place=True, node_feats=G2.node_feats) is G
     G.to("cpu")
-    assert "_nt_csr" not in G.__dict__  # caches are device-bound
+    assert G._nt_csr == "cache"  # a move that moves nothing keeps the per-batch preprocessing (N4: Lightning's transfer_batch_to_device)
+    G.to(torch.device("meta"))
+    assert "_nt_csr" not in G.__dict__  # off the GPU the caches are dropped: they only serve the CUDA kernels
     G3 = BatchedGraph(torch.zeros(3, 2), torch.zeros(0, 2), torch.zeros(2, 0, dtype=torch.long), torch.zeros(0, dtype=torch.long),
                       batch_node_index=torch.tensor([0, 0, 2]), batch_edge_index=torch.zeros(0, dtype=torch.long))
     assert len(G3) == 3  # size inferred like the reference (graph.py:184)

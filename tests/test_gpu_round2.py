@@ -1,0 +1,293 @@
+"""Round-2 GPU parity tests: the sizes BASELINE.json quotes (element-wise, not only through properties), the fused
+GraphEmbedding + edge initialisation, the recompute-messages mode, and the cache-hazard regressions of ADVICE.md."""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from helpers import REL_F32, assert_close, oracle_inputs, rel_err
+from oracle import dmpnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _defaults():
+    from notorch_b200 import ops
+
+    ops.set_index_validation("sync")
+    yield
+    ops.set_gemm_mode("tf32x3")
+    ops.set_save_messages(True)
+
+
+def _load(blk, p):
+    with torch.no_grad():
+        for l, layer in enumerate(blk.layers):
+            layer.module.update[0].weight.copy_(p["weights"][l])
+            layer.module.update[0].bias.copy_(p["biases"][l])
+
+
+def _block_parity(p, depth, agg_kind, mode, *, rel=REL_F32, check_fp32_oracle=True, with_gE=True):
+    """ChempropBlock + read-out through the nn modules vs the oracle: forward against the fp32 AND fp64 oracle, every gradient against
+    the fp64 hand-derived backward (chemprop.py:81-88, agg.py:27,36). Prints the ReLU sign-flip count and the gradient error both
+    with and without evaluating the oracle's ReLU derivative at the CUDA path's own h_l (``act_grad_at``)."""
+    from notorch_b200 import BatchedGraph, ops
+    from notorch_b200.nn import ChempropBlock, Mean, Sum
+
+    ops.set_gemm_mode(mode)
+    d, B, V, E = p["d"], p["B"], p["V"], p["E"]
+    ei, rev, bni = p["edge_index"], p["rev_index"], p["batch_node_index"]
+    blk = ChempropBlock(hidden_dim=d, depth=depth).cuda()
+    _load(blk, p)
+    agg = (Sum if agg_kind == "sum" else Mean)()
+    gen = torch.Generator().manual_seed(17)
+    gH = torch.randn(B, d, generator=gen)
+    gE = torch.randn(E, d, generator=gen) if with_gE else None
+    xv, xe = p["x_v"].cuda().requires_grad_(True), p["x_e"].cuda().requires_grad_(True)
+    G = BatchedGraph(xv, xe, ei.cuda(), rev.cuda(), batch_node_index=bni.cuda(), batch_edge_index=p["batch_edge_index"].cuda(), size=B)
+    # the per-depth states, to count ReLU sign flips against the fp64 run (same launches the block makes)
+    csr = ops.graph_csr(G)
+    hs = [ops.edge_init(xv.detach(), xe.detach(), csr)]
+    for l in range(depth):
+        lin = blk.layers[l].module.update[0]
+        hs.append(ops.layer(hs[-1], lin.weight.detach(), lin.bias.detach(), csr))
+    G1 = blk(G)
+    H = agg(G1)
+    assert torch.equal(G1.edge_feats.detach(), hs[-1])  # the module path IS those launches
+    loss = (H * gH.cuda()).sum()
+    if with_gE:
+        loss = loss + (G1.edge_feats * gE.cuda()).sum()
+    loss.backward()
+
+    f64 = torch.float64
+    W64, b64 = [w.to(f64) for w in p["weights"]], [b.to(f64) for b in p["biases"]]
+    node64, edge64, hs64 = O.block_forward(p["x_v"].to(f64), p["x_e"].to(f64), ei, rev, W64, b64)
+    refs = [(node64, edge64, "fp64 oracle")]
+    if check_fp32_oracle:
+        node32, edge32, _ = O.block_forward(p["x_v"], p["x_e"], ei, rev, p["weights"], p["biases"])
+        refs.append((node32, edge32, "fp32 oracle"))
+    for ref_node, ref_edge, tag in refs:
+        assert_close(G1.node_feats, ref_node, f"node_out vs {tag}", rel)
+        assert_close(G1.edge_feats, ref_edge, f"edge_out vs {tag}", rel)
+        assert_close(H, O.readout(ref_node, bni, B, agg_kind), f"H vs {tag}", rel)
+    flips = sum(int(((hs[l].cpu() > 0) != (hs64[l] > 0)).sum()) for l in range(depth))
+    g_node = O.readout_backward(gH.to(f64), bni, V, agg_kind)
+    gE64 = gE.to(f64) if with_gE else torch.zeros(E, d, dtype=f64)
+    plain = O.block_backward(p["x_v"].to(f64), p["x_e"].to(f64), ei, rev, W64, b64, g_node, gE64)
+    ref = plain if not flips else O.block_backward(p["x_v"].to(f64), p["x_e"].to(f64), ei, rev, W64, b64, g_node, gE64,
+                                                   act_grad_at=[h.cpu() for h in hs[:depth]])
+    got = {"x_v": xv.grad, "x_e": xe.grad}
+    want, want_plain = {"x_v": ref["x_v"], "x_e": ref["x_e"]}, {"x_v": plain["x_v"], "x_e": plain["x_e"]}
+    for l, layer in enumerate(blk.layers):
+        lin = layer.module.update[0]
+        got[f"W{l}"], got[f"b{l}"] = lin.weight.grad, lin.bias.grad
+        want[f"W{l}"], want[f"b{l}"] = ref["weights"][l], ref["biases"][l]
+        want_plain[f"W{l}"], want_plain[f"b{l}"] = plain["weights"][l], plain["biases"][l]
+    worst = max(rel_err(got[k], want[k]) for k in got)
+    worst_plain = max(rel_err(got[k], want_plain[k]) for k in got)
+    print(f"[parity] mode={mode} B={B} V={V} E={E} d={d} L={depth}: relu sign flips vs fp64 = {flips} of {depth * E * d}; "
+          f"worst gradient rel-to-max error {worst:.2e} (oracle derivative at the CUDA h_l) / {worst_plain:.2e} (unpatched fp64 oracle)")
+    assert flips <= 1e-4 * depth * E * d
+    for k in got:
+        assert_close(got[k], want[k], f"grad {k}", rel)
+    return flips, worst, worst_plain
+
+
+# ---------------------------------------------------------------- the sizes BASELINE.json quotes
+def test_config2_full_size_elementwise():
+    """BASELINE configs[1] exactly: B = 4096 ZINC-size molecules, d = 300, L = 3, Sum — every output element and every gradient
+    against the fp32 and fp64 oracle (the CPU oracle does this size in seconds)."""
+    p = oracle_inputs(4096, 300, 3, config=2, seed=2)
+    _block_parity(p, 3, "sum", "tf32x3", with_gE=False)  # the bench's loss touches H only
+
+
+def test_config2_full_size_elementwise_with_edge_cotangent():
+    p = oracle_inputs(4096, 300, 3, config=2, seed=3)
+    _block_parity(p, 3, "sum", "tf32x3", check_fp32_oracle=False)
+
+
+def test_config3_shape_d1024_depth5_mean():
+    """BASELINE configs[2] shape: d = 1024, L = 5, Mean read-out (block reduce = sum), ZINC-size molecules, B = 256."""
+    p = oracle_inputs(256, 1024, 5, config=3, seed=4)
+    _block_parity(p, 5, "mean", "tf32x3", check_fp32_oracle=False)
+
+
+def test_config5_shape_d2048_depth6_tf32x3():
+    """BASELINE configs[4] shape in the fp32-parity mode: 100-300-atom molecules, d = 2048, L = 6, B = 8."""
+    p = oracle_inputs(8, 2048, 6, config=5, seed=5)
+    _block_parity(p, 6, "sum", "tf32x3", check_fp32_oracle=False)
+
+
+def test_config5_shape_d2048_depth6_bf16_stated_bounds():
+    """BASELINE configs[4] in its own mode (bf16 operands, fp32 accumulation) at its own shape: the stated bounds of
+    tests/test_bf16_mode.py (embeddings rel-to-max 2e-2; gradients relative L2 5e-2) against the exact fp64 oracle."""
+    from notorch_b200 import BatchedGraph, ops
+    from notorch_b200.nn import ChempropBlock, Sum
+
+    depth, d, B = 6, 2048, 8
+    p = oracle_inputs(B, d, depth, config=5, seed=6)
+    ops.set_gemm_mode("bf16")
+    blk = ChempropBlock(hidden_dim=d, depth=depth).cuda()
+    _load(blk, p)
+    xv, xe = p["x_v"].cuda().requires_grad_(True), p["x_e"].cuda().requires_grad_(True)
+    G = BatchedGraph(xv, xe, p["edge_index"].cuda(), p["rev_index"].cuda(), batch_node_index=p["batch_node_index"].cuda(),
+                     batch_edge_index=p["batch_edge_index"].cuda(), size=B)
+    G1 = blk(G)
+    H = Sum()(G1)
+    gH = torch.randn(B, d, generator=torch.Generator().manual_seed(1))
+    (H * gH.cuda()).sum().backward()
+    f64 = torch.float64
+    W64, b64 = [w.to(f64) for w in p["weights"]], [b.to(f64) for b in p["biases"]]
+    node64, edge64, _ = O.block_forward(p["x_v"].to(f64), p["x_e"].to(f64), p["edge_index"], p["rev_index"], W64, b64)
+    assert_close(G1.edge_feats, edge64, "edge_out (bf16 mode)", 2e-2)
+    assert_close(H, O.readout(node64, p["batch_node_index"], B, "sum"), "H (bf16 mode)", 2e-2)
+    ref = O.block_backward(p["x_v"].to(f64), p["x_e"].to(f64), p["edge_index"], p["rev_index"], W64, b64,
+                           O.readout_backward(gH.to(f64), p["batch_node_index"], p["V"], "sum"), torch.zeros(p["E"], d, dtype=f64))
+    l2 = lambda a, r: float((a.detach().double().cpu() - r).norm() / r.norm())  # noqa: E731
+    errs = {"x_v": l2(xv.grad, ref["x_v"]), "x_e": l2(xe.grad, ref["x_e"])}
+    for l, layer in enumerate(blk.layers):
+        errs[f"W{l}"] = l2(layer.module.update[0].weight.grad, ref["weights"][l])
+        errs[f"b{l}"] = l2(layer.module.update[0].bias.grad, ref["biases"][l])
+    print("[parity] bf16 mode, configs[4] shape: relative L2 gradient errors", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) <= 5e-2, errs
+
+
+# ---------------------------------------------------------------- N1: GraphEmbedding fused into the edge initialisation
+@pytest.mark.parametrize("d,B", [(300, 64), (64, 16), (1024, 12), (2048, 4), (8, 5)])
+def test_fused_embedding_edge_init_is_bit_identical_and_differentiates(d, B):
+    """embed.py:20-24 + chemprop.py:83 in one kernel: h0 equals the unfused kernels bit for bit (and torch's EmbeddingBag within
+    1e-6); the table gradients equal autograd of the fp64 restatement within the fp32 bound; two runs are bit-identical."""
+    from notorch_b200 import BatchedGraph, ops
+    from notorch_b200.data.models.graph import PendingFeats
+    from notorch_b200.nn import ChempropBlock, GraphEmbedding
+
+    p = oracle_inputs(B, 8, 0, seed=21 + d)
+    gen = torch.Generator().manual_seed(3)
+    V, E = p["V"], p["E"]
+    nv, ne = torch.randint(0, 45, (V, 7), generator=gen), torch.randint(0, 13, (E, 2), generator=gen)
+    g = torch.randn(E, d, generator=gen)
+    torch.manual_seed(0)
+    emb = GraphEmbedding(hidden_dim=d).cuda()
+    G = BatchedGraph(nv.cuda(), ne.cuda(), p["edge_index"].cuda(), p["rev_index"].cuda(), batch_node_index=p["batch_node_index"].cuda(),
+                     batch_edge_index=p["batch_edge_index"].cuda(), size=B)
+    csr = ops.graph_csr(G)
+    G1 = emb(G)
+    assert isinstance(G1.peek("node_feats"), PendingFeats) and G1.num_nodes == V and G1.num_edges == E
+    blk0 = ChempropBlock(hidden_dim=d, depth=0).cuda()  # depth 0: edge_feats of the result IS h0
+    runs = []
+    for _ in range(2):
+        emb.zero_grad()
+        out = blk0(emb(G))
+        (out.edge_feats * g.cuda()).sum().backward()
+        runs.append((out.edge_feats.detach().clone(), emb.node.weight.grad.clone(), emb.edge.weight.grad.clone()))
+    assert all(torch.equal(a, b) for a, b in zip(*runs))
+    fused_h0, gtv, gte = runs[0]
+    # unfused path: reading the attributes materialises x_v / x_e through nt_embedding_bag_sum, then K0
+    emb.zero_grad()
+    G2 = emb(G)
+    xv, xe = G2.node_feats, G2.edge_feats
+    assert isinstance(xv, torch.Tensor) and not isinstance(G2.peek("node_feats"), PendingFeats)
+    h0 = ops.edge_init(xv, xe, csr)
+    (h0 * g.cuda()).sum().backward()
+    assert torch.equal(fused_h0, h0.detach())
+    assert torch.equal(blk0(G2).edge_feats, h0)  # a materialised graph takes the plain K0
+    # reference arithmetic (fp64 EmbeddingBag + gather) for the gradients
+    wv64, we64 = emb.node.weight.detach().double().cpu().requires_grad_(True), emb.edge.weight.detach().double().cpu().requires_grad_(True)
+    ref = torch.nn.functional.embedding_bag(nv, wv64, mode="sum")[p["edge_index"][0]] + torch.nn.functional.embedding_bag(ne, we64, mode="sum")
+    (ref * g.double()).sum().backward()
+    assert_close(fused_h0, ref.detach(), "fused h0", 1e-6)
+    assert_close(gtv, wv64.grad, "grad node table (fused)")
+    assert_close(gte, we64.grad, "grad edge table (fused)")
+    assert_close(emb.node.weight.grad, wv64.grad, "grad node table (unfused)")
+    with pytest.raises(IndexError):
+        blk0(emb(G.update(node_feats=nv.cuda() + 45)))
+
+
+def test_fused_embedding_through_a_training_step_matches_unfused():
+    from notorch_b200 import BatchedGraph, ops
+    from notorch_b200.nn import ChempropBlock, GraphEmbedding, Sum
+
+    p = oracle_inputs(96, 8, 0, config=2, seed=5)
+    gen = torch.Generator().manual_seed(9)
+    nv, ne = torch.randint(0, 45, (p["V"], 7), generator=gen), torch.randint(0, 13, (p["E"], 2), generator=gen)
+    torch.manual_seed(1)
+    emb, blk = GraphEmbedding(hidden_dim=300).cuda(), ChempropBlock(hidden_dim=300, depth=3).cuda()
+    G = BatchedGraph(nv.cuda(), ne.cuda(), p["edge_index"].cuda(), p["rev_index"].cuda(), batch_node_index=p["batch_node_index"].cuda(),
+                     batch_edge_index=p["batch_edge_index"].cuda(), size=96)
+    res = []
+    for fuse in (True, False):
+        ops._fuse_embedding = fuse
+        try:
+            emb.zero_grad(), blk.zero_grad()
+            H = Sum()(blk(emb(G)))
+            H.square().mean().backward()
+            res.append((H.detach().clone(), emb.node.weight.grad.clone(), emb.edge.weight.grad.clone(), blk.layers[0].module.update[0].weight.grad.clone()))
+        finally:
+            ops._fuse_embedding = True
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][3], res[1][3])  # forward and block gradients: same bits
+    assert_close(res[0][1], res[1][1], "node table grad fused vs unfused", 2e-6)       # table gradients: another summation order
+    assert_close(res[0][2], res[1][2], "edge table grad fused vs unfused", 2e-6)
+
+
+# ---------------------------------------------------------------- recompute-messages mode (activation memory)
+@pytest.mark.parametrize("d", [300, 64])
+def test_recompute_messages_mode_matches_saved_messages(d):
+    """ops.set_save_messages(False): K2 does not write m_l, the weight gradient re-gathers n[src] - act(h)[rev] (wgrad_tc.cu)."""
+    from notorch_b200 import ops
+
+    p = oracle_inputs(64, d, 2, config=1, seed=7)
+    res = []
+    for save in (True, False):
+        ops.set_save_messages(save)
+        res.append(_block_parity(p, 2, "sum", "tf32x3"))
+    ops.set_save_messages(True)
+
+
+# ---------------------------------------------------------------- caches keyed on tensor addresses
+def test_layer_csr_cache_survives_address_recycling():
+    """Two different same-shape topologies back to back, the first freed in between: the caching allocator hands the second batch
+    the first one's addresses (same [2, E] shape, _version 0) — the stand-alone layer must still use the NEW topology."""
+    from notorch_b200.nn import ChempropLayer
+
+    torch.manual_seed(0)
+    d, V, E = 32, 40, 96
+    layer = ChempropLayer(d).cuda()
+    gen = torch.Generator().manual_seed(1)
+    h, xv = torch.randn(E, d, generator=gen).cuda(), torch.zeros(V, d).cuda()
+    outs, ptrs = [], []
+    for trial in range(2):
+        src, dst, rev = torch.randint(0, V, (E,), generator=gen), torch.randint(0, V, (E,), generator=gen), torch.randint(0, E, (E,), generator=gen)
+        ei, rv = torch.stack([src, dst]).cuda(), rev.cuda()
+        ptrs.append((ei.data_ptr(), rv.data_ptr()))
+        out = layer(h, xv, ei, rv)
+        W, b = layer.update[0].weight.detach().cpu().double(), layer.update[0].bias.detach().cpu().double()
+        ref, _ = O.layer_forward(h.cpu().double(), V, src, dst, rev, W, b, residual=False)
+        assert_close(out, ref, f"stand-alone layer, topology {trial}")
+        outs.append(out.detach().clone())
+        del ei, rv, out
+    assert not torch.equal(outs[0], outs[1])
+    from notorch_b200 import ops
+    assert all(c.source[0].data_ptr() == k[0][0] for k, c in ops._layer_csr_cache)  # every entry owns the tensors its key names
+
+
+def test_graph_to_keeps_and_carries_the_csr_bundle():
+    """N4 (lightning_models/model.py:221-271 moves the batch with .to(device)): a no-op move keeps the cached CSR bundle; after a real
+    move of the index tensors the bundle is re-keyed to the new tensors and NOT rebuilt (no kernel launch)."""
+    from notorch_b200 import BatchedGraph, _lib, ops
+
+    p = oracle_inputs(16, 32, 0, seed=3)
+    G = BatchedGraph(p["x_v"].cuda(), p["x_e"].cuda(), p["edge_index"].cuda(), p["rev_index"].cuda(), batch_node_index=p["batch_node_index"].cuda(),
+                     batch_edge_index=p["batch_edge_index"].cuda(), size=16)
+    csr = ops.graph_csr(G)
+    mol = ops.segment_csr_for(G, "batch_node_index", 16)
+    assert G.to("cuda") is G and ops.graph_csr(G) is csr
+    before = {name: getattr(G, name) for name in G._TENSOR_FIELDS}
+    caches = {a: G.__dict__.pop(a) for a in G._CACHE_ATTRS if a in G.__dict__}
+    for name, t in before.items():
+        setattr(G, name, t.clone())  # what .to(another device) does to the fields
+    ops.carry_graph_caches(G, caches, before)
+    n0 = _lib.lib().nt_kernel_launch_count()
+    csr2, mol2 = ops.graph_csr(G), ops.segment_csr_for(G, "batch_node_index", 16)
+    assert _lib.lib().nt_kernel_launch_count() == n0
+    assert csr2.by_dst.perm is csr.by_dst.perm and csr2.source[0] is G.edge_index and mol2 is mol
