@@ -133,11 +133,11 @@ def seg_reduce(x: Tensor, index: Tensor, size: int, reduce: str = "sum") -> Tens
     if reduce in ("max", "min"):
         return seg_extreme(x, index, size, reduce)[0]
     idx = index.view(-1, 1).expand_as(x)
-    out = torch.zeros((size, x.shape[1]), dtype=x.dtype).scatter_add_(0, idx, x)
+    out = torch.zeros((size, x.shape[1]), dtype=x.dtype, device=x.device).scatter_add_(0, idx, x)  # device: the port also runs as the eager-CUDA baseline
     if reduce == "sum":
         return out
     if reduce == "mean":
-        count = torch.zeros(size, dtype=x.dtype).scatter_add_(0, index, torch.ones(len(index), dtype=x.dtype))
+        count = torch.zeros(size, dtype=x.dtype, device=x.device).scatter_add_(0, index, torch.ones(len(index), dtype=x.dtype, device=x.device))
         count = count.clamp(min=1)
         return out / count.view(-1, 1)
     raise NotImplementedError(reduce)
@@ -383,4 +383,4 @@ def train_step_cpu(model: CpuPort, x_v, x_e, edge_index, rev_index, batch_node_i
     H, _, _ = model(x_v, x_e, edge_index, rev_index, batch_node_index, size)
     loss = H.square().mean()
     loss.backward()
-    return float(loss)
+    return float(loss.detach())

@@ -556,7 +556,7 @@ def test_graph_embedding_matches_torch_embedding_bag(d):
     assert_close(emb.edge.weight.grad, we64.grad, "grad edge table")
     assert list(emb.state_dict()) == ["node.weight", "edge.weight"]
     with pytest.raises(IndexError):
-        emb(G.update(node_feats=nv.cuda() + 45))
+        emb(G.update(node_feats=nv.cuda() + 45)).node_feats  # the look-up is deferred until the features are read (or fused into K0)
 
 
 def _mol_graph(x, batch, B, Q=None):
