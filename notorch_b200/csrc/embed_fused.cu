@@ -9,12 +9,12 @@
 //             order from a zero accumulator and the two sums are added last, i.e. exactly the arithmetic of
 //             nt_embedding_bag_sum + nt_gather_add: the fused result is bit-identical to the unfused one.
 //   backward  gTe[t, :] = sum_{(e,k): edge_types[e,k]=t} g[e, :]      gTv[t, :] = sum_{(e,j): node_types[src[e],j]=t} g[e, :]
-//             ONE pass over g = g_{h0} [E, d] (the unfused path reads it twice and makes a [V, d] intermediate with K5).
-//             A CTA holds G private copies of the combined gradient table [Tv + Te, cols] in shared memory, one per "row group"
-//             of ceil(cols / 128) warps; a row group walks ITS contiguous range of edges in ascending order, every thread owns
-//             one 16-byte column chunk and does one shared-memory read-modify-write per (edge, slot) — no atomics, no barrier in
-//             the loop, no two threads ever touch the same word. The G copies, then the CTAs' tables, are added in fixed order:
-//             run-to-run deterministic. Bound by the shared-memory pipe: (t_v + t_e) x 2 x d x 4 bytes per edge.
+//             ONE pass over g = g_{h0} [E, d] (the unfused path reads it twice and makes a [V, d] intermediate with K5), as a
+//             skinny tensor-core GEMM against the on-the-fly count matrix (see embed_bwd_mma_kernel below). Deterministic:
+//             every CTA owns a fixed range of rows, the CTAs' tables are added in ascending order, no atomics.
+//             (A first version did one shared-memory read-modify-write per (edge, slot) on per-thread columns of private tables:
+//             661 us at BASELINE configs[1] - the dependent LDS/FADD/STS chains of nine warps per SM cannot hide their own
+//             latency. Measured, replaced.)
 #include "common.cuh"
 
 namespace nt {
@@ -74,74 +74,158 @@ embed_edge_init_kernel(const float* __restrict__ tab_v, int Tv, const float* __r
   }
 }
 
-constexpr int EFB_UNROLL = 4;  // edges whose ids and gradient rows are in flight per thread
+// ---- backward on the (legacy, warp-level) tensor-core path -------------------------------------------------------------------
+// The table gradient is a skinny GEMM:  gT[t, c] = sum_r Cnt[t, r] * g[r, c],  Cnt[t, r] = how many slots of row r hold type t
+// (a small-integer matrix, exact in TF32). One CTA per SM walks a contiguous range of 64-row blocks:
+//   * two BUILDER warps turn the ids of block b + 1 into Cnt (one thread per row: it zeroes its own column of the [types][64]
+//     count tile and bumps one cell per slot - no two threads share a cell, so no atomics);
+//   * sixteen MMA warps own up to three 8-column tiles each: per 8-row k-step they load the g fragment straight from global memory
+//     (one k-step ahead in registers), split it into TF32 hi + lo (two mma.sync.m16n8k8 per tile: the product is exact to 2^-22)
+//     and accumulate all `MT` 16-type tiles in registers;
+//   * one barrier per block hands the count tile over. Per-CTA tables, then a fixed-order sum (same kernel as above).
+// mma.sync is the warp-level tensor-core path (SASS HMMA): right for a 58 x 300 output whose M is far below a tcgen05 tile; the
+// kernel is bound by streaming g once.
+constexpr int EFM_MMA_WARPS = 16, EFM_BUILD_WARPS = 2, EFM_THREADS = (EFM_MMA_WARPS + EFM_BUILD_WARPS) * 32;
+constexpr int EFM_ROWS = 64, EFM_LD = 68;  // rows per block; padded row length of the count tile (conflict-free fragment loads)
+constexpr int EFM_NT = 3;                   // 8-column tiles per MMA warp -> 384 columns per pass (one tile when there are 8 type tiles)
 
-__global__ void __launch_bounds__(1024)
-embed_edge_init_bwd_kernel(const float* __restrict__ g, const int64_t* __restrict__ node_types, int bv, const int64_t* __restrict__ edge_types, int be,
-                           const int32_t* __restrict__ src, int64_t E, int64_t V, int Tv, int Te, int d, int col0, int cols, int G, int warps_per_group,
-                           int64_t rows_per_group, float* __restrict__ partial) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int chunks = cols / 4, T = Tv + Te, S = bv + be;
-  float4* tab = reinterpret_cast<float4*>(smem_raw);  // [G][T][chunks]
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(EFM_THREADS, 1)
+embed_bwd_mma_kernel(const float* __restrict__ g, const int64_t* __restrict__ node_types, int bv, const int64_t* __restrict__ edge_types, int be,
+                     const int32_t* __restrict__ src, int64_t n_rows, int64_t V, int Tv, int Te, int d, int col0, int cols, int64_t blocks_per_cta,
+                     int flush_blocks, float* __restrict__ partial) {
+  extern __shared__ __align__(16) float cnt_smem[];  // [2][MT * 16][EFM_LD]
+  constexpr int TYPES = MT * 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = warp / warps_per_group;
-  const int c = (warp - grp * warps_per_group) * 32 + lane;  // this thread's 16-byte column chunk inside the window
-  const bool active = c < chunks;
-  for (int i = tid; i < G * T * chunks; i += blockDim.x) tab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-  float4* my = tab + (size_t)grp * T * chunks + c;
-  const int64_t q = (int64_t)blockIdx.x * G + grp;
-  const int64_t e0 = q * rows_per_group;
-  int64_t e1 = e0 + rows_per_group;
-  if (e1 > E) e1 = E;
-  for (int64_t e = e0; e < e1; e += EFB_UNROLL) {  // bounds are uniform over the row group: every warp takes the shuffles together
-    int off[EFB_UNROLL];
-    float4 gv[EFB_UNROLL];
-#pragma unroll
-    for (int u = 0; u < EFB_UNROLL; ++u) {
-      off[u] = 0;
-      gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e + u < e1) {
-        if (lane < S) {  // lane j holds the table row of slot j of this edge (node slots first)
-          int64_t k;
-          int base, limit;
-          if (lane < bv) {
-            int64_t s = __ldg(src + e + u);
-            if (s < 0 || s >= V) s = 0;
-            k = __ldg(node_types + s * bv + lane);
-            base = 0; limit = Tv;
-          } else {
-            k = __ldg(edge_types + (e + u) * be + (lane - bv));
-            base = Tv; limit = Te;
-          }
-          if (k < 0 || k >= limit) k = 0;  // the forward pass has reported it (status flag); stay in bounds here
-          off[u] = (base + (int)k) * chunks;
-        }
-        if (active) gv[u] = ldg4_stream(g + (e + u) * d + col0 + 4 * c);
+  const int grp = lane >> 2, tig = lane & 3;
+  const int64_t nblocks = (n_rows + EFM_ROWS - 1) / EFM_ROWS;
+  const int64_t b0 = (int64_t)blockIdx.x * blocks_per_cta;
+  int64_t b1 = b0 + blocks_per_cta;
+  if (b1 > nblocks) b1 = nblocks;
+  const bool builder = warp >= EFM_MMA_WARPS;
+
+  auto build = [&](int64_t blk, int buf) {  // builder threads only: thread i owns row i of the block (= column i of the count tile)
+    const int i = tid - EFM_MMA_WARPS * 32;
+    float* col = cnt_smem + (size_t)buf * TYPES * EFM_LD + i;
+#pragma unroll 4
+    for (int t = 0; t < TYPES; ++t) col[t * EFM_LD] = 0.f;
+    const int64_t r = blk * EFM_ROWS + i;
+    if (r < n_rows) {
+      int64_t s = src ? (int64_t)__ldg(src + r) : r;
+      if (s < 0 || s >= V) s = 0;
+      for (int j = 0; j < bv; ++j) {
+        int64_t k = __ldg(node_types + s * bv + j);
+        if (k < 0 || k >= Tv) k = 0;  // reported by the forward pass (status flag); stay in bounds here
+        col[(int)k * EFM_LD] += 1.f;
+      }
+      for (int j = 0; j < be; ++j) {
+        int64_t k = __ldg(edge_types + r * be + j);
+        if (k < 0 || k >= Te) k = 0;
+        col[(Tv + (int)k) * EFM_LD] += 1.f;
       }
     }
+  };
+
+  float acc[NT][MT][4];
 #pragma unroll
-    for (int u = 0; u < EFB_UNROLL; ++u) {
-      if (e + u < e1) {
-        for (int j = 0; j < S; ++j) {
-          const int o = __shfl_sync(0xffffffffu, off[u], j);
-          if (active) {
-            float4 a = my[o];
-            my[o] = make_float4(a.x + gv[u].x, a.y + gv[u].y, a.z + gv[u].z, a.w + gv[u].w);
+  for (int i = 0; i < NT; ++i)
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) acc[i][m][x] = 0.f;
+
+  // this warp's column tiles: tile index warp + 16 i  ->  first column n0[i] (window-relative); a tile past the window is skipped
+  int ncol[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) ncol[i] = (warp + EFM_MMA_WARPS * i) * 8 + grp;  // the column this lane loads (B fragment: n = grp)
+  auto load_b = [&](int64_t blk, int ks, float (&out)[NT][2]) {
+    const int64_t r = blk * EFM_ROWS + ks * 8 + tig;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const bool cok = ncol[i] < cols;
+      out[i][0] = (cok && blk < b1 && r < n_rows) ? __ldg(g + r * d + col0 + ncol[i]) : 0.f;
+      out[i][1] = (cok && blk < b1 && r + 4 < n_rows) ? __ldg(g + (r + 4) * d + col0 + ncol[i]) : 0.f;
+    }
+  };
+
+  auto flush = [&](int64_t plane) {
+    // accumulator fragment: c0/c1 -> (type 16 m + grp, columns 2 tig, 2 tig + 1), c2/c3 -> type + 8
+    const int T = Tv + Te;
+    float* dst = partial + (size_t)plane * T * cols;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int c = (warp + EFM_MMA_WARPS * i) * 8 + 2 * tig;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int t0 = 16 * m + grp;
+        if (c < cols) {  // cols % 4 == 0 and c is even: c + 1 < cols as well
+          if (t0 < T) *reinterpret_cast<float2*>(dst + (size_t)t0 * cols + c) = make_float2(acc[i][m][0], acc[i][m][1]);
+          if (t0 + 8 < T) *reinterpret_cast<float2*>(dst + (size_t)(t0 + 8) * cols + c) = make_float2(acc[i][m][2], acc[i][m][3]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc[i][m][x] = 0.f;
+      }
+    }
+  };
+
+  if (builder && b0 < b1) build(b0, 0);
+  __syncthreads();
+  float nxt[NT][2];
+  if (!builder) load_b(b0, 0, nxt);
+  // The tensor core TRUNCATES when it adds into its fp32 accumulator, so the error of a long accumulation chain grows with its
+  // length: every `flush_blocks` blocks the accumulators are written out as one more partial table (70 KB each at d = 300 - cheap)
+  // and restarted from zero; the partial tables are then added in fp32 (round to nearest) in fixed order.
+  for (int64_t blk = b0; blk < b0 + blocks_per_cta; ++blk) {
+    const bool last_of_group = ((blk - b0 + 1) % flush_blocks == 0) || blk + 1 == b0 + blocks_per_cta;
+    if (blk >= b1) {  // a CTA with fewer blocks than the others still writes its (zero) tables: the sum reads every plane
+      if (!builder && last_of_group) flush(((blk - b0) / flush_blocks) * gridDim.x + blockIdx.x);
+      continue;       // uniform over the CTA: no barrier is skipped by part of it
+    }
+    const int buf = (int)((blk - b0) & 1);
+    if (builder) {
+      if (blk + 1 < b1) build(blk + 1, buf ^ 1);
+    } else {
+      const float* cnt = cnt_smem + (size_t)buf * TYPES * EFM_LD;
+#pragma unroll 1
+      for (int ks = 0; ks < EFM_ROWS / 8; ++ks) {
+        float cur[NT][2];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) { cur[i][0] = nxt[i][0]; cur[i][1] = nxt[i][1]; }
+        if (ks + 1 < EFM_ROWS / 8) load_b(blk, ks + 1, nxt);
+        else load_b(blk + 1, 0, nxt);
+        uint32_t a[MT][4];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const float* p = cnt + (size_t)(16 * m + grp) * EFM_LD + ks * 8 + tig;
+          a[m][0] = __float_as_uint(p[0]);
+          a[m][1] = __float_as_uint(p[8 * EFM_LD]);
+          a[m][2] = __float_as_uint(p[4]);
+          a[m][3] = __float_as_uint(p[8 * EFM_LD + 4]);
+        }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          if ((warp + EFM_MMA_WARPS * i) * 8 < cols) {  // warp-uniform
+            uint32_t hi0, hi1;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi0) : "f"(cur[i][0]));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi1) : "f"(cur[i][1]));
+            const uint32_t lo0 = __float_as_uint(cur[i][0] - __uint_as_float(hi0)), lo1 = __float_as_uint(cur[i][1] - __uint_as_float(hi1));
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              mma_tf32_16x8x8(acc[i][m], a[m], hi0, hi1);
+              mma_tf32_16x8x8(acc[i][m], a[m], lo0, lo1);
+            }
           }
         }
       }
     }
-  }
-  __syncthreads();
-  float4* dst = reinterpret_cast<float4*>(partial) + (size_t)blockIdx.x * T * chunks;
-  for (int i = tid; i < T * chunks; i += blockDim.x) {
-    float4 s = tab[i];
-    for (int k = 1; k < G; ++k) {  // ascending group order
-      const float4 v = tab[(size_t)k * T * chunks + i];
-      s = make_float4(s.x + v.x, s.y + v.y, s.z + v.z, s.w + v.w);
-    }
-    dst[i] = s;
+    if (!builder && last_of_group) flush(((blk - b0) / flush_blocks) * gridDim.x + blockIdx.x);
+    __syncthreads();  // count tile of block blk + 1 complete; the one of block blk free for block blk + 2
   }
 }
 
@@ -171,37 +255,78 @@ __global__ void __launch_bounds__(256) embed_edge_init_bwd_reduce(const float* _
   stg4(out + col0 + 4 * c, s);
 }
 
-// ---- launch geometry (shared by the workspace query and the launcher) ----------------------------------------------------
-struct EfbPlan {
-  int cols;             // columns per pass (multiple of 4)
-  int G;                // private tables (= row groups) per CTA
-  int warps_per_group;
-  int grid;             // CTAs = partial tables
-  size_t smem;
+// ---- launch geometry of the backward (shared by the workspace query and the launchers) ----------------------------------------
+struct EfmPlan {
+  int mt;      // 16-type tiles (1, 2, 4 or 8)
+  int cols;    // columns per pass
+  int grid;    // CTAs
+  int64_t blocks_per_cta;
+  int flush_blocks;  // blocks per accumulation chain (64 rows each)
+  int planes;        // partial tables = grid * ceil(blocks_per_cta / flush_blocks)
 };
 
-static bool efb_plan(int64_t E, int64_t T, int64_t d, EfbPlan* p) {
-  const size_t budget = 208 * 1024;
-  if (d % 4 != 0 || T <= 0 || T * 16 > (int64_t)budget) return false;
-  int64_t cols = (int64_t)(budget / 3 / (size_t)(T * 4)) / 4 * 4;  // room for three private tables if the width allows it
-  if (cols < 128) cols = (int64_t)(budget / (size_t)(T * 4)) / 4 * 4;  // wide vocabulary: fewer, wider-than-nothing tables
-  if (cols > d) cols = d;
-  if (cols < 4) return false;
-  if (cols > 4096) cols = 4096;  // 1024 threads x 16 bytes
-  p->cols = (int)cols;
-  const int chunks = (int)cols / 4;
-  p->warps_per_group = (chunks + 31) / 32;
-  int G = (int)(budget / ((size_t)T * cols * 4));
-  if (G > 4) G = 4;
-  while (G > 1 && G * p->warps_per_group > 32) --G;
-  if (G < 1) return false;
-  p->G = G;
-  p->smem = (size_t)G * T * cols * 4;
+static bool efm_plan(int64_t n_rows, int64_t T, int64_t d, EfmPlan* p) {
+  if (d % 4 != 0 || T <= 0 || T > 128 || n_rows <= 0) return false;
+  p->mt = T <= 16 ? 1 : T <= 32 ? 2 : T <= 64 ? 4 : 8;
+  const int pass_cols = EFM_MMA_WARPS * (p->mt == 8 ? 1 : EFM_NT) * 8;
+  p->cols = (int)(d < pass_cols ? d : pass_cols);
   int sms = num_sms();
   if (sms <= 0) sms = 148;
-  const int64_t want = cdiv(E, 64 * G);  // at least ~64 edges per row group
-  p->grid = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
+  const int64_t nblocks = cdiv(n_rows, EFM_ROWS);
+  p->grid = (int)(nblocks < sms ? nblocks : sms);
+  p->blocks_per_cta = cdiv(nblocks, p->grid);
+  p->grid = (int)cdiv(nblocks, p->blocks_per_cta);
+  p->flush_blocks = 6;  // 6 blocks x 8 k-steps x (hi, lo) = 96 truncating accumulations per chain
+  p->planes = p->grid * (int)cdiv(p->blocks_per_cta, p->flush_blocks);
   return true;
+}
+
+template <int MT, int NT>
+static cudaError_t efm_launch(const EfmPlan& plan, const float* g, const int64_t* node_types, int bv, const int64_t* edge_types, int be, const int32_t* src,
+                              int64_t n_rows, int64_t V, int Tv, int Te, int d, int col0, int w, float* partial, cudaStream_t st) {
+  const size_t smem = (size_t)2 * MT * 16 * EFM_LD * sizeof(float);
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([] { return cudaFuncSetAttribute(embed_bwd_mma_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * EFM_LD * 4); });
+  if (e != cudaSuccess) return e;
+  embed_bwd_mma_kernel<MT, NT><<<plan.grid, EFM_THREADS, smem, st>>>(g, node_types, bv, edge_types, be, src, n_rows, V, Tv, Te, d, col0, w,
+                                                                 plan.blocks_per_cta, plan.flush_blocks, partial);
+  return cudaSuccess;
+}
+
+// shared by nt_embed_edge_init_backward (two id sources, node ids gathered through src) and nt_embedding_bag_backward (one source)
+int embed_bwd_mma(const float* g, const int64_t* node_types, int64_t bv, const int64_t* edge_types, int64_t be, const int32_t* src, int64_t n_rows, int64_t V,
+                  int64_t Tv, int64_t Te, int64_t d, float* g_tab_v, float* g_tab_e, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  EfmPlan plan;
+  if (!efm_plan(n_rows, Tv + Te, d, &plan)) return NT_ERR_UNSUPPORTED;
+  if (workspace_bytes < (size_t)plan.planes * (size_t)(Tv + Te) * plan.cols * sizeof(float)) {
+    set_error("embedding backward: workspace too small");
+    return NT_ERR_WORKSPACE;
+  }
+  const int T = (int)(Tv + Te);
+  int launches = 0;
+  for (int64_t col0 = 0; col0 < d; col0 += plan.cols) {
+    const int w = (int)(col0 + plan.cols <= d ? plan.cols : d - col0);
+    cudaError_t e;
+    float* part = static_cast<float*>(workspace);
+    switch (plan.mt) {
+      case 1: e = efm_launch<1, EFM_NT>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
+      case 2: e = efm_launch<2, EFM_NT>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
+      case 4: e = efm_launch<4, EFM_NT>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
+      default: e = efm_launch<8, 1>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(embed_bwd_mma_kernel)");
+    embed_edge_init_bwd_reduce<<<(unsigned)cdiv((int64_t)T * (w / 4), 256), 256, 0, st>>>(part, plan.grid, (int)Tv, (int)Te, (int)d, (int)col0, w, g_tab_v,
+                                                                                         g_tab_e);
+    launches += 2;
+  }
+  NT_LAUNCH_CHECK("embed_bwd_mma", launches);
+  return NT_OK;
+}
+
+size_t embed_bwd_mma_workspace_bytes(int64_t n_rows, int64_t T, int64_t d) {
+  EfmPlan plan;
+  if (!efm_plan(n_rows, T, d, &plan)) return 0;
+  return (size_t)plan.planes * (size_t)T * plan.cols * sizeof(float) + 256;
 }
 
 }  // namespace nt
@@ -252,9 +377,8 @@ extern "C" int nt_embed_edge_init(const void* table_v, int64_t num_node_types, c
 }
 
 extern "C" size_t nt_embed_edge_init_backward_workspace_bytes(int64_t E, int64_t num_node_types, int64_t num_edge_types, int64_t d) {
-  EfbPlan plan;
-  if (E <= 0 || d <= 0 || !efb_plan(E, num_node_types + num_edge_types, d, &plan)) return 0;
-  return (size_t)plan.grid * (size_t)(num_node_types + num_edge_types) * plan.cols * sizeof(float) + 256;
+  if (E <= 0 || d <= 0) return 0;
+  return embed_bwd_mma_workspace_bytes(E, num_node_types + num_edge_types, d);
 }
 
 extern "C" int nt_embed_edge_init_backward(const void* g, const int64_t* node_types, int64_t bag_v, const int64_t* edge_types, int64_t bag_e,
@@ -272,30 +396,14 @@ extern "C" int nt_embed_edge_init_backward(const void* g, const int64_t* node_ty
     return NT_OK;
   }
   NT_CHECK_ARG(g && node_types && edge_types && src, "nt_embed_edge_init_backward: null pointer");
-  EfbPlan plan;
-  if (!aligned16(g) || !aligned16(g_table_v) || !aligned16(g_table_e) || !efb_plan(E, num_node_types + num_edge_types, d, &plan)) {
-    set_error("nt_embed_edge_init_backward: needs d %% 4 == 0, 16-byte aligned rows and a vocabulary that fits shared memory");
+  if (!aligned16(g_table_v) || !aligned16(g_table_e) || nt_embed_edge_init_backward_workspace_bytes(E, num_node_types, num_edge_types, d) == 0) {
+    set_error("nt_embed_edge_init_backward: needs d %% 4 == 0, 16-byte aligned tables and at most 128 types in total");
     return NT_ERR_UNSUPPORTED;
   }
   if (!workspace || !aligned16(workspace) || workspace_bytes < nt_embed_edge_init_backward_workspace_bytes(E, num_node_types, num_edge_types, d)) {
     set_error("nt_embed_edge_init_backward: workspace too small (nt_embed_edge_init_backward_workspace_bytes)");
     return NT_ERR_WORKSPACE;
   }
-  static PerDeviceOnce once;
-  NT_CUDA(once.run([] { return cudaFuncSetAttribute(embed_edge_init_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); }));
-  const int T = (int)(num_node_types + num_edge_types);
-  const int64_t rows_per_group = cdiv(E, (int64_t)plan.grid * plan.G);
-  int launches = 0;
-  for (int64_t col0 = 0; col0 < d; col0 += plan.cols) {
-    const int w = (int)(col0 + plan.cols <= d ? plan.cols : d - col0);
-    embed_edge_init_bwd_kernel<<<plan.grid, plan.G * plan.warps_per_group * 32, (size_t)plan.G * T * w * 4, st>>>(
-        static_cast<const float*>(g), node_types, (int)bag_v, edge_types, (int)bag_e, src, E, V, (int)num_node_types, (int)num_edge_types, (int)d,
-        (int)col0, w, plan.G, plan.warps_per_group, rows_per_group, static_cast<float*>(workspace));
-    embed_edge_init_bwd_reduce<<<(unsigned)cdiv((int64_t)T * (w / 4), 256), 256, 0, st>>>(static_cast<const float*>(workspace), plan.grid,
-                                                                                         (int)num_node_types, (int)num_edge_types, (int)d, (int)col0, w,
-                                                                                         static_cast<float*>(g_table_v), static_cast<float*>(g_table_e));
-    launches += 2;
-  }
-  NT_LAUNCH_CHECK("nt_embed_edge_init_backward", launches);
-  return NT_OK;
+  return embed_bwd_mma(static_cast<const float*>(g), node_types, bag_v, edge_types, bag_e, src, E, V, num_node_types, num_edge_types, d,
+                       static_cast<float*>(g_table_v), static_cast<float*>(g_table_e), workspace, workspace_bytes, st);
 }

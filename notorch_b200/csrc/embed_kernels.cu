@@ -4,6 +4,8 @@
 // Forward is a gather-sum (tables are tiny and stay in L1/L2); backward is a deterministic two-stage
 // histogram-style reduction (per-CTA partial tables in shared memory, then a fixed-order sum) — the stock
 // path uses atomics (embedding_bag backward), this one does not.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nt {
@@ -298,6 +300,13 @@ static bool embb_plan(int64_t n, int64_t bag, int64_t num_types, int64_t d, Embb
 
 }  // namespace nt
 
+namespace nt {
+// embed_fused.cu: the table gradient as a skinny tensor-core GEMM against the on-the-fly count matrix (at most 128 types, d % 4 == 0)
+int embed_bwd_mma(const float* g, const int64_t* node_types, int64_t bv, const int64_t* edge_types, int64_t be, const int32_t* src, int64_t n_rows, int64_t V,
+                  int64_t Tv, int64_t Te, int64_t d, float* g_tab_v, float* g_tab_e, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t embed_bwd_mma_workspace_bytes(int64_t n_rows, int64_t T, int64_t d);
+}  // namespace nt
+
 using namespace nt;
 
 extern "C" int nt_embedding_bag_sum(const void* table, int64_t num_types, const int64_t* idx, int64_t n, int64_t bag, int64_t d, void* out,
@@ -339,7 +348,9 @@ extern "C" size_t nt_embedding_bag_backward_workspace_bytes(int64_t n, int64_t n
   int sms = num_sms();
   if (sms <= 0) sms = 148;
   if (nblk < (size_t)sms) nblk = (size_t)sms;
-  return (nblk + (size_t)cdiv((int64_t)nblk, EMB_GROUP)) * (size_t)num_types * (size_t)d * sizeof(float) + 256;
+  const size_t classic = (nblk + (size_t)cdiv((int64_t)nblk, EMB_GROUP)) * (size_t)num_types * (size_t)d * sizeof(float) + 256;
+  const size_t mma = embed_bwd_mma_workspace_bytes(n, num_types, d);
+  return classic > mma ? classic : mma;
 }
 
 extern "C" int nt_embedding_bag_backward(const void* g, const int64_t* idx, int64_t n, int64_t bag, int64_t num_types, int64_t d, void* g_table,
@@ -357,6 +368,13 @@ extern "C" int nt_embedding_bag_backward(const void* g, const int64_t* idx, int6
   if (!workspace || workspace_bytes < nt_embedding_bag_backward_workspace_bytes(n, num_types, d)) {
     set_error("nt_embedding_bag_backward: workspace too small");
     return NT_ERR_WORKSPACE;
+  }
+  if (bag <= 64 && aligned16(g_table) && aligned16(workspace) && embed_bwd_mma_workspace_bytes(n, num_types, d) > 0) {
+    // the common case (small vocabulary): tensor-core path shared with nt_embed_edge_init_backward (one id source, identity row map)
+    static const bool classic = getenv("NOTORCH_B200_EMBBWD_CLASSIC") != nullptr && atoi(getenv("NOTORCH_B200_EMBBWD_CLASSIC")) != 0;
+    if (!classic)
+      return embed_bwd_mma(static_cast<const float*>(g), idx, bag, nullptr, 0, nullptr, n, n, num_types, 0, d, static_cast<float*>(g_table), nullptr,
+                           workspace, workspace_bytes, st);
   }
   float* partial = static_cast<float*>(workspace);
   int launches = 0;

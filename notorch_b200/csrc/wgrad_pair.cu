@@ -46,7 +46,21 @@ struct Geometry {
   // fewer edge splits than the full-height ones, in proportion to their cost per edge.
   int half_last, full_units, half_units, splits, splits_last, planes;
   int64_t kb_total, kb_per_split, kb_per_split_last;
+  // Accumulation chains are cut every `seg_kb` K-blocks (32 edges each): the tensor core TRUNCATES when it adds into its fp32
+  // accumulator, so the error of a chain grows in proportion to its length (measured at BASELINE configs[1]: 4.6e-5 of the largest
+  // weight-gradient entry for chains of 5.5 k edges). At the end of a segment the epilogue adds the accumulator into the split's
+  // partial plane in fp32 (round to nearest) and the next segment restarts from zero.
+  int seg_kb;
 };
+
+static int segment_kblocks() {
+  static const int v = [] {
+    const char* e = getenv("NOTORCH_B200_WGRAD_SEG");
+    const int x = e ? atoi(e) : 16;
+    return x > 0 ? x : (1 << 30);
+  }();
+  return v;
+}
 
 static float half_unit_cost() {
   static const float w = [] {
@@ -91,6 +105,7 @@ static Geometry make_geometry(int64_t E, int d, int sms) {
   g.planes = (int)(sf > sl ? sf : sl);
   g.kb_per_split = sf > 0 ? (g.kb_total + sf - 1) / sf : 0;
   g.kb_per_split_last = sl > 0 ? (g.kb_total + sl - 1) / sl : 0;
+  g.seg_kb = segment_kblocks();
   return g;
 }
 
@@ -126,8 +141,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
   const uint32_t bar_ready = sbase + OFF_BAR;         // [STAGES] (leader's copy is the live one)
   const uint32_t bar_empty = bar_ready + 8 * STAGES;  // [STAGES]
   const uint32_t bar_tmem_full = bar_empty + 8 * STAGES;
-  const uint32_t tmem_slot = bar_tmem_full + 8;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * STAGES + 1));
+  const uint32_t bar_tmem_empty = bar_tmem_full + 8;  // leader's copy is the live one: all 8 epilogue warps of the pair arrive
+  const uint32_t tmem_slot = bar_tmem_empty + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * STAGES + 2));
 
   const Geometry& geo = p.geo;
   const int d = geo.d;
@@ -165,6 +181,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tmem_full, 1);
+    mbar_init(bar_tmem_empty, 2 * NUM_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) {
@@ -178,35 +195,60 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp < NUM_EPI_WARPS) {
-    // ===================================== EPILOGUE (once) =====================================
+    // ===================================== EPILOGUE (once per segment) =====================================
     // Accumulator layout in tensor memory. M = 256: lane = feature row (128 per CTA), column = output column. M = 128 (half-height
     // unit, 64 rows per CTA): lanes 0-63 hold the rows for the first half of each MMA's N, lanes 64-127 the same rows for the
     // second half, so an MMA of width N occupies N / 2 columns.
+    // Partial plane layout: [output column / 4][feature row][4] - a warp's 32 rows of one 4-column group are 512 contiguous bytes,
+    // so the per-segment read-modify-write below is fully coalesced (a row-major plane would make every lane touch its own line).
     const int row = half ? (warp & 1) * 32 + lane : warp * 32 + lane;
-    float* dst = p.partial + ((int64_t)split * geo.m_units * 2 * TILE_M + i0 + row) * geo.ld_partial + o0;
-    if (nkb > 0) {
-      mbar_wait_relaxed(bar_tmem_full, 0);
-      tc_fence_after();
-      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-      auto drain = [&](uint32_t col0, int ncols, float* out) {
-        for (int cc = 0; cc < ncols / 16; ++cc) {
-          uint32_t v[16];
-          tmem_ld16(lane_base + col0 + (uint32_t)(cc * 16), v);
-          tmem_ld_wait();
+    const int64_t plane_rows = (int64_t)geo.m_units * 2 * TILE_M;
+    float* plane = p.partial + (int64_t)split * plane_rows * geo.ld_partial;
+    const int64_t prow = i0 + row;
+    auto at = [&](int col) { return plane + (((int64_t)(o0 + col) >> 2) * plane_rows + prow) * 4; };  // col % 4 == 0
+    const int seg = geo.seg_kb;
+    const int64_t nseg = nkb > 0 ? (nkb + seg - 1) / seg : 0;
+    const uint32_t empty_leader = map_to_cta(bar_tmem_empty, 0);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    auto drain = [&](uint32_t tcol0, int ncols, int out_col0, bool accumulate) {
+      for (int cc = 0; cc < ncols / 16; ++cc) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + tcol0 + (uint32_t)(cc * 16), v);
+        float4 old[4];
+        if (accumulate) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(out + cc * 16 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) old[q] = *reinterpret_cast<const float4*>(at(out_col0 + cc * 16 + q * 4));
         }
-      };
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 r = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          if (accumulate) r = make_float4(old[q].x + r.x, old[q].y + r.y, old[q].z + r.z, old[q].w + r.w);
+          *reinterpret_cast<float4*>(at(out_col0 + cc * 16 + q * 4)) = r;
+        }
+      }
+    };
+    for (int64_t sg = 0; sg < nseg; ++sg) {
+      mbar_wait_relaxed(bar_tmem_full, (uint32_t)(sg & 1));
+      tc_fence_after();
       if (!half) {
-        drain(0u, geo.n_tile, dst);
+        drain(0u, geo.n_tile, 0, sg > 0);
       } else {
         const int hi_half = warp >> 1;
-        drain(0u, geo.n_a / 2, dst + hi_half * (geo.n_a / 2));
-        if (geo.n_b > 0) drain((uint32_t)geo.n_a, geo.n_b / 2, dst + geo.n_a + hi_half * (geo.n_b / 2));
+        drain(0u, geo.n_a / 2, hi_half * (geo.n_a / 2), sg > 0);
+        if (geo.n_b > 0) drain((uint32_t)geo.n_a, geo.n_b / 2, geo.n_a + hi_half * (geo.n_b / 2), sg > 0);
       }
-    } else if (!half || warp < 2) {
-      for (int c = 0; c < geo.n_tile; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sg + 1 < nseg) {  // hand the accumulator back: the next segment's first MMA overwrites it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(bar_tmem_empty);
+          else mbar_arrive_cluster(empty_leader);
+        }
+      }
+    }
+    if (nkb == 0 && (!half || warp < 2)) {
+      for (int c = 0; c < geo.n_tile; c += 4) *reinterpret_cast<float4*>(at(c)) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else if (warp == MMA_WARP) {
     // ===================================== MMA ISSUER (leader CTA only) =====================================
@@ -217,9 +259,14 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
       int s = 0;
       uint32_t ph = 0;
 #pragma unroll 1
+      const int seg = geo.seg_kb;
+      int kb_in_seg = 0;
+      uint32_t seg_idx = 0;
       for (int64_t kb = 0; kb < nkb; ++kb) {
+        if (kb_in_seg == 0 && kb > 0) mbar_wait(bar_tmem_empty, (seg_idx - 1) & 1);  // both CTAs' epilogues have drained the previous segment
         mbar_wait(bar_ready + 8 * s, ph);
         tc_fence_after();
+        const bool seg_end = kb_in_seg + 1 == seg || kb == nkb - 1;
         if (elect_one()) {
           const uint32_t st0 = sbase + s * STAGE_BYTES;
           const uint32_t a_hi = mnmajor_desc_lo(st0, CHUNK_BYTES), b_hi = mnmajor_desc_lo(st0 + A_CHUNKS * CHUNK_BYTES, CHUNK_BYTES);
@@ -229,7 +276,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
 #pragma unroll
           for (int j = 0; j < BLOCK_E / 8; ++j) {
             const uint32_t k16 = j * (1024u >> 4);  // next 8 edges = the next two 4-row swizzle atoms of every chunk
-            const uint32_t acc = (kb | j) != 0 ? 1u : 0u;
+            const uint32_t acc = (kb_in_seg | j) != 0 ? 1u : 0u;
             if (p.ablate & 1) {
             } else if (p.products == 3) {
               umma2_tf32_lo(tmem_base, a_lo + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, acc);
@@ -246,9 +293,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
             }
           }
           umma2_commit_both(bar_empty + 8 * s);
-          if (kb == nkb - 1) umma2_commit_both(bar_tmem_full);
+          if (seg_end) umma2_commit_both(bar_tmem_full);
         }
         __syncwarp();
+        if (seg_end) { kb_in_seg = 0; ++seg_idx; } else ++kb_in_seg;
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -354,20 +402,31 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
   }
 }
 
-// gW[o,i] = sum_z partial[z][i][o] in ascending z; gb[o] = the all-ones row i == d when present.
+// gW[o,i] = sum_z partial[z](i, o) in ascending z; gb[o] = the all-ones row i == d when present. One thread per (4 output columns,
+// feature row): a coalesced float4 read of every plane (layout [o / 4][i][4]) and four coalesced stores along i.
 __global__ void __launch_bounds__(256) wgrad_pair_reduce(const float* __restrict__ partial, Geometry geo, float* __restrict__ gW, float* __restrict__ gb) {
   const int d = geo.d;
   const int rows = d + (geo.ones_row ? 1 : 0);
-  int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (t >= (int64_t)rows * d) return;
-  const int i = (int)(t / d), o = (int)(t - (int64_t)i * d);  // o fastest: coalesced reads of the partial planes
-  const int64_t plane = (int64_t)geo.m_units * 2 * TILE_M * geo.ld_partial;
-  const float* src = partial + (int64_t)i * geo.ld_partial + o;
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int o4 = (int)(t / rows), i = (int)(t - (int64_t)o4 * rows);  // i fastest
+  if (4 * o4 >= d) return;
+  const int64_t plane_rows = (int64_t)geo.m_units * 2 * TILE_M;
+  const int64_t plane = plane_rows * geo.ld_partial;
+  const float4* src = reinterpret_cast<const float4*>(partial) + ((int64_t)o4 * plane_rows + i);
   const int nz = (geo.half_last && i >= (geo.m_units - 1) * 2 * TILE_M) ? geo.splits_last : geo.splits;
-  float s = 0.f;
-  for (int z = 0; z < nz; ++z) s += __ldg(src + z * plane);
-  if (i < d) gW[(int64_t)o * d + i] = s;
-  else if (gb) gb[o] = s;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < nz; ++z) {
+    const float4 v = __ldg(src + z * (plane / 4));
+    s = make_float4(s.x + v.x, s.y + v.y, s.z + v.z, s.w + v.w);
+  }
+  const float vals[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int o = 4 * o4 + q;
+    if (o >= d) break;
+    if (i < d) gW[(int64_t)o * d + i] = vals[q];
+    else if (gb) gb[o] = vals[q];
+  }
 }
 
 }  // namespace wgp
@@ -435,7 +494,7 @@ int pair_layer_wgrad(const float* g, const float* m, int64_t E, int64_t d, float
   cfg.numAttrs = 1;
   cudaError_t e = drop_p > 0.f ? cudaLaunchKernelEx(&cfg, wgp::wgrad_pair_kernel<true>, p) : cudaLaunchKernelEx(&cfg, wgp::wgrad_pair_kernel<false>, p);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(wgrad_pair_kernel)");
-  const int64_t total = (d + (p.geo.ones_row ? 1 : 0)) * d;
+  const int64_t total = (d + (p.geo.ones_row ? 1 : 0)) * ((d + 3) / 4);  // one thread per (4 output columns, feature row)
   wgp::wgrad_pair_reduce<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(p.partial, p.geo, gW, gb);
   NT_LAUNCH_CHECK("pair_layer_wgrad", 2);
   return NT_OK;
