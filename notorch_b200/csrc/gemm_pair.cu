@@ -60,9 +60,13 @@ static_assert(STAGE_BYTES % 1024 == 0 && W_PART_BYTES % 1024 == 0, "swizzle-128B
 
 struct Geometry {
   int d, n_tile, n_tiles, k_blocks, n_a, n_b, rows_per_cta;
-  // Long reductions (d > 1024): even and odd K-blocks accumulate into TWO tensor-memory windows that the epilogue adds in fp32.
-  // The tensor core truncates when it adds into its accumulator, so the 3xTF32 residue grows with the reduction length (1.2e-5
-  // rel-to-max at d = 2048 with one accumulator); halving the length per accumulator halves it. Costs the epilogue / MMA overlap.
+  // Long reductions (d >= 640): TWO tensor-memory windows that the epilogue adds in fp32 - the main product hi x hi goes to the
+  // first, the two small cross products (lo x hi, hi x lo) to the second. The tensor core truncates when it adds into its
+  // accumulator, so the residue of an accumulation chain grows with the number of MMAs added into it; every MMA into a window
+  // truncates the WHOLE running sum, however small its own contribution, so keeping the cross terms out of the main window cuts
+  // its chain to a third (d = 1024: 128 instead of 384 truncations; the cross window holds values 2^-11 times smaller, its
+  // truncation error is negligible). Measured: a 5-layer d = 1024 block was 1.8e-5 off the fp64 oracle with one accumulator. The
+  // first version split even / odd K-blocks instead (chains of one half). Costs the epilogue / MMA overlap.
   int split_acc;
   size_t part_bytes;  // bytes of one (hi or lo) image
 };
@@ -77,7 +81,7 @@ __host__ __device__ inline Geometry make_geometry(int d) {
   if (g.n_tile <= 256) { g.n_a = g.n_tile; g.n_b = 0; }
   else { g.n_a = ((g.n_tile / 2) + 15) / 16 * 16; g.n_b = g.n_tile - g.n_a; }
   g.rows_per_cta = g.n_tile / 2;  // n_a / 2 rows of the first MMA followed by n_b / 2 rows of the second
-  g.split_acc = (g.k_blocks > 32 && g.n_tile <= 256) ? 1 : 0;
+  g.split_acc = (g.k_blocks >= 20 && g.n_tile <= 256) ? 1 : 0;
   g.part_bytes = (size_t)g.n_tiles * g.k_blocks * g.n_tile * 128;
   return g;
 }
@@ -144,7 +148,7 @@ __device__ __forceinline__ void trace_event_t(const Params& p, int region, uint3
   }
 }
 
-template <int MODE, bool DROP, bool RELU, bool TRACE, bool BF16, bool SPLIT>  // SPLIT = two accumulators per pass (d > 1024); BF16 = bf16 operands, one kind::f16 pass; MODE 0 = K2 forward, 1 = K4a dgrad, 2 = dense forward (atom message passing); TRACE = the role-timeline build (scripts/trace_pair.py)
+template <int MODE, bool DROP, bool RELU, bool TRACE, bool BF16, bool SPLIT>  // SPLIT = main / cross-product accumulators (d >= 640, 3xTF32); BF16 = bf16 operands, one kind::f16 pass; MODE 0 = K2 forward, 1 = K4a dgrad, 2 = dense forward (atom message passing); TRACE = the role-timeline build (scripts/trace_pair.py)
 __global__ void __launch_bounds__(THREADS, 1)
 layer_gemm_pair(const Params p) {
   auto trace_event = [](const Params& pp, int region, uint32_t& cursor, int ev, int64_t tile, int aux = 0) {
@@ -341,9 +345,10 @@ layer_gemm_pair(const Params p) {
             if (elect_one()) {
               const int rem = d - kb * BLOCK_K;
               const uint32_t st0 = sbase + s * STAGE_BYTES;
-              const uint32_t col_base = SPLIT ? (uint32_t)(kb & 1) * 256u : win_base;  // odd K-blocks -> the second accumulator
-              const int kfirst = SPLIT ? kb >> 1 : kb;                                   // 0 on an accumulator's first K-block
+              const uint32_t col_base = SPLIT ? 0u : win_base;
+              const int kfirst = kb;                                   // 0 on an accumulator's first K-block
               const uint32_t d0 = tmem_base + col_base, d1 = d0 + (uint32_t)geo.n_a;
+              const uint32_t x0 = SPLIT ? d0 + 256u : d0, x1 = SPLIT ? d1 + 256u : d1;  // where the cross products accumulate
               if (BF16) {
                 const int ksteps = (p.ablate & 8) ? 0 : (rem >= BLOCK_K ? 2 : (rem + 15) / 16);  // K = 16 bf16 per MMA
                 const uint32_t a_bf = kmajor_desc_lo(st0 + OFF_A0), w_bf = kmajor_desc_lo(st0 + OFF_WHI);
@@ -368,13 +373,13 @@ layer_gemm_pair(const Params p) {
                   const uint32_t k16 = j * 2;
                   const uint32_t acc = (kfirst | j) != 0 ? 1u : 0u;
                   if (p.products == 3) {
-                    umma2_tf32_lo(d0, a_lo + k16, w_hi + k16, KMAJOR_SW128_DESC_HI, idesc_a, acc);
-                    umma2_tf32_lo(d0, a_hi + k16, w_lo + k16, KMAJOR_SW128_DESC_HI, idesc_a, 1u);
-                    umma2_tf32_lo(d0, a_hi + k16, w_hi + k16, KMAJOR_SW128_DESC_HI, idesc_a, 1u);
+                    umma2_tf32_lo(x0, a_lo + k16, w_hi + k16, KMAJOR_SW128_DESC_HI, idesc_a, acc);
+                    umma2_tf32_lo(x0, a_hi + k16, w_lo + k16, KMAJOR_SW128_DESC_HI, idesc_a, 1u);
+                    umma2_tf32_lo(d0, a_hi + k16, w_hi + k16, KMAJOR_SW128_DESC_HI, idesc_a, SPLIT ? acc : 1u);
                     if (geo.n_b > 0) {
-                      umma2_tf32_lo(d1, a_lo + k16, w_hi + woff + k16, KMAJOR_SW128_DESC_HI, idesc_b, acc);
-                      umma2_tf32_lo(d1, a_hi + k16, w_lo + woff + k16, KMAJOR_SW128_DESC_HI, idesc_b, 1u);
-                      umma2_tf32_lo(d1, a_hi + k16, w_hi + woff + k16, KMAJOR_SW128_DESC_HI, idesc_b, 1u);
+                      umma2_tf32_lo(x1, a_lo + k16, w_hi + woff + k16, KMAJOR_SW128_DESC_HI, idesc_b, acc);
+                      umma2_tf32_lo(x1, a_hi + k16, w_lo + woff + k16, KMAJOR_SW128_DESC_HI, idesc_b, 1u);
+                      umma2_tf32_lo(d1, a_hi + k16, w_hi + woff + k16, KMAJOR_SW128_DESC_HI, idesc_b, SPLIT ? acc : 1u);
                     }
                   } else {
                     umma2_tf32_lo(d0, a_hi + k16, w_hi + k16, KMAJOR_SW128_DESC_HI, idesc_a, acc);
@@ -688,7 +693,7 @@ static int launch_by_flags(const Params& p, cudaStream_t st) {
 template <int MODE>
 static int launch(const Params& p, cudaStream_t st) {
   if (p.products == 0) return launch_by_flags<MODE, true, false>(p, st);  // bf16 operands (the mode's error dwarfs the accumulator's)
-  if (p.geo.split_acc) return launch_by_flags<MODE, false, true>(p, st);  // d > 1024: two accumulators per pass
+  if (p.geo.split_acc && p.products == 3) return launch_by_flags<MODE, false, true>(p, st);  // d >= 640, 3xTF32: main / cross accumulators
   const bool drop = p.drop_p > 0.f;
   const bool relu = MODE != 0 || p.act == NT_ACT_RELU;
   if (MODE != 2 && p.trace != nullptr && !drop && relu) return launch_variant<MODE, false, true, true, false, false>(p, st);  // the role-timeline build exists for the default case only

@@ -128,7 +128,7 @@ __device__ __forceinline__ uint32_t make_idesc_pair_mn(int n, int m) {
 }
 
 template <bool DROP>
-__global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) {
+__global__ void __maxnreg__(144) wgrad_pair_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -204,29 +204,54 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
     const int row = half ? (warp & 1) * 32 + lane : warp * 32 + lane;
     const int64_t plane_rows = (int64_t)geo.m_units * 2 * TILE_M;
     float* plane = p.partial + (int64_t)split * plane_rows * geo.ld_partial;
-    const int64_t prow = i0 + row;
-    auto at = [&](int col) { return plane + (((int64_t)(o0 + col) >> 2) * plane_rows + prow) * 4; };  // col % 4 == 0
+    float* prow_base = plane + (((int64_t)o0 >> 2) * plane_rows + (i0 + row)) * 4;       // this thread's row in the unit's first column group
+    const uint32_t cg_stride = (uint32_t)plane_rows * 4u;                                 // floats between column groups (< 2^24)
+    auto at = [&](int col) { return prow_base + (uint32_t)(col >> 2) * cg_stride; };      // col % 4 == 0
     const int seg = geo.seg_kb;
     const int64_t nseg = nkb > 0 ? (nkb + seg - 1) / seg : 0;
     const uint32_t empty_leader = map_to_cta(bar_tmem_empty, 0);
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    auto drain = [&](uint32_t tcol0, int ncols, int out_col0, bool accumulate) {
+    auto drain_store = [&](uint32_t tcol0, int ncols, int out_col0) {  // first segment: the plane takes the accumulator as is
       for (int cc = 0; cc < ncols / 16; ++cc) {
         uint32_t v[16];
         tmem_ld16(lane_base + tcol0 + (uint32_t)(cc * 16), v);
-        float4 old[4];
-        if (accumulate) {
+        tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) old[q] = *reinterpret_cast<const float4*>(at(out_col0 + cc * 16 + q * 4));
-        }
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(at(out_col0 + cc * 16 + q * 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    };
+    // later segments: plane += accumulator. The plane lives in L2 (~700 clk away); the loads of chunk cc + 2 are issued before chunk
+    // cc is processed (three 64-byte register sets per thread, rotated), otherwise every 16-column chunk pays a full round trip and
+    // a drain costs more than the segment it closes (measured: +116 us per launch at BASELINE configs[1] without the ring).
+    auto drain_add = [&](uint32_t tcol0, int ncols, int out_col0) {
+      const int nch = ncols / 16;
+      float4 cur[4], nxt[4], inc[4];  // plane values of chunk cc, cc + 1 and (arriving) cc + 2: rotated by register moves, never indexed
+      auto fetch = [&](int cc, float4 (&o)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = *reinterpret_cast<const float4*>(at(out_col0 + cc * 16 + q * 4));
+      };
+      fetch(0, cur);
+      if (nch > 1) fetch(1, nxt);
+#pragma unroll 1
+      for (int cc = 0; cc < nch; ++cc) {
+        if (cc + 2 < nch) fetch(cc + 2, inc);
+        uint32_t v[16];
+        tmem_ld16(lane_base + tcol0 + (uint32_t)(cc * 16), v);
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float4 r = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-          if (accumulate) r = make_float4(old[q].x + r.x, old[q].y + r.y, old[q].z + r.z, old[q].w + r.w);
-          *reinterpret_cast<float4*>(at(out_col0 + cc * 16 + q * 4)) = r;
+          *reinterpret_cast<float4*>(at(out_col0 + cc * 16 + q * 4)) =
+              make_float4(cur[q].x + __uint_as_float(v[4 * q]), cur[q].y + __uint_as_float(v[4 * q + 1]), cur[q].z + __uint_as_float(v[4 * q + 2]),
+                          cur[q].w + __uint_as_float(v[4 * q + 3]));
+          cur[q] = nxt[q];
+          nxt[q] = inc[q];
         }
       }
+    };
+    auto drain = [&](uint32_t tcol0, int ncols, int out_col0, bool accumulate) {
+      if (accumulate) drain_add(tcol0, ncols, out_col0);
+      else drain_store(tcol0, ncols, out_col0);
     };
     for (int64_t sg = 0; sg < nseg; ++sg) {
       mbar_wait_relaxed(bar_tmem_full, (uint32_t)(sg & 1));

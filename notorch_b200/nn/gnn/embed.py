@@ -20,37 +20,51 @@ DEFAULT_NUM_BOND_TYPES = 13
 DEFAULT_HIDDEN_DIM = 256  # notorch/conf.py:11
 
 
+def _embedding_bag_sum_raw(table: Tensor, idx: Tensor) -> Tensor:
+    table = ops._require_float(table, "embedding table")
+    idx = ops._require(idx, "type indices", torch.int64, 2)
+    n, bag = idx.shape
+    T, d = table.shape
+    with torch.cuda.device(table.device):
+        out = torch.empty((n, d), dtype=table.dtype, device=table.device)
+        status = torch.zeros(1, dtype=torch.int32, device=table.device)
+        ops._run("emb:nt_embedding_bag_sum", _lib.lib().nt_embedding_bag_sum, ops._p(table), T, ops._p(idx), n, bag, d, ops._p(out), ops._p(status),
+                 _lib.NT_F32, ops._stream())
+    ops._check_status(status, "GraphEmbedding type indices")
+    return out
+
+
+def _embedding_bag_backward_raw(g: Tensor, idx: Tensor, T: int) -> Tensor:
+    n, bag = idx.shape
+    d = g.shape[1]
+    L = _lib.lib()
+    with torch.cuda.device(g.device):
+        gt = torch.empty((T, d), dtype=g.dtype, device=g.device)
+        ws = ops._workspace(g.device, L.nt_embedding_bag_backward_workspace_bytes(n, T, d), slot=2)
+        ops._run("embbwd:nt_embedding_bag_backward", L.nt_embedding_bag_backward, ops._p(g), ops._p(idx), n, bag, T, d, ops._p(gt), ops._p(ws),
+                 ws.numel(), _lib.NT_F32, ops._stream())
+    return gt
+
+
 class _EmbeddingBagSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, table: Tensor, idx: Tensor):
-        table = ops._require_float(table, "embedding table")
-        idx = ops._require(idx, "type indices", torch.int64, 2)
-        n, bag = idx.shape
-        T, d = table.shape
-        L = _lib.lib()
-        with torch.cuda.device(table.device):
-            out = torch.empty((n, d), dtype=table.dtype, device=table.device)
-            status = torch.zeros(1, dtype=torch.int32, device=table.device)
-            ops._run("emb:nt_embedding_bag_sum", L.nt_embedding_bag_sum, ops._p(table), T, ops._p(idx), n, bag, d, ops._p(out), ops._p(status),
-                     _lib.NT_F32, ops._stream())
-        ops._check_status(status, "GraphEmbedding type indices")
-        ctx.save_for_backward(idx)
-        ctx.shape = (T, d)
+        out = _embedding_bag_sum_raw(table, idx)
+        ctx.save_for_backward(idx.contiguous())
+        ctx.shape = tuple(table.shape)
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
         (idx,) = ctx.saved_tensors
-        T, d = ctx.shape
-        n, bag = idx.shape
-        g = g.contiguous()
-        L = _lib.lib()
-        with torch.cuda.device(g.device):
-            gt = torch.empty((T, d), dtype=g.dtype, device=g.device)
-            ws = ops._workspace(g.device, L.nt_embedding_bag_backward_workspace_bytes(n, T, d), slot=2)
-            ops._run("embbwd:nt_embedding_bag_backward", L.nt_embedding_bag_backward, ops._p(g), ops._p(idx), n, bag, T, d, ops._p(gt), ops._p(ws),
-                     ws.numel(), _lib.NT_F32, ops._stream())
-        return gt, None
+        return _embedding_bag_backward_raw(g.contiguous(), idx, ctx.shape[0]), None
+
+
+def embedding_bag_sum(table: Tensor, idx: Tensor) -> Tensor:
+    if ops._via_ops(table, idx):
+        ops._torch_ops()
+        return torch.ops.notorch_b200.embedding_bag_sum(table, idx)
+    return _EmbeddingBagSum.apply(table, idx)
 
 
 class GraphEmbedding(nn.Module):
@@ -69,9 +83,9 @@ class GraphEmbedding(nn.Module):
             call = object()  # the two placeholders of ONE forward call recognise each other by this token
             d, dev = wv.shape[1], wv.device
             return G.update(
-                node_feats=PendingFeats(lambda: _EmbeddingBagSum.apply(wv, node_types), (node_types.shape[0], d), wv.dtype, dev, (call, wv, node_types)),
-                edge_feats=PendingFeats(lambda: _EmbeddingBagSum.apply(we, edge_types), (edge_types.shape[0], d), we.dtype, dev, (call, we, edge_types)))
-        return G.update(node_feats=_EmbeddingBagSum.apply(wv, node_types), edge_feats=_EmbeddingBagSum.apply(we, edge_types))
+                node_feats=PendingFeats(lambda: embedding_bag_sum(wv, node_types), (node_types.shape[0], d), wv.dtype, dev, (call, wv, node_types)),
+                edge_feats=PendingFeats(lambda: embedding_bag_sum(we, edge_types), (edge_types.shape[0], d), we.dtype, dev, (call, we, edge_types)))
+        return G.update(node_feats=embedding_bag_sum(wv, node_types), edge_feats=embedding_bag_sum(we, edge_types))
 
     @property
     def num_node_types(self) -> int:

@@ -22,42 +22,51 @@ from ..ops import _p, _run, _stream, _workspace
 DEFAULT_HIDDEN_DIM = 256  # notorch/conf.py:11
 
 
+def _linear_forward_raw(x: Tensor, W: Tensor, b: Tensor | None) -> Tensor:
+    x, W = ops._require_float(x, "input"), ops._require_float(W, "weight")
+    rows, k = x.shape
+    n = W.shape[0]
+    if W.shape[1] != k:
+        raise RuntimeError(f"notorch_b200: Linear weight {tuple(W.shape)} does not match input features {k}")
+    if b is not None:
+        b = ops._require(b, "bias", torch.float32, 1)
+    with torch.cuda.device(x.device):
+        out = torch.empty((rows, n), dtype=x.dtype, device=x.device)
+        _run("head:nt_linear_forward", _lib.lib().nt_linear_forward, _p(x), _p(W), _p(b), rows, n, k, _p(out), NT_F32, _stream())
+    return out
+
+
+def _linear_backward_raw(g: Tensor, x: Tensor, W: Tensor, has_bias: bool, need_x: bool, need_w: bool):
+    rows, k = x.shape
+    n = W.shape[0]
+    L = _lib.lib()
+    gx = gW = gb = None
+    with torch.cuda.device(g.device):
+        if need_x:
+            gx = torch.empty_like(x)
+            _run("head:nt_linear_backward_input", L.nt_linear_backward_input, _p(g), _p(W), rows, n, k, _p(gx), NT_F32, _stream())
+        if need_w:
+            gW = torch.empty_like(W)
+            gb = torch.empty(n, dtype=W.dtype, device=W.device) if has_bias else None
+            ws = _workspace(g.device, L.nt_linear_backward_weight_workspace_bytes(rows, n, k), slot=4)
+            _run("head:nt_linear_backward_weight", L.nt_linear_backward_weight, _p(g), _p(x), rows, n, k, _p(gW), _p(gb), _p(ws), ws.numel(),
+                 NT_F32, _stream())
+    return gx, gW, gb
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor, W: Tensor, b: Tensor | None):
-        x, W = ops._require_float(x, "input"), ops._require_float(W, "weight")
-        rows, k = x.shape
-        n = W.shape[0]
-        if W.shape[1] != k:
-            raise RuntimeError(f"notorch_b200: Linear weight {tuple(W.shape)} does not match input features {k}")
-        if b is not None:
-            b = ops._require(b, "bias", torch.float32, 1)
-        with torch.cuda.device(x.device):
-            out = torch.empty((rows, n), dtype=x.dtype, device=x.device)
-            _run("head:nt_linear_forward", _lib.lib().nt_linear_forward, _p(x), _p(W), _p(b), rows, n, k, _p(out), NT_F32, _stream())
-        ctx.save_for_backward(x, W)
+        out = _linear_forward_raw(x, W, b)
+        ctx.save_for_backward(x.contiguous(), W.contiguous())
         ctx.has_bias = b is not None
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
         x, W = ctx.saved_tensors
-        rows, k = x.shape
-        n = W.shape[0]
-        g = g.contiguous()
-        L = _lib.lib()
-        gx = gW = gb = None
-        with torch.cuda.device(g.device):
-            if ctx.needs_input_grad[0]:
-                gx = torch.empty_like(x)
-                _run("head:nt_linear_backward_input", L.nt_linear_backward_input, _p(g), _p(W), rows, n, k, _p(gx), NT_F32, _stream())
-            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-                gW = torch.empty_like(W)
-                gb = torch.empty(n, dtype=W.dtype, device=W.device) if ctx.has_bias else None
-                ws = _workspace(g.device, L.nt_linear_backward_weight_workspace_bytes(rows, n, k), slot=4)
-                _run("head:nt_linear_backward_weight", L.nt_linear_backward_weight, _p(g), _p(x), rows, n, k, _p(gW), _p(gb), _p(ws), ws.numel(),
-                     NT_F32, _stream())
-        return gx, gW, gb
+        return _linear_backward_raw(g.contiguous(), x, W, ctx.has_bias, ctx.needs_input_grad[0],
+                                    ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]))
 
 
 class Linear(nn.Linear):
@@ -69,7 +78,11 @@ class Linear(nn.Linear):
         x = input.reshape(-1, input.shape[-1])
         if not x.is_contiguous():
             x = x.contiguous()
-        out = _LinearFn.apply(x, self.weight, self.bias)
+        if ops._via_ops(x, self.weight):
+            ops._torch_ops()
+            out = torch.ops.notorch_b200.linear(x, self.weight, self.bias)
+        else:
+            out = _LinearFn.apply(x, self.weight, self.bias)
         return out.reshape(*lead, self.out_features)
 
 

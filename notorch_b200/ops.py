@@ -20,7 +20,7 @@ __all__ = [
     "GraphCSR", "SegmentCSR", "build_segment_csr", "graph_csr", "segment_csr_for", "seg_reduce", "gather_add",
     "edge_init", "edge_to_atom", "readout", "layer", "set_gemm_mode", "get_gemm_mode", "collate_packed",
     "dropout_mask", "set_index_validation", "KernelTimer", "embed_edge_init", "embed_edge_init_supported", "carry_graph_caches",
-    "set_save_messages",
+    "set_save_messages", "set_dispatch",
 ]
 
 ACT_CODES = {
@@ -61,6 +61,32 @@ def set_gemm_mode(mode: str) -> None:
 
 def get_gemm_mode() -> str:
     return {v: k for k, v in _GEMM_MODES.items()}[_gemm_mode]
+
+
+_dispatch = os.environ.get("NOTORCH_B200_DISPATCH", "function").lower()  # "function" (autograd.Function) | "ops" (torch.ops.notorch_b200.*)
+
+
+def set_dispatch(mode: str) -> None:
+    """``"function"`` (default): the modules call the kernels through ``torch.autograd.Function`` (cheapest eager call).
+    ``"ops"``: through the registered dispatcher ops ``torch.ops.notorch_b200.*`` (``torch_ops.py``) — what tracing needs; the
+    modules switch to it by themselves while ``torch.compile`` traces them or when they see fake tensors."""
+    global _dispatch
+    assert mode in ("function", "ops")
+    _dispatch = mode
+
+
+def _via_ops(*tensors) -> bool:
+    if _dispatch == "ops" or torch.compiler.is_compiling():
+        return True
+    from torch._subclasses.fake_tensor import FakeTensor
+
+    return any(isinstance(t, FakeTensor) for t in tensors)
+
+
+def _torch_ops():
+    from . import torch_ops  # registers torch.ops.notorch_b200.* on first use
+
+    return torch_ops
 
 
 def set_index_validation(mode: str) -> None:
@@ -260,6 +286,11 @@ def _launch_build_csr(keys: Tensor, num_segments: int, outs: tuple[Tensor, Tenso
 
 def build_segment_csr(keys: Tensor, num_segments: int, what: str = "index", status: Tensor | None = None,
                       validate: bool = True) -> SegmentCSR:
+    if _via_ops(keys):
+        rowptr, perm, keys32, st = torch.ops.notorch_b200.build_csr(keys, num_segments) if _torch_ops() else None
+        if validate and not torch.compiler.is_compiling() and type(st) is Tensor:
+            _check_status(st, what)
+        return SegmentCSR(rowptr, perm, keys32, num_segments, st)
     keys = _require(keys, what, torch.int64, 1)
     dev = keys.device
     with torch.cuda.device(dev):
@@ -320,6 +351,10 @@ def _tensor_key(t: Tensor) -> tuple:
 
 
 def build_graph_csr(edge_index: Tensor, rev_index: Tensor, num_nodes: int) -> GraphCSR:
+    if _via_ops(edge_index, rev_index):
+        E = edge_index.shape[1]
+        segs = [build_segment_csr(k, S, "edge_index / rev_index") for k, S in ((edge_index[0], num_nodes), (edge_index[1], num_nodes), (rev_index, E))]
+        return GraphCSR(num_nodes, E, segs[1], segs[0], segs[2])
     edge_index = _require(edge_index, "edge_index", torch.int64, 2)
     rev_index = _require(rev_index, "rev_index", torch.int64, 1)
     if edge_index.shape[0] != 2:
@@ -530,13 +565,15 @@ class _SegExtreme(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g: Tensor):
         (arg,) = ctx.saved_tensors
-        g = g.contiguous()
-        d = g.shape[1]
-        with torch.cuda.device(g.device):
-            gx = torch.empty((ctx.n, d), dtype=g.dtype, device=g.device)
-            _run(f"{ctx.tag}bwd:nt_seg_max_backward", _lib.lib().nt_seg_max_backward, _p(g), _p(arg), _p(ctx.csr.keys32), ctx.n, d, _p(gx), NT_F32,
-                 _stream())
-        return gx, None, None, None
+        return _seg_extreme_backward_raw(g.contiguous(), arg, ctx.csr.keys32, ctx.n, ctx.tag), None, None, None
+
+
+def _seg_extreme_backward_raw(g: Tensor, arg: Tensor, keys32: Tensor, n: int, tag: str = "K1x") -> Tensor:
+    d = g.shape[1]
+    with torch.cuda.device(g.device):
+        gx = torch.empty((n, d), dtype=g.dtype, device=g.device)
+        _run(f"{tag}bwd:nt_seg_max_backward", _lib.lib().nt_seg_max_backward, _p(g), _p(arg), _p(keys32), n, d, _p(gx), NT_F32, _stream())
+    return gx
 
 
 class _GatherAdd(torch.autograd.Function):
@@ -563,6 +600,29 @@ class _GatherAdd(torch.autograd.Function):
         return (g if ctx.needs_input_grad[0] else None), gx, None
 
 
+def _embed_edge_init_raw(table_v: Tensor, table_e: Tensor, node_types: Tensor, edge_types: Tensor, src32: Tensor, V: int) -> Tensor:
+    E, d = edge_types.shape[0], table_v.shape[1]
+    with torch.cuda.device(table_v.device):
+        h0 = torch.empty((E, d), dtype=table_v.dtype, device=table_v.device)
+        status = torch.zeros(1, dtype=torch.int32, device=table_v.device)
+        _run("K0e:nt_embed_edge_init", _lib.lib().nt_embed_edge_init, _p(table_v), table_v.shape[0], _p(table_e), table_e.shape[0],
+             _p(node_types), node_types.shape[1], _p(edge_types), edge_types.shape[1], _p(src32), E, V, d, _p(h0), _p(status), NT_F32, _stream())
+    _check_status(status, "GraphEmbedding type indices")
+    return h0
+
+
+def _embed_edge_init_backward_raw(g: Tensor, node_types: Tensor, edge_types: Tensor, src32: Tensor, V: int, Tv: int, Te: int) -> tuple[Tensor, Tensor]:
+    E, d = g.shape
+    L = _lib.lib()
+    with torch.cuda.device(g.device):
+        gv = torch.empty((Tv, d), dtype=g.dtype, device=g.device)
+        ge = torch.empty((Te, d), dtype=g.dtype, device=g.device)
+        ws = _workspace(g.device, L.nt_embed_edge_init_backward_workspace_bytes(E, Tv, Te, d))
+        _run("K0ebwd:nt_embed_edge_init_backward", L.nt_embed_edge_init_backward, _p(g), _p(node_types), node_types.shape[1], _p(edge_types),
+             edge_types.shape[1], _p(src32), E, V, Tv, Te, d, _p(gv), _p(ge), _p(ws), ws.numel(), NT_F32, _stream())
+    return gv, ge
+
+
 class _EmbedEdgeInit(torch.autograd.Function):
     """GraphEmbedding fused into K0: h0 = bag(Tv, node_types)[src] + bag(Te, edge_types)
     (embed.py:20-24 + chemprop.py:83) in one kernel, both tables in shared memory; backward = one pass over g_{h0}."""
@@ -576,13 +636,7 @@ class _EmbedEdgeInit(torch.autograd.Function):
         if table_e.shape[1] != d or E != csr.E or V != csr.V:
             raise RuntimeError(f"notorch_b200: fused embedding shape mismatch: tables {tuple(table_v.shape)} / {tuple(table_e.shape)}, "
                                f"ids {tuple(node_types.shape)} / {tuple(edge_types.shape)}, graph V={csr.V} E={csr.E}")
-        with torch.cuda.device(table_v.device):
-            h0 = torch.empty((E, d), dtype=table_v.dtype, device=table_v.device)
-            status = torch.zeros(1, dtype=torch.int32, device=table_v.device)
-            _run("K0e:nt_embed_edge_init", _lib.lib().nt_embed_edge_init, _p(table_v), table_v.shape[0], _p(table_e), table_e.shape[0],
-                 _p(node_types), node_types.shape[1], _p(edge_types), edge_types.shape[1], _p(csr.src), E, V, d, _p(h0), _p(status), NT_F32,
-                 _stream())
-        _check_status(status, "GraphEmbedding type indices")
+        h0 = _embed_edge_init_raw(table_v, table_e, node_types, edge_types, csr.src, V)
         ctx.save_for_backward(node_types, edge_types)
         ctx.csr, ctx.shapes = csr, (table_v.shape, table_e.shape)
         return h0
@@ -592,14 +646,7 @@ class _EmbedEdgeInit(torch.autograd.Function):
         node_types, edge_types = ctx.saved_tensors
         (Tv, d), (Te, _) = ctx.shapes
         csr = ctx.csr
-        g = g.contiguous()
-        L = _lib.lib()
-        with torch.cuda.device(g.device):
-            gv = torch.empty((Tv, d), dtype=g.dtype, device=g.device)
-            ge = torch.empty((Te, d), dtype=g.dtype, device=g.device)
-            ws = _workspace(g.device, L.nt_embed_edge_init_backward_workspace_bytes(csr.E, Tv, Te, d))
-            _run("K0ebwd:nt_embed_edge_init_backward", L.nt_embed_edge_init_backward, _p(g), _p(node_types), node_types.shape[1], _p(edge_types),
-                 edge_types.shape[1], _p(csr.src), csr.E, csr.V, Tv, Te, d, _p(gv), _p(ge), _p(ws), ws.numel(), NT_F32, _stream())
+        gv, ge = _embed_edge_init_backward_raw(g.contiguous(), node_types, edge_types, csr.src, csr.V, Tv, Te)
         return gv, ge, None, None, None
 
 
@@ -620,6 +667,9 @@ def embed_edge_init_supported(table_v: Tensor, table_e: Tensor, node_types: Tens
 
 
 def embed_edge_init(table_v: Tensor, table_e: Tensor, node_types: Tensor, edge_types: Tensor, csr: "GraphCSR") -> Tensor:
+    if _via_ops(table_v, node_types):
+        _torch_ops()
+        return torch.ops.notorch_b200.embed_edge_init(table_v, table_e, node_types, edge_types, csr.src, csr.V)
     return _EmbedEdgeInit.apply(table_v, table_e, node_types, edge_types, csr)
 
 
@@ -733,7 +783,13 @@ def seg_reduce(x: Tensor, csr: SegmentCSR, reduce: str = "sum", scale: float = 1
     if reduce in ("max", "min"):
         if scale != 1.0:
             raise ValueError("notorch_b200: a scale factor only applies to sum / mean reductions")
+        if _via_ops(x):
+            _torch_ops()
+            return torch.ops.notorch_b200.seg_extreme(x, csr.rowptr, csr.perm, csr.keys32, csr.num_segments, reduce == "min")[0]
         return _SegExtreme.apply(x, csr, reduce == "min", tag + "x")
+    if _via_ops(x):
+        _torch_ops()
+        return torch.ops.notorch_b200.seg_reduce(x, csr.rowptr, csr.perm, csr.keys32, csr.num_segments, reduce == "mean", float(scale))
     return _SegReduce.apply(x, csr, reduce == "mean", float(scale), tag)
 
 
@@ -743,6 +799,8 @@ def gather_add(base: Tensor, x: Tensor, csr: SegmentCSR) -> Tensor:
 
 def edge_init(node_feats: Tensor, edge_feats: Tensor, csr: GraphCSR) -> Tensor:
     """K0: ``h0 = node_feats[src] + edge_feats`` (chemprop.py:83)."""
+    if _via_ops(node_feats, edge_feats):
+        return _torch_ops().edge_init_op(node_feats, edge_feats, csr)
     return _GatherAdd.apply(edge_feats, node_feats, csr.by_src)
 
 
@@ -775,6 +833,8 @@ def layer(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, *, act:
         _dropout_calls += 1
         offset = _dropout_calls
     extreme = {"max": 1, "min": 2}.get(reduce, 0)
+    if extreme == 0 and _via_ops(h, weight):
+        return _torch_ops().layer_from_csr(h, weight, bias, csr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)
     return _Layer.apply(h, weight, bias, csr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode, extreme)
 
 
@@ -821,6 +881,49 @@ def _seg_reduce_ex_raw(x: Tensor, seg: SegmentCSR, act: int, act_param: float, m
     return out
 
 
+def _atom_layer_forward_raw(h: Tensor, s_e: Tensor, W: Tensor, b: Tensor | None, acsr: AtomCSR, act: int, act_param: float, mean: bool,
+                            residual: bool, p: float, seed: int, offset: int, mode: int) -> tuple[Tensor, Tensor]:
+    h, s_e, W = _require_float(h, "node_feats"), _require_float(s_e, "edge aggregate"), _require_float(W, "weight")
+    V, d = h.shape
+    if V != acsr.V or s_e.shape != h.shape or W.shape != (d, d):
+        raise RuntimeError(f"notorch_b200: atom layer shape mismatch: h {tuple(h.shape)}, s_e {tuple(s_e.shape)}, W {tuple(W.shape)}, V={acsr.V}")
+    if mode == GEMM_FP32 or d % 4 != 0:
+        raise NotImplementedError("notorch_b200: atom message passing runs on the tensor-core path only (gemm_mode tf32x3 / tf32, d % 4 == 0)")
+    if b is not None:
+        b = _require(b, "bias", torch.float32, 1)
+    L = _lib.lib()
+    with torch.cuda.device(h.device):
+        n = _seg_reduce_ex_raw(h, acsr.nbr_in, act, act_param, mean, s_e, None, tag="A1")
+        img = _weight_image(W, False)
+        out = torch.empty_like(h)
+        _run("A2:nt_dense_forward", L.nt_dense_forward, _p(n), _p(img), _p(b), _p(h) if residual else None, V, d, p, seed, offset, _p(out),
+             NT_F32, mode, _stream())
+    return out, n
+
+
+def _atom_layer_backward_raw(g: Tensor, h: Tensor, n: Tensor, W: Tensor, has_bias: bool, acsr: AtomCSR, act: int, act_param: float, mean: bool,
+                             residual: bool, p: float, seed: int, offset: int, mode: int, need_w: bool, need_h: bool):
+    V, d = h.shape
+    L = _lib.lib()
+    gW = gb = gh = gs = None
+    with torch.cuda.device(g.device):
+        if need_w:
+            gW = torch.empty_like(W)
+            gb = torch.empty(d, dtype=W.dtype, device=W.device) if has_bias else None
+            ws = _workspace(g.device, L.nt_layer_backward_wgrad_workspace_bytes(V, d), slot=1)
+            _run("A4b:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(g), _p(n), None, None, None, None, V, V, d, act, act_param, p, seed,
+                 offset, _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream())
+        if need_h:
+            g_n = torch.empty_like(h)
+            _run("A4a:nt_layer_backward_dgrad", L.nt_layer_backward_dgrad, _p(g), _p(W), _p(_weight_image(W, True)), V, d, p, seed, offset,
+                 _p(g_n), NT_F32, mode, _stream())
+            gs = g_n  # n = s_e + reduce(...): the edge aggregate receives g_n as is
+            # mean: every incoming message of atom v carries 1 / indeg(v)
+            g_msg = _gather_add_raw(None, g_n, acsr.ident, acsr.nbr_in.rowptr, tag="A5") if mean else g_n
+            gh = _seg_reduce_ex_raw(g_msg, acsr.nbr_out, act, act_param, False, g if residual else None, h, tag="A6")
+    return gh, gs, gW, gb
+
+
 class _AtomLayer(torch.autograd.Function):
     """One depth of atom-state message passing:
 
@@ -834,50 +937,17 @@ class _AtomLayer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h: Tensor, s_e: Tensor, W: Tensor, b: Tensor | None, acsr: AtomCSR, act: int, act_param: float, mean: bool,
                 residual: bool, p: float, seed: int, offset: int, mode: int):
-        h, s_e, W = _require_float(h, "node_feats"), _require_float(s_e, "edge aggregate"), _require_float(W, "weight")
-        V, d = h.shape
-        if V != acsr.V or s_e.shape != h.shape or W.shape != (d, d):
-            raise RuntimeError(f"notorch_b200: atom layer shape mismatch: h {tuple(h.shape)}, s_e {tuple(s_e.shape)}, W {tuple(W.shape)}, V={acsr.V}")
-        if mode == GEMM_FP32 or d % 4 != 0:
-            raise NotImplementedError("notorch_b200: atom message passing runs on the tensor-core path only (gemm_mode tf32x3 / tf32, d % 4 == 0)")
-        if b is not None:
-            b = _require(b, "bias", torch.float32, 1)
-        L = _lib.lib()
-        with torch.cuda.device(h.device):
-            n = _seg_reduce_ex_raw(h, acsr.nbr_in, act, act_param, mean, s_e, None, tag="A1")
-            img = _weight_image(W, False)
-            out = torch.empty_like(h)
-            _run("A2:nt_dense_forward", L.nt_dense_forward, _p(n), _p(img), _p(b), _p(h) if residual else None, V, d, p, seed, offset, _p(out),
-                 NT_F32, mode, _stream())
-        ctx.save_for_backward(h, n, W)
+        out, n = _atom_layer_forward_raw(h, s_e, W, b, acsr, act, act_param, mean, residual, p, seed, offset, mode)
+        ctx.save_for_backward(h.contiguous(), n, W.contiguous())
         ctx.acsr, ctx.cfg, ctx.has_bias = acsr, (act, act_param, mean, residual, p, seed, offset, mode), b is not None
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
         h, n, W = ctx.saved_tensors
-        acsr = ctx.acsr
-        act, act_param, mean, residual, p, seed, offset, mode = ctx.cfg
-        V, d = h.shape
-        g = g.contiguous()
-        L = _lib.lib()
-        gW = gb = gh = gs = None
-        with torch.cuda.device(g.device):
-            if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
-                gW = torch.empty_like(W)
-                gb = torch.empty(d, dtype=W.dtype, device=W.device) if ctx.has_bias else None
-                ws = _workspace(g.device, L.nt_layer_backward_wgrad_workspace_bytes(V, d), slot=1)
-                _run("A4b:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(g), _p(n), None, None, None, None, V, V, d, act, act_param, p, seed,
-                     offset, _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream())
-            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-                g_n = torch.empty_like(h)
-                _run("A4a:nt_layer_backward_dgrad", L.nt_layer_backward_dgrad, _p(g), _p(W), _p(_weight_image(W, True)), V, d, p, seed, offset,
-                     _p(g_n), NT_F32, mode, _stream())
-                gs = g_n  # n = s_e + reduce(...): the edge aggregate receives g_n as is
-                if ctx.needs_input_grad[0]:
-                    # mean: every incoming message of atom v carries 1 / indeg(v)
-                    g_msg = _gather_add_raw(None, g_n, acsr.ident, acsr.nbr_in.rowptr, tag="A5") if mean else g_n
-                    gh = _seg_reduce_ex_raw(g_msg, acsr.nbr_out, act, act_param, False, g if residual else None, h, tag="A6")
+        need_w = ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3])
+        need_h = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gh, gs, gW, gb = _atom_layer_backward_raw(g.contiguous(), h, n, W, ctx.has_bias, ctx.acsr, *ctx.cfg, need_w, need_h)
         return gh, gs, gW, gb, None, None, None, None, None, None, None, None, None
 
 
@@ -894,6 +964,10 @@ def atom_layer(h: Tensor, s_e: Tensor, weight: Tensor, bias: Tensor | None, acsr
         seed = int(torch.empty((), dtype=torch.int64).random_().item())
         _dropout_calls += 1
         offset = _dropout_calls
+    if _via_ops(h, weight):
+        _torch_ops()
+        return torch.ops.notorch_b200.atom_layer(h, s_e, weight, bias, acsr.nbr_in.rowptr, acsr.nbr_in.perm, acsr.nbr_out.rowptr, acsr.nbr_out.perm,
+                                                 acsr.ident, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)[0]
     return _AtomLayer.apply(h, s_e, weight, bias, acsr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)
 
 
@@ -909,6 +983,15 @@ def collate_packed(num_atoms: Tensor, num_edges: Tensor, local_edge_index: Tenso
                    V: int, E: int, fixed_rev: bool = False) -> dict[str, Tensor]:
     """K-l: device-side ``BatchedGraph.from_graphs`` on packed int32 inputs already on the GPU
     (graph.py:186-223). Returns the reference's int64 index tensors plus int32 molecule row pointers."""
+    if _via_ops(num_atoms, local_edge_index):
+        _torch_ops()
+        outs = torch.ops.notorch_b200.collate(num_atoms, num_edges, local_edge_index, local_rev_index, V, E, fixed_rev)
+        return dict(zip(("edge_index", "rev_index", "batch_node_index", "batch_edge_index", "mol_atom_ptr", "mol_edge_ptr"), outs))
+    return _collate_packed_raw(num_atoms, num_edges, local_edge_index, local_rev_index, V, E, fixed_rev)
+
+
+def _collate_packed_raw(num_atoms: Tensor, num_edges: Tensor, local_edge_index: Tensor, local_rev_index: Tensor,
+                        V: int, E: int, fixed_rev: bool = False) -> dict[str, Tensor]:
     num_atoms = _require(num_atoms, "num_atoms", torch.int32, 1)
     num_edges = _require(num_edges, "num_edges", torch.int32, 1)
     lei = _require(local_edge_index, "local_edge_index", torch.int32, 2)
