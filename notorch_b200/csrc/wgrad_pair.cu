@@ -128,7 +128,7 @@ __device__ __forceinline__ uint32_t make_idesc_pair_mn(int n, int m) {
 }
 
 template <bool DROP>
-__global__ void __maxnreg__(144) wgrad_pair_kernel(const Params p) {
+__global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);

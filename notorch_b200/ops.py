@@ -347,6 +347,8 @@ class GraphCSR:
 
 
 def _tensor_key(t: Tensor) -> tuple:
+    if type(t) is not Tensor and type(t) is not torch.nn.Parameter:  # fake / traced tensors have no address: identity of the object
+        return (id(t), tuple(t.shape), 0, t.device.index)
     return (t.data_ptr(), tuple(t.shape), t._version, t.device.index)
 
 

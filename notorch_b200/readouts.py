@@ -170,6 +170,11 @@ class _SegWeightedSum(torch.autograd.Function):
 
 
 def seg_max(x: Tensor, csr: SegmentCSR) -> tuple[Tensor, Tensor]:
+    from . import ops
+
+    if ops._via_ops(x):  # tracing / fake tensors / ops.set_dispatch("ops"): the registered op (nt_seg_max is nt_seg_extreme with identity, max)
+        ops._torch_ops()
+        return torch.ops.notorch_b200.seg_extreme(x, csr.rowptr, csr.perm, csr.keys32, csr.num_segments, False)
     return _SegMax.apply(x, csr)
 
 
