@@ -79,15 +79,15 @@ embed_edge_init_kernel(const float* __restrict__ tab_v, int Tv, const float* __r
 // (a small-integer matrix, exact in TF32). One CTA per SM walks a contiguous range of 64-row blocks:
 //   * two BUILDER warps turn the ids of block b + 1 into Cnt (one thread per row: it zeroes its own column of the [types][64]
 //     count tile and bumps one cell per slot - no two threads share a cell, so no atomics);
-//   * sixteen MMA warps own up to three 8-column tiles each: per 8-row k-step they load the g fragment straight from global memory
-//     (one k-step ahead in registers), split it into TF32 hi + lo (two mma.sync.m16n8k8 per tile: the product is exact to 2^-22)
-//     and accumulate all `MT` 16-type tiles in registers;
+//   * twelve MMA warps own 32 adjacent columns each (four interleaved 8-column tiles): per 8-row k-step they load the g fragment
+//     straight from global memory (two 16-byte loads per lane, two k-steps ahead in registers), split it into TF32 hi + lo (two
+//     mma.sync.m16n8k8 per tile: the product is exact to 2^-22) and accumulate all `MT` 16-type tiles in registers;
 //   * one barrier per block hands the count tile over. Per-CTA tables, then a fixed-order sum (same kernel as above).
 // mma.sync is the warp-level tensor-core path (SASS HMMA): right for a 58 x 300 output whose M is far below a tcgen05 tile; the
 // kernel is bound by streaming g once.
-constexpr int EFM_MMA_WARPS = 16, EFM_BUILD_WARPS = 2, EFM_THREADS = (EFM_MMA_WARPS + EFM_BUILD_WARPS) * 32;
+constexpr int EFM_MMA_WARPS = 12, EFM_BUILD_WARPS = 2, EFM_THREADS = (EFM_MMA_WARPS + EFM_BUILD_WARPS) * 32;
 constexpr int EFM_ROWS = 64, EFM_LD = 68;  // rows per block; padded row length of the count tile (conflict-free fragment loads)
-constexpr int EFM_NT = 3;                   // 8-column tiles per MMA warp -> 384 columns per pass (one tile when there are 8 type tiles)
+constexpr int EFM_NT = 4;                   // 8-column MMA tiles per warp = 32 adjacent columns -> 384 columns per pass
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -95,13 +95,16 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int MT, int NT>
+// Column mapping. A warp owns 32 ADJACENT columns c0 .. c0 + 31 and runs four 8-column MMA tiles over them, interleaved: column
+// n of tile i is physical column c0 + 4 n + i. The B fragment of a lane (n = lane / 4) for all four tiles is then ONE aligned
+// 16-byte load per row (columns c0 + 4 n .. + 3) instead of four scalar loads, and the eight lanes of a row read 128 contiguous bytes.
+template <int MT>
 __global__ void __launch_bounds__(EFM_THREADS, 1)
 embed_bwd_mma_kernel(const float* __restrict__ g, const int64_t* __restrict__ node_types, int bv, const int64_t* __restrict__ edge_types, int be,
                      const int32_t* __restrict__ src, int64_t n_rows, int64_t V, int Tv, int Te, int d, int col0, int cols, int64_t blocks_per_cta,
                      int flush_blocks, float* __restrict__ partial) {
   extern __shared__ __align__(16) float cnt_smem[];  // [2][MT * 16][EFM_LD]
-  constexpr int TYPES = MT * 16;
+  constexpr int TYPES = MT * 16, NT = EFM_NT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = lane >> 2, tig = lane & 3;
   const int64_t nblocks = (n_rows + EFM_ROWS - 1) / EFM_ROWS;
@@ -140,33 +143,39 @@ embed_bwd_mma_kernel(const float* __restrict__ g, const int64_t* __restrict__ no
 #pragma unroll
       for (int x = 0; x < 4; ++x) acc[i][m][x] = 0.f;
 
-  // this warp's column tiles: tile index warp + 16 i  ->  first column n0[i] (window-relative); a tile past the window is skipped
-  int ncol[NT];
-#pragma unroll
-  for (int i = 0; i < NT; ++i) ncol[i] = (warp + EFM_MMA_WARPS * i) * 8 + grp;  // the column this lane loads (B fragment: n = grp)
-  auto load_b = [&](int64_t blk, int ks, float (&out)[NT][2]) {
-    const int64_t r = blk * EFM_ROWS + ks * 8 + tig;
-#pragma unroll
-    for (int i = 0; i < NT; ++i) {
-      const bool cok = ncol[i] < cols;
-      out[i][0] = (cok && blk < b1 && r < n_rows) ? __ldg(g + r * d + col0 + ncol[i]) : 0.f;
-      out[i][1] = (cok && blk < b1 && r + 4 < n_rows) ? __ldg(g + (r + 4) * d + col0 + ncol[i]) : 0.f;
+  const int c_lane = warp * 32 + 4 * grp;            // first of this lane's four columns (window-relative); cols % 4 == 0
+  const bool col_ok = c_lane < cols;
+  const bool warp_on = warp * 32 < cols;             // warp-uniform: any column of this warp inside the window
+  struct Frag { float4 lo, hi; };                    // rows tig and tig + 4 of a k-step, columns c_lane .. + 3
+  auto load_b = [&](int64_t kstep_global) {          // k-step index counted from this CTA's first row
+    Frag f;
+    f.lo = f.hi = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t r = b0 * EFM_ROWS + kstep_global * 8 + tig;
+    if (col_ok && r < b1 * EFM_ROWS) {
+      if (r < n_rows) f.lo = ldg4_stream(g + r * d + col0 + c_lane);
+      if (r + 4 < n_rows) f.hi = ldg4_stream(g + (r + 4) * d + col0 + c_lane);
     }
+    return f;
   };
 
   auto flush = [&](int64_t plane) {
-    // accumulator fragment: c0/c1 -> (type 16 m + grp, columns 2 tig, 2 tig + 1), c2/c3 -> type + 8
+    // accumulator fragment of tile i: c0/c1 -> (type 16 m + grp, tile columns 2 tig, 2 tig + 1), c2/c3 -> type + 8;
+    // tile column n is physical column warp * 32 + 4 n + i
     const int T = Tv + Te;
     float* dst = partial + (size_t)plane * T * cols;
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-      const int c = (warp + EFM_MMA_WARPS * i) * 8 + 2 * tig;
+      const int ca = warp * 32 + 4 * (2 * tig) + i, cb = ca + 4;
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         const int t0 = 16 * m + grp;
-        if (c < cols) {  // cols % 4 == 0 and c is even: c + 1 < cols as well
-          if (t0 < T) *reinterpret_cast<float2*>(dst + (size_t)t0 * cols + c) = make_float2(acc[i][m][0], acc[i][m][1]);
-          if (t0 + 8 < T) *reinterpret_cast<float2*>(dst + (size_t)(t0 + 8) * cols + c) = make_float2(acc[i][m][2], acc[i][m][3]);
+        if (t0 < T) {
+          if (ca < cols) dst[(size_t)t0 * cols + ca] = acc[i][m][0];
+          if (cb < cols) dst[(size_t)t0 * cols + cb] = acc[i][m][1];
+        }
+        if (t0 + 8 < T) {
+          if (ca < cols) dst[(size_t)(t0 + 8) * cols + ca] = acc[i][m][2];
+          if (cb < cols) dst[(size_t)(t0 + 8) * cols + cb] = acc[i][m][3];
         }
 #pragma unroll
         for (int x = 0; x < 4; ++x) acc[i][m][x] = 0.f;
@@ -176,8 +185,8 @@ embed_bwd_mma_kernel(const float* __restrict__ g, const int64_t* __restrict__ no
 
   if (builder && b0 < b1) build(b0, 0);
   __syncthreads();
-  float nxt[NT][2];
-  if (!builder) load_b(b0, 0, nxt);
+  Frag f1, f2;  // the fragments of the next two k-steps, in flight
+  if (!builder) { f1 = load_b(0); f2 = load_b(1); }
   // The tensor core TRUNCATES when it adds into its fp32 accumulator, so the error of a long accumulation chain grows with its
   // length: every `flush_blocks` blocks the accumulators are written out as one more partial table (70 KB each at d = 300 - cheap)
   // and restarted from zero; the partial tables are then added in fp32 (round to nearest) in fixed order.
@@ -190,15 +199,13 @@ embed_bwd_mma_kernel(const float* __restrict__ g, const int64_t* __restrict__ no
     const int buf = (int)((blk - b0) & 1);
     if (builder) {
       if (blk + 1 < b1) build(blk + 1, buf ^ 1);
-    } else {
+    } else if (warp_on) {
       const float* cnt = cnt_smem + (size_t)buf * TYPES * EFM_LD;
 #pragma unroll 1
       for (int ks = 0; ks < EFM_ROWS / 8; ++ks) {
-        float cur[NT][2];
-#pragma unroll
-        for (int i = 0; i < NT; ++i) { cur[i][0] = nxt[i][0]; cur[i][1] = nxt[i][1]; }
-        if (ks + 1 < EFM_ROWS / 8) load_b(blk, ks + 1, nxt);
-        else load_b(blk + 1, 0, nxt);
+        const Frag cur = f1;
+        f1 = f2;
+        f2 = load_b((blk - b0) * (EFM_ROWS / 8) + ks + 2);
         uint32_t a[MT][4];
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
@@ -208,20 +215,24 @@ embed_bwd_mma_kernel(const float* __restrict__ g, const int64_t* __restrict__ no
           a[m][2] = __float_as_uint(p[4]);
           a[m][3] = __float_as_uint(p[8 * EFM_LD + 4]);
         }
+        const float b_lo[NT] = {cur.lo.x, cur.lo.y, cur.lo.z, cur.lo.w}, b_hi[NT] = {cur.hi.x, cur.hi.y, cur.hi.z, cur.hi.w};
+        uint32_t h0[NT], h1[NT], l0[NT], l1[NT];
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-          if ((warp + EFM_MMA_WARPS * i) * 8 < cols) {  // warp-uniform
-            uint32_t hi0, hi1;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi0) : "f"(cur[i][0]));
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi1) : "f"(cur[i][1]));
-            const uint32_t lo0 = __float_as_uint(cur[i][0] - __uint_as_float(hi0)), lo1 = __float_as_uint(cur[i][1] - __uint_as_float(hi1));
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              mma_tf32_16x8x8(acc[i][m], a[m], hi0, hi1);
-              mma_tf32_16x8x8(acc[i][m], a[m], lo0, lo1);
-            }
-          }
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h0[i]) : "f"(b_lo[i]));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h1[i]) : "f"(b_hi[i]));
+          l0[i] = __float_as_uint(b_lo[i] - __uint_as_float(h0[i]));
+          l1[i] = __float_as_uint(b_hi[i] - __uint_as_float(h1[i]));
         }
+        // all sixteen hi products first, then the sixteen lo products: consecutive MMAs never depend on each other
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+          for (int m = 0; m < MT; ++m) mma_tf32_16x8x8(acc[i][m], a[m], h0[i], h1[i]);
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+          for (int m = 0; m < MT; ++m) mma_tf32_16x8x8(acc[i][m], a[m], l0[i], l1[i]);
       }
     }
     if (!builder && last_of_group) flush(((blk - b0) / flush_blocks) * gridDim.x + blockIdx.x);
@@ -266,9 +277,9 @@ struct EfmPlan {
 };
 
 static bool efm_plan(int64_t n_rows, int64_t T, int64_t d, EfmPlan* p) {
-  if (d % 4 != 0 || T <= 0 || T > 128 || n_rows <= 0) return false;
-  p->mt = T <= 16 ? 1 : T <= 32 ? 2 : T <= 64 ? 4 : 8;
-  const int pass_cols = EFM_MMA_WARPS * (p->mt == 8 ? 1 : EFM_NT) * 8;
+  if (d % 4 != 0 || T <= 0 || T > 64 || n_rows <= 0) return false;  // four 16-type tiles of accumulators per warp at most
+  p->mt = T <= 16 ? 1 : T <= 32 ? 2 : 4;
+  const int pass_cols = EFM_MMA_WARPS * EFM_NT * 8;
   p->cols = (int)(d < pass_cols ? d : pass_cols);
   int sms = num_sms();
   if (sms <= 0) sms = 148;
@@ -281,14 +292,14 @@ static bool efm_plan(int64_t n_rows, int64_t T, int64_t d, EfmPlan* p) {
   return true;
 }
 
-template <int MT, int NT>
+template <int MT>
 static cudaError_t efm_launch(const EfmPlan& plan, const float* g, const int64_t* node_types, int bv, const int64_t* edge_types, int be, const int32_t* src,
                               int64_t n_rows, int64_t V, int Tv, int Te, int d, int col0, int w, float* partial, cudaStream_t st) {
   const size_t smem = (size_t)2 * MT * 16 * EFM_LD * sizeof(float);
   static PerDeviceOnce once;
-  cudaError_t e = once.run([] { return cudaFuncSetAttribute(embed_bwd_mma_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * EFM_LD * 4); });
+  cudaError_t e = once.run([] { return cudaFuncSetAttribute(embed_bwd_mma_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * EFM_LD * 4); });
   if (e != cudaSuccess) return e;
-  embed_bwd_mma_kernel<MT, NT><<<plan.grid, EFM_THREADS, smem, st>>>(g, node_types, bv, edge_types, be, src, n_rows, V, Tv, Te, d, col0, w,
+  embed_bwd_mma_kernel<MT><<<plan.grid, EFM_THREADS, smem, st>>>(g, node_types, bv, edge_types, be, src, n_rows, V, Tv, Te, d, col0, w,
                                                                  plan.blocks_per_cta, plan.flush_blocks, partial);
   return cudaSuccess;
 }
@@ -309,10 +320,9 @@ int embed_bwd_mma(const float* g, const int64_t* node_types, int64_t bv, const i
     cudaError_t e;
     float* part = static_cast<float*>(workspace);
     switch (plan.mt) {
-      case 1: e = efm_launch<1, EFM_NT>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
-      case 2: e = efm_launch<2, EFM_NT>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
-      case 4: e = efm_launch<4, EFM_NT>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
-      default: e = efm_launch<8, 1>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
+      case 1: e = efm_launch<1>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
+      case 2: e = efm_launch<2>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
+      default: e = efm_launch<4>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
     }
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(embed_bwd_mma_kernel)");
     embed_edge_init_bwd_reduce<<<(unsigned)cdiv((int64_t)T * (w / 4), 256), 256, 0, st>>>(part, plan.grid, (int)Tv, (int)Te, (int)d, (int)col0, w, g_tab_v,
@@ -397,7 +407,7 @@ extern "C" int nt_embed_edge_init_backward(const void* g, const int64_t* node_ty
   }
   NT_CHECK_ARG(g && node_types && edge_types && src, "nt_embed_edge_init_backward: null pointer");
   if (!aligned16(g_table_v) || !aligned16(g_table_e) || nt_embed_edge_init_backward_workspace_bytes(E, num_node_types, num_edge_types, d) == 0) {
-    set_error("nt_embed_edge_init_backward: needs d %% 4 == 0, 16-byte aligned tables and at most 128 types in total");
+    set_error("nt_embed_edge_init_backward: needs d %% 4 == 0, 16-byte aligned tables and at most 64 types in total");
     return NT_ERR_UNSUPPORTED;
   }
   if (!workspace || !aligned16(workspace) || workspace_bytes < nt_embed_edge_init_backward_workspace_bytes(E, num_node_types, num_edge_types, d)) {

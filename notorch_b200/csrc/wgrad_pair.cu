@@ -127,6 +127,55 @@ __device__ __forceinline__ uint32_t make_idesc_pair_mn(int n, int m) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (3u << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// plane[row, cols] += accumulator[row, cols] for one thread's row: `nch` chunks of 16 columns; the plane stores a row's 4-column
+// groups `cg_stride` floats apart (layout [column / 4][row][4]). The plane lives in L2 (~700 clk away): four statically named
+// register sets hold the values of chunks cc .. cc + 3 and each is refilled with chunk cc + 4 as soon as it has been consumed (no
+// indexing, no moves - a move out of a register with a load in flight would wait for it). Without this every 16-column chunk pays a
+// full round trip and a drain costs more than the segment it closes (measured: +124 us per launch at BASELINE configs[1]).
+// Out of line on purpose: inlined into the warp-specialised kernel the register allocator spilled the in-flight loads to local
+// memory, which serialises them again.
+static __device__ __noinline__ void drain_add_rows(uint32_t taddr, int nch, float* p0, uint32_t cg_stride) {
+  const uint32_t chunk_stride = 4u * cg_stride;
+  float4 r0[4], r1[4], r2[4], r3[4];
+  auto fetch = [&](int cc, float4 (&o)[4]) {
+    const float* pc = p0 + (uint32_t)cc * chunk_stride;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = *reinterpret_cast<const float4*>(pc + (uint32_t)q * cg_stride);
+  };
+  auto consume = [&](int cc, const float4 (&o)[4]) {
+    uint32_t v[16];
+    tmem_ld16(taddr + (uint32_t)(cc * 16), v);
+    tmem_ld_wait();
+    float* pc = p0 + (uint32_t)cc * chunk_stride;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(pc + (uint32_t)q * cg_stride) =
+          make_float4(o[q].x + __uint_as_float(v[4 * q]), o[q].y + __uint_as_float(v[4 * q + 1]), o[q].z + __uint_as_float(v[4 * q + 2]),
+                      o[q].w + __uint_as_float(v[4 * q + 3]));
+  };
+  if (nch > 0) fetch(0, r0);
+  if (nch > 1) fetch(1, r1);
+  if (nch > 2) fetch(2, r2);
+  if (nch > 3) fetch(3, r3);
+#pragma unroll 1
+  for (int cc0 = 0; cc0 < nch; cc0 += 4) {
+    consume(cc0, r0);
+    if (cc0 + 4 < nch) fetch(cc0 + 4, r0);
+    if (cc0 + 1 < nch) {
+      consume(cc0 + 1, r1);
+      if (cc0 + 5 < nch) fetch(cc0 + 5, r1);
+    }
+    if (cc0 + 2 < nch) {
+      consume(cc0 + 2, r2);
+      if (cc0 + 6 < nch) fetch(cc0 + 6, r2);
+    }
+    if (cc0 + 3 < nch) {
+      consume(cc0 + 3, r3);
+      if (cc0 + 7 < nch) fetch(cc0 + 7, r3);
+    }
+  }
+}
+
 template <bool DROP>
 __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -221,34 +270,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
           *reinterpret_cast<uint4*>(at(out_col0 + cc * 16 + q * 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     };
-    // later segments: plane += accumulator. The plane lives in L2 (~700 clk away); the loads of chunk cc + 2 are issued before chunk
-    // cc is processed (three 64-byte register sets per thread, rotated), otherwise every 16-column chunk pays a full round trip and
-    // a drain costs more than the segment it closes (measured: +116 us per launch at BASELINE configs[1] without the ring).
-    auto drain_add = [&](uint32_t tcol0, int ncols, int out_col0) {
-      const int nch = ncols / 16;
-      float4 cur[4], nxt[4], inc[4];  // plane values of chunk cc, cc + 1 and (arriving) cc + 2: rotated by register moves, never indexed
-      auto fetch = [&](int cc, float4 (&o)[4]) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = *reinterpret_cast<const float4*>(at(out_col0 + cc * 16 + q * 4));
-      };
-      fetch(0, cur);
-      if (nch > 1) fetch(1, nxt);
-#pragma unroll 1
-      for (int cc = 0; cc < nch; ++cc) {
-        if (cc + 2 < nch) fetch(cc + 2, inc);
-        uint32_t v[16];
-        tmem_ld16(lane_base + tcol0 + (uint32_t)(cc * 16), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          *reinterpret_cast<float4*>(at(out_col0 + cc * 16 + q * 4)) =
-              make_float4(cur[q].x + __uint_as_float(v[4 * q]), cur[q].y + __uint_as_float(v[4 * q + 1]), cur[q].z + __uint_as_float(v[4 * q + 2]),
-                          cur[q].w + __uint_as_float(v[4 * q + 3]));
-          cur[q] = nxt[q];
-          nxt[q] = inc[q];
-        }
-      }
-    };
+    // later segments: plane += accumulator (drain_add_rows above)
+    auto drain_add = [&](uint32_t tcol0, int ncols, int out_col0) { drain_add_rows(lane_base + tcol0, ncols / 16, at(out_col0), cg_stride); };
     auto drain = [&](uint32_t tcol0, int ncols, int out_col0, bool accumulate) {
       if (accumulate) drain_add(tcol0, ncols, out_col0);
       else drain_store(tcol0, ncols, out_col0);
