@@ -40,7 +40,7 @@ def _digest() -> str:
     for f in files:
         path = f if os.path.isabs(f) else os.path.join(CSRC, f)
         with open(path, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())  # never the absolute path: the tree is copied to another location on the GPU box
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -54,8 +54,22 @@ def is_fresh() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_fresh():
         return LIB
-    nvcc = _nvcc()
     os.makedirs(BUILD, exist_ok=True)
+    # one builder at a time (torchrun starts N ranks that all import the package): the others wait, then find the library fresh
+    import fcntl
+
+    with open(os.path.join(BUILD, "lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    nvcc = _nvcc()
 
     def compile_one(src: str) -> tuple[str, str]:
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
@@ -73,10 +87,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 print(f"==== {src}\n{log}")
     objs = [o for o, _ in results]
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    tmp = LIB + ".tmp"  # link beside the target, then rename: a concurrent dlopen never sees a half-written library
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     with open(os.path.join(BUILD, "digest"), "w") as fh:
         fh.write(_digest())
     return LIB
