@@ -546,9 +546,8 @@ def run_screening(args, wl, batch):
                "e2e": {"value": world * batch * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                        "d2h_bytes_per_step": batch * d * 4, "ms_per_step": e2e_ms / args.steps},
                "screening_job": screen, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None, "kernels": kernels})
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    outs.clear()
+    _shutdown(world, graphs)
 
 
 def allreduce_parity_check(rank: int, world: int, dev) -> dict:
@@ -928,9 +927,37 @@ def run_ours(args, wl, batch):
             "eager_cuda_baseline": eager, "allreduce_check": ar_check, "kernels": kernels,
         }
         _emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    _shutdown(world, graphs)
+
+
+def _shutdown(world: int, graphs: dict) -> None:
+    """End of a multi-rank run. CUDA graphs that captured NCCL kernels must be destroyed BEFORE the communicator is (its teardown
+    otherwise waits for them: the 2-rank run printed its line and then sat in destroy_process_group until the timeout killed it);
+    and should the teardown still stall, the process leaves after 20 s - the JSON line is already on stdout."""
+    import gc
+
+    if world <= 1:
+        return
+    import torch.distributed as dist
+
+    dist.barrier()
+    torch.cuda.synchronize()
+    graphs.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    done = threading.Event()
+
+    def _destroy():
+        try:
+            dist.destroy_process_group()
+        finally:
+            done.set()
+
+    threading.Thread(target=_destroy, daemon=True).start()
+    if not done.wait(20.0):
+        print("bench.py: destroy_process_group did not return within 20 s; exiting", file=sys.stderr)
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def _emit(line: dict) -> None:
