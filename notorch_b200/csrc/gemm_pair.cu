@@ -71,6 +71,17 @@ struct Geometry {
   size_t part_bytes;  // bytes of one (hi or lo) image
 };
 
+// smallest number of 32-wide K-blocks for which the main / cross accumulators are used (NOTORCH_B200_SPLIT_MIN_KB, default 20 = d >= 640;
+// a large value switches it off for A/B timing: d = 1024 then runs 35 % faster in K2 and a 5-depth block is 1.8e-5 instead of 9.8e-6 off)
+static int split_min_kblocks() {
+  static const int v = [] {
+    const char* e = getenv("NOTORCH_B200_SPLIT_MIN_KB");
+    const int x = e ? atoi(e) : 20;
+    return x > 0 ? x : 20;
+  }();
+  return v;
+}
+
 __host__ __device__ inline Geometry make_geometry(int d) {
   Geometry g;
   g.d = d;
@@ -81,7 +92,7 @@ __host__ __device__ inline Geometry make_geometry(int d) {
   if (g.n_tile <= 256) { g.n_a = g.n_tile; g.n_b = 0; }
   else { g.n_a = ((g.n_tile / 2) + 15) / 16 * 16; g.n_b = g.n_tile - g.n_a; }
   g.rows_per_cta = g.n_tile / 2;  // n_a / 2 rows of the first MMA followed by n_b / 2 rows of the second
-  g.split_acc = (g.k_blocks >= 20 && g.n_tile <= 256) ? 1 : 0;
+  g.split_acc = 0;  // decided on the host (launch<>): needs getenv
   g.part_bytes = (size_t)g.n_tiles * g.k_blocks * g.n_tile * 128;
   return g;
 }
@@ -259,26 +270,21 @@ layer_gemm_pair(const Params p) {
           const int c0 = chunk_c0(cc), w = chunk_w(cc);
           const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(col_base + c0);
           uint32_t v[16];
-          // thread = accumulator row: 16 columns -> pieces `half * 4 .. + 3` of its 128-byte staging row (XOR-swizzled). With two
-          // accumulators per pass the second one is added through the staging row (read-modify-write of the thread's own pieces),
-          // which keeps the register footprint of the common single-accumulator case unchanged.
+          // thread = accumulator row: 16 columns -> pieces `half * 4 .. + 3` of its 128-byte staging row (XOR-swizzled)
           auto stage16 = [&](uint32_t ta, int half) {
             tmem_ld16(ta, v);
-            tmem_ld_wait();
+            if (SPLIT) {  // main + cross-product accumulators: both loads in flight together, added in registers (fp32, round to nearest)
+              uint32_t x[16];
+              tmem_ld16(ta + 256u, x);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(x[q]));
+            } else {
+              tmem_ld_wait();
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               *reinterpret_cast<uint4*>(stage + lane * 128 + (((q + 4 * half) ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            if (SPLIT) {
-              tmem_ld16(ta + 256u, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float4* slot = reinterpret_cast<float4*>(stage + lane * 128 + (((q + 4 * half) ^ (lane & 7)) << 4));
-                float4 a = *slot;
-                a.x += __uint_as_float(v[4 * q]); a.y += __uint_as_float(v[4 * q + 1]); a.z += __uint_as_float(v[4 * q + 2]); a.w += __uint_as_float(v[4 * q + 3]);
-                *slot = a;
-              }
-            }
           };
           stage16(taddr, 0);
           if (w > 16) stage16(taddr + 16, 1);
@@ -693,7 +699,7 @@ static int launch_by_flags(const Params& p, cudaStream_t st) {
 template <int MODE>
 static int launch(const Params& p, cudaStream_t st) {
   if (p.products == 0) return launch_by_flags<MODE, true, false>(p, st);  // bf16 operands (the mode's error dwarfs the accumulator's)
-  if (p.geo.split_acc && p.products == 3) return launch_by_flags<MODE, false, true>(p, st);  // d >= 640, 3xTF32: main / cross accumulators
+  if (p.products == 3 && p.geo.k_blocks >= split_min_kblocks() && p.geo.n_tile <= 256) return launch_by_flags<MODE, false, true>(p, st);  // d >= 640, 3xTF32: main / cross accumulators
   const bool drop = p.drop_p > 0.f;
   const bool relu = MODE != 0 || p.act == NT_ACT_RELU;
   if (MODE != 2 && p.trace != nullptr && !drop && relu) return launch_variant<MODE, false, true, true, false, false>(p, st);  // the role-timeline build exists for the default case only
@@ -742,7 +748,6 @@ int pair_layer_forward(const float* h, const float* n, const int32_t* src, const
   p.src = src; p.rev = rev; p.wimg = static_cast<const uint8_t*>(wimg); p.bias = bias;
   p.resid = residual ? h : nullptr; p.out = out; p.E = E; p.geo = pair::make_geometry((int)d);
   p.act = act; p.act_param = act_param; p.products = products;
-  if (products == 0) p.geo.split_acc = 0;
   pair::fill_dropout(p, drop_p, seed, offset);
   (void)V;
   p.a0 = n; p.a1 = h;
@@ -757,7 +762,6 @@ int pair_dense_forward(const float* x, const void* wimg, const float* bias, cons
   p.a0 = x; p.wimg = static_cast<const uint8_t*>(wimg); p.bias = bias; p.resid = resid; p.out = out; p.E = R;
   p.geo = pair::make_geometry((int)d);
   p.act = NT_ACT_IDENTITY; p.products = products;
-  if (products == 0) p.geo.split_acc = 0;
   pair::fill_dropout(p, drop_p, seed, offset);
   return pair::launch<2>(p, st);
 }
@@ -767,7 +771,6 @@ int pair_layer_dgrad(const float* g, const void* wimg, int64_t E, int64_t d, flo
   pair::Params p{};
   p.wimg = static_cast<const uint8_t*>(wimg); p.out = g_m; p.E = E; p.geo = pair::make_geometry((int)d);
   p.act = NT_ACT_IDENTITY; p.products = products;
-  if (products == 0) p.geo.split_acc = 0;
   pair::fill_dropout(p, drop_p, seed, offset);
   p.a0 = g;
   return pair::launch<1>(p, st);

@@ -502,6 +502,7 @@ int pair_layer_wgrad(const float* g, const float* m, int64_t E, int64_t d, float
   if (sms <= 0) sms = 148;
   wgp::Params p{};
   p.geo = wgp::make_geometry(E, (int)d, sms);
+  if (products != 3) p.geo.seg_kb = 1 << 30;  // single-pass TF32 (tf32 / bf16 modes): the operand rounding (1e-3) dwarfs the chain error - no drains
   if (gb && !p.geo.ones_row) return NT_ERR_UNSUPPORTED;
   if (workspace_bytes < pair_wgrad_workspace_bytes(E, d)) {
     set_error("pair_layer_wgrad: workspace too small");
