@@ -85,6 +85,9 @@ def parse_args():
     ap.add_argument("--graph-collective", default=os.environ.get("NOTORCH_B200_GRAPH_COLLECTIVE", "on"), choices=["on", "off"],
                     help="N > 1: capture the NCCL gradient all-reduce INSIDE the step's CUDA graph (issued from autograd hooks right after layer 0's "
                          "weight gradient, overlapped with the rest of backward) instead of launching it eagerly between two graphs")
+    ap.add_argument("--allreduce", default=os.environ.get("NOTORCH_B200_ALLREDUCE", "overlap"), choices=["overlap", "end"],
+                    help="N > 1: 'overlap' issues each gradient bucket's all-reduce from autograd hooks as soon as the bucket is final (under the "
+                         "rest of backward); 'end' runs ONE all-reduce of the whole buffer after backward")
     ap.add_argument("--no-eager-cuda-baseline", action="store_true")
     ap.add_argument("--screen-molecules", type=int, default=0, help="workload c4: also time a whole screening job of this many molecules end to end")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained-clock run after the timed steps")
@@ -574,14 +577,16 @@ def allreduce_parity_check(rank: int, world: int, dev) -> dict:
     state = {"embed": {k: v.clone() for k, v in embed.state_dict().items()}, "block": {k: v.clone() for k, v in block.state_dict().items()}}
     embed, block = embed.to(dev), block.to(dev)
     flat = FlatGradients([list(block.parameters()), list(embed.parameters())], overlap=True)
-    old_mode = ops._validate_mode
+    old_mode, old_gemm = ops._validate_mode, ops.get_gemm_mode()
     ops.set_index_validation("sync")
+    ops.set_gemm_mode("tf32x3")  # the check is about the exchange: always in the fp32-parity mode, whatever the workload runs in
     mols, nt_, et_ = problem(rank)
     G = BatchedGraph.from_packed(mols, nt_, et_, device=dev)
     flat.zero()
     Sum()(block(embed(G))).square().mean().backward()
     flat.finish()
     ops.set_index_validation(old_mode)
+    ops.set_gemm_mode(old_gemm)
     got = flat.flat.detach().cpu().double()
     out = None
     if rank == 0:
@@ -639,7 +644,7 @@ def run_ours(args, wl, batch):
     # N > 1: two buckets. The block's gradients are final after layer 0's weight gradient (K4b), i.e. before layer 0's dgrad / backward
     # epilogue and the embedding backward: their all-reduce (1.08 MB at d = 300) is issued there from an autograd hook and runs on
     # NCCL's stream under the rest of backward; the 70 KB embedding bucket follows at the end; the mean is ReduceOp.AVG (no div kernel)
-    overlap = world > 1 and (args.graph_collective == "on" or not use_graph)
+    overlap = world > 1 and args.allreduce == "overlap" and (args.graph_collective == "on" or not use_graph)
     flat = FlatGradients([list(block.parameters()), list(embed.parameters())], overlap=overlap)
     opt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=use_graph)
 
@@ -918,9 +923,10 @@ def run_ours(args, wl, batch):
             "dtype": "bf16 operands, f32 accumulate / activations" if ops.get_gemm_mode() == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(wl, batch, V, E, world),
             "run": {"gemm": ops.get_gemm_mode(), "launch": launch_mode,
-                    "collective": None if world == 1 else ("NCCL all-reduce (AVG) of 2 gradient buckets captured in the step graph, issued from autograd hooks"
-                                                           if overlap and launch_mode == "cuda_graph" else
-                                                           "NCCL all-reduce (AVG), eager" + (" between two graphs" if launch_mode == "cuda_graph" else "")),
+                    "collective": None if world == 1 else (
+                        "NCCL all-reduce (AVG) of 2 gradient buckets captured in the step graph, issued from autograd hooks" if overlap and launch_mode == "cuda_graph"
+                        else "ONE NCCL all-reduce (AVG) after backward, captured in the step graph" if launch_mode == "cuda_graph" and args.graph_collective == "on"
+                        else "NCCL all-reduce (AVG), eager" + (" between two graphs" if launch_mode == "cuda_graph" else "")),
                     "embedding": "fused into the edge initialisation (nt_embed_edge_init)" if ops._fuse_embedding else "separate kernels",
                     "step": "collate+CSR, GraphEmbedding+edge init, ChempropBlock, readout, loss, backward, grad all-reduce (N>1), fused Adam"},
             "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
