@@ -85,9 +85,10 @@ def parse_args():
     ap.add_argument("--graph-collective", default=os.environ.get("NOTORCH_B200_GRAPH_COLLECTIVE", "on"), choices=["on", "off"],
                     help="N > 1: capture the NCCL gradient all-reduce INSIDE the step's CUDA graph (issued from autograd hooks right after layer 0's "
                          "weight gradient, overlapped with the rest of backward) instead of launching it eagerly between two graphs")
-    ap.add_argument("--allreduce", default=os.environ.get("NOTORCH_B200_ALLREDUCE", "overlap"), choices=["overlap", "end"],
-                    help="N > 1: 'overlap' issues each gradient bucket's all-reduce from autograd hooks as soon as the bucket is final (under the "
-                         "rest of backward); 'end' runs ONE all-reduce of the whole buffer after backward")
+    ap.add_argument("--allreduce", default=os.environ.get("NOTORCH_B200_ALLREDUCE", "end"), choices=["overlap", "end"],
+                    help="N > 1: 'end' (default) runs ONE all-reduce of the whole buffer after backward; 'overlap' issues each gradient bucket's "
+                         "all-reduce from autograd hooks as soon as the bucket is final, under the rest of backward - measured 35 us SLOWER per step "
+                         "at N = 8: the NCCL kernel takes SMs from persistent kernels that want all 148")
     ap.add_argument("--no-eager-cuda-baseline", action="store_true")
     ap.add_argument("--screen-molecules", type=int, default=0, help="workload c4: also time a whole screening job of this many molecules end to end")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained-clock run after the timed steps")
