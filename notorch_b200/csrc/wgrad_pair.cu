@@ -134,13 +134,36 @@ __device__ __forceinline__ uint32_t make_idesc_pair_mn(int n, int m) {
 // full round trip and a drain costs more than the segment it closes (measured: +124 us per launch at BASELINE configs[1]).
 // Out of line on purpose: inlined into the warp-specialised kernel the register allocator spilled the in-flight loads to local
 // memory, which serialises them again.
+// L2 residency hints: the partial planes (19-28 MB in all) are re-read and re-written every segment while 0.7 GB of operands
+// stream past them; ncu showed the planes falling out of L2 between drains (DRAM traffic 721 -> 903 MB with the drains).
+// evict_last on the planes (and evict_first on the streamed operands, see the producers) keeps them resident.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld_plane(const float* ptr, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st_plane(float* ptr, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 static __device__ __noinline__ void drain_add_rows(uint32_t taddr, int nch, float* p0, uint32_t cg_stride) {
   const uint32_t chunk_stride = 4u * cg_stride;
+  const uint64_t keep = l2_policy_evict_last();
   float4 r0[4], r1[4], r2[4], r3[4];
   auto fetch = [&](int cc, float4 (&o)[4]) {
     const float* pc = p0 + (uint32_t)cc * chunk_stride;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) o[q] = *reinterpret_cast<const float4*>(pc + (uint32_t)q * cg_stride);
+    for (int q = 0; q < 4; ++q) o[q] = ld_plane(pc + (uint32_t)q * cg_stride, keep);
   };
   auto consume = [&](int cc, const float4 (&o)[4]) {
     uint32_t v[16];
@@ -149,9 +172,10 @@ static __device__ __noinline__ void drain_add_rows(uint32_t taddr, int nch, floa
     float* pc = p0 + (uint32_t)cc * chunk_stride;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<float4*>(pc + (uint32_t)q * cg_stride) =
-          make_float4(o[q].x + __uint_as_float(v[4 * q]), o[q].y + __uint_as_float(v[4 * q + 1]), o[q].z + __uint_as_float(v[4 * q + 2]),
-                      o[q].w + __uint_as_float(v[4 * q + 3]));
+      st_plane(pc + (uint32_t)q * cg_stride,
+               make_float4(o[q].x + __uint_as_float(v[4 * q]), o[q].y + __uint_as_float(v[4 * q + 1]), o[q].z + __uint_as_float(v[4 * q + 2]),
+                           o[q].w + __uint_as_float(v[4 * q + 3])),
+               keep);
   };
   if (nch > 0) fetch(0, r0);
   if (nch > 1) fetch(1, r1);
@@ -260,6 +284,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
     const int64_t nseg = nkb > 0 ? (nkb + seg - 1) / seg : 0;
     const uint32_t empty_leader = map_to_cta(bar_tmem_empty, 0);
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint64_t keep = l2_policy_evict_last();
     auto drain_store = [&](uint32_t tcol0, int ncols, int out_col0) {  // first segment: the plane takes the accumulator as is
       for (int cc = 0; cc < ncols / 16; ++cc) {
         uint32_t v[16];
@@ -267,7 +292,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(at(out_col0 + cc * 16 + q * 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          st_plane(at(out_col0 + cc * 16 + q * 4),
+                   make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), keep);
       }
     };
     // later segments: plane += accumulator (drain_add_rows above)
@@ -354,6 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
     // row (u & 255) >> 3, physical slot u & 7 (the 32-byte-unit XOR swizzle undone to find the feature).
     const int pt = threadIdx.x - FIRST_X_WARP * 32;  // 0..255: one unit per chunk
     constexpr int MAX_UNITS = A_CHUNKS + B_CHUNKS_MAX;  // 9
+    const uint64_t stream_pol = l2_policy_evict_first();  // m and g are read once per unit: do not let them push the partial planes out of L2
     const int n_chunks = A_CHUNKS + b_chunks;
     const int r = pt >> 3, pos = pt & 7;
     const int c16 = ((((pos >> 1) ^ (r & 3)) << 1) | (pos & 1));  // logical 16-byte chunk inside the 128-byte feature row
@@ -377,7 +404,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
           const int f = feature_of(k);
           const bool ok = e < E_i && f < d;
           const float* src = (k < A_CHUNKS ? p.m : p.g) + (ok ? (int64_t)e * d + f : 0);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + k * CHUNK_BYTES), "l"(src), "r"(ok ? 16 : 0) : "memory");
+          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst + k * CHUNK_BYTES), "l"(src), "r"(ok ? 16 : 0), "l"(stream_pol)
+                       : "memory");
         }
       }
     };

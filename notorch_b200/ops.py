@@ -287,8 +287,9 @@ def _launch_build_csr(keys: Tensor, num_segments: int, outs: tuple[Tensor, Tenso
 def build_segment_csr(keys: Tensor, num_segments: int, what: str = "index", status: Tensor | None = None,
                       validate: bool = True) -> SegmentCSR:
     if _via_ops(keys):
-        rowptr, perm, keys32, st = torch.ops.notorch_b200.build_csr(keys, num_segments) if _torch_ops() else None
-        if validate and not torch.compiler.is_compiling() and type(st) is Tensor:
+        _torch_ops()
+        rowptr, perm, keys32, st = torch.ops.notorch_b200.build_csr(keys, num_segments)
+        if validate and not torch.compiler.is_compiling() and type(st) is Tensor:  # a real verdict exists only outside tracing
             _check_status(st, what)
         return SegmentCSR(rowptr, perm, keys32, num_segments, st)
     keys = _require(keys, what, torch.int64, 1)
