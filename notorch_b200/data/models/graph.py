@@ -54,15 +54,17 @@ class PendingFeats:
 
 
 def _feats_property(name: str) -> property:
+    slot = "_" + name  # the value lives under another name than the property (self.__dict__[name] would re-enter the property under torch.compile)
+
     def getter(self):
-        v = self.__dict__[name]
+        v = getattr(self, slot)
         if isinstance(v, PendingFeats):
             v = v.materialize()
-            self.__dict__[name] = v
+            object.__setattr__(self, slot, v)
         return v
 
     def setter(self, value):
-        self.__dict__[name] = value
+        object.__setattr__(self, slot, value)
 
     return property(getter, setter)
 
@@ -81,7 +83,7 @@ class Graph(UpdateMixin):
 
     def peek(self, name: str):
         """``node_feats`` / ``edge_feats`` WITHOUT materialising a :class:`PendingFeats` placeholder."""
-        return self.__dict__[name]
+        return getattr(self, "_" + name)
 
     @property
     def num_nodes(self) -> int:

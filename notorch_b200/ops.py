@@ -403,6 +403,8 @@ def graph_csr(G, num_nodes: int | None = None) -> GraphCSR:
     """CSR bundle of a ``Graph``/``BatchedGraph``, cached on the object (``Graph.update`` makes
     shallow copies, so the cache rides along GraphEmbedding -> ChempropBlock -> Aggregation)."""
     V = len(peek_feats(G, "node_feats")) if num_nodes is None else num_nodes
+    if torch.compiler.is_compiling():  # under tracing the graph object is an input of the trace: no address-keyed cache, three build_csr ops
+        return build_graph_csr(G.edge_index, G.rev_index, V)
     key = (_tensor_key(G.edge_index), _tensor_key(G.rev_index), V)
     cached = getattr(G, "_nt_csr", None)
     if cached is not None and cached.key == key:
@@ -462,6 +464,8 @@ def graph_csr_from_tensors(edge_index: Tensor, rev_index: Tensor, num_nodes: int
 def segment_csr_for(G, attr: str, num_segments: int) -> SegmentCSR:
     """CSR of ``G.<attr>`` (e.g. ``batch_node_index``), cached on the graph object."""
     t = getattr(G, attr)
+    if torch.compiler.is_compiling():
+        return build_segment_csr(t, num_segments, attr)
     key = (_tensor_key(t), num_segments)
     cache = getattr(G, "_nt_seg_csr", None)
     if cache is None:

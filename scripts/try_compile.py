@@ -42,4 +42,6 @@ for backend in ("eager", "aot_eager"):
         out = g(G)
         print(backend, "module OK", torch.equal(out, ref), "graph breaks:", torch._dynamo.utils.counters.get("graph_break", {}))
     except Exception as e:
+        import traceback
         print(backend, "module FAILED:", type(e).__name__, str(e)[:300])
+        traceback.print_exc(limit=40)

@@ -208,3 +208,49 @@ def test_modules_through_the_dispatcher_equal_the_function_path():
             ops.set_dispatch("function")
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_torch_compile_traces_the_functional_api_and_the_modules():
+    """torch.compile (dynamo + AOT autograd, backend aot_eager: tracing, fake tensors, functionalisation, joint forward/backward graph -
+    everything but a code generator): the functional layer API compiles as ONE graph (fullgraph=True) through
+    torch.ops.notorch_b200.chemprop_layer and differentiates; ChempropBlock + read-out compile with graph breaks only at copy.copy
+    (Graph.update is a shallow copy by contract, utils.py:34-40). Same kernels underneath, so the same bits as eager."""
+    import torch._dynamo
+
+    from notorch_b200 import BatchedGraph, ops
+    from notorch_b200.nn import ChempropBlock, Sum
+
+    ops.set_index_validation("off")
+    try:
+        p = oracle_inputs(16, 64, 2, seed=3)
+        csr = ops.build_graph_csr(p["edge_index"].cuda(), p["rev_index"].cuda(), p["V"])
+        h = torch.randn(p["E"], 64, device="cuda", requires_grad=True)
+        W = (torch.randn(64, 64, device="cuda") / 8).requires_grad_(True)
+        b = torch.zeros(64, device="cuda", requires_grad=True)
+
+        def f(h, W, b):
+            return ops.layer(ops.layer(h, W, b, csr), W, b, csr).square().mean()
+
+        ref = f(h, W, b)
+        ref.backward()
+        want = (h.grad.clone(), W.grad.clone())
+        h.grad = W.grad = b.grad = None
+        torch._dynamo.reset()
+        out = torch.compile(f, backend="aot_eager", fullgraph=True)(h, W, b)
+        out.backward()
+        assert torch.equal(out, ref) and torch.equal(h.grad, want[0]) and torch.equal(W.grad, want[1])
+
+        blk = ChempropBlock(hidden_dim=64, depth=2).cuda()
+        G = BatchedGraph(p["x_v"].cuda(), p["x_e"].cuda(), p["edge_index"].cuda(), p["rev_index"].cuda(), batch_node_index=p["batch_node_index"].cuda(),
+                         batch_edge_index=p["batch_edge_index"].cuda(), size=16)
+
+        def m(G):
+            return Sum()(blk(G))
+
+        ref = m(G)
+        torch._dynamo.reset()
+        assert torch.equal(torch.compile(m, backend="aot_eager")(G), ref)
+    finally:
+        torch._dynamo.reset()
+        ops.set_index_validation("sync")
