@@ -126,6 +126,8 @@ def algorithmic_bytes(V: int, E: int, B: int, d: int, L: int, s: int = 4) -> dic
         "K6": (V + 4 * E) * d * s + 12 * E,
         "K1bwd": (V + 2 * E) * d * s + 4 * E,  # g_hL = gE + g_node[dst]
         "K3bwd": (V + B) * d * s + 4 * V,
+        "K3e": (E + B) * d * s + 4 * (B + 1),  # read-out summed straight over the molecules' edge states (K1 + K3 in one pass)
+        "K3ebwd": (E + B) * d * s + 4 * E,
         "K0e": (V * 7 + E * 2) * 8 + 4 * E + E * d * s,  # fused GraphEmbedding + edge init: type ids + src in, h0 out
         "K0ebwd": (V * 7 + E * 2) * 8 + 4 * E + E * d * s,  # one pass over g_{h0}, ids again
         "emb": 0.5 * ((V * 7 + E * 2) * 8 + (V + E) * d * s),  # two launches (atoms, bonds): average per launch

@@ -99,7 +99,7 @@ class Graph(UpdateMixin):
 
     _TENSOR_FIELDS = ("node_feats", "edge_feats", "edge_index", "rev_index")
 
-    _CACHE_ATTRS = ("_nt_csr", "_nt_seg_csr", "_nt_mol_ptr", "_nt_mol_csr")
+    _CACHE_ATTRS = ("_nt_csr", "_nt_seg_csr", "_nt_mol_ptr", "_nt_mol_csr", "_nt_mol_edge_ptr", "_nt_mol_edge_csr", "_nt_mol_atom_count")
 
     def to(self, device, non_blocking: bool = False) -> Self:
         """Move the tensors (graph.py:45-53 / :229-239 of the reference) AND whatever the kernels cached on this object: the
@@ -210,4 +210,7 @@ class BatchedGraph(Graph):
                 batch_node_index=out["batch_node_index"], batch_edge_index=out["batch_edge_index"], size=len(packed.num_atoms))
         # molecules are contiguous atom ranges: the read-out CSR needs no permutation
         G._nt_mol_ptr = out["mol_atom_ptr"]
+        # ... and contiguous edge ranges whose destination atoms all lie in the same molecule (this collation made them so): lets a Sum /
+        # Mean / Norm read-out of a sum-reduced block run straight over the edge states (agg.py here)
+        G._nt_mol_edge_ptr = out["mol_edge_ptr"]
         return G

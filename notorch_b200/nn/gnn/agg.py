@@ -28,6 +28,37 @@ def _mol_csr(G: BatchedGraph) -> ops.SegmentCSR:
     return ops.segment_csr_for(G, "batch_node_index", len(G))
 
 
+def _readout_over_edges(G: BatchedGraph, kind: str, norm: float = 100.0) -> Tensor | None:
+    """``H[b] = sum_{v in b} sum_{e: dst[e] = v} h_L[e] = sum_{e in b} h_L[e]``: when the node features are the still-uncomputed
+    edge -> atom SUM of a block (``PendingFeats`` left by ``ChempropBlock``) and the graph was collated by ``BatchedGraph.from_packed``
+    (every molecule is a contiguous range of edges whose atoms are its own), Sum / Mean / Norm run over the edge states in one
+    contiguous segmented reduction - K1 + K3 become one pass forward, and one gather backward. Returns ``None`` when it does not apply."""
+    from ...data.models.graph import PendingFeats
+
+    x = ops.peek_feats(G, "node_feats")
+    eptr = getattr(G, "_nt_mol_edge_ptr", None)
+    if not (ops._fuse_readout and isinstance(x, PendingFeats) and not x.materialized and x.origin[0] == "edge_to_atom_sum" and eptr is not None):
+        return None
+    h = x.origin[1]
+    if eptr.device != h.device:
+        return None
+    csr = getattr(G, "_nt_mol_edge_csr", None)
+    if csr is None:
+        csr = ops.SegmentCSR(eptr, None, G.batch_edge_index.to(torch.int32), len(G))
+        G._nt_mol_edge_csr = csr
+    if kind == "norm":
+        return ops.seg_reduce(h, csr, "sum", 1.0 / norm, tag="K3e")
+    H = ops.seg_reduce(h, csr, "sum", tag="K3e")
+    if kind == "mean":  # scatter_mean = sum / clamp(count, 1) (agg.py:36): the count is the molecule's ATOM count
+        cnt = getattr(G, "_nt_mol_atom_count", None)
+        if cnt is None:
+            aptr = G._nt_mol_ptr
+            cnt = (aptr[1:] - aptr[:-1]).clamp(min=1).to(h.dtype).unsqueeze(1)
+            G._nt_mol_atom_count = cnt
+        H = H / cnt
+    return H
+
+
 class Aggregation(nn.Module):
     @abstractmethod
     def forward(self, G: BatchedGraph, **kwargs) -> Tensor:
@@ -36,12 +67,14 @@ class Aggregation(nn.Module):
 
 class Sum(Aggregation):
     def forward(self, G: BatchedGraph, **kwargs) -> Tensor:
-        return ops.readout(G.node_feats, _mol_csr(G), "sum")
+        H = _readout_over_edges(G, "sum")
+        return H if H is not None else ops.readout(G.node_feats, _mol_csr(G), "sum")
 
 
 class Mean(Aggregation):
     def forward(self, G: BatchedGraph, **kwargs) -> Tensor:
-        return ops.readout(G.node_feats, _mol_csr(G), "mean")
+        H = _readout_over_edges(G, "mean")
+        return H if H is not None else ops.readout(G.node_feats, _mol_csr(G), "mean")
 
 
 class Norm(Aggregation):
@@ -52,7 +85,8 @@ class Norm(Aggregation):
         self.norm = float(norm)
 
     def forward(self, G: BatchedGraph, **kwargs) -> Tensor:
-        return ops.readout(G.node_feats, _mol_csr(G), "norm", self.norm)
+        H = _readout_over_edges(G, "norm", self.norm)
+        return H if H is not None else ops.readout(G.node_feats, _mol_csr(G), "norm", self.norm)
 
 
 class Max(Aggregation):

@@ -80,5 +80,11 @@ class ChempropBlock(nn.Module):
             fused_residual = isinstance(entry, Residual)
             layer = entry.module if fused_residual else entry
             h = layer(h, xv, G.edge_index, G.rev_index, _residual=fused_residual, _csr=csr)  # xv: only its length is used
-        atoms = ops.edge_to_atom(h, csr, self.reduce)  # K1 without activation (chemprop.py:86)
+        if self.reduce == "sum" and ops._fuse_readout and isinstance(G, Graph) and getattr(G, "_nt_mol_edge_ptr", None) is not None:
+            # K1 without activation (chemprop.py:86), deferred: a Sum / Mean / Norm read-out right behind the block sums h_L over each
+            # molecule's edges directly (one pass instead of K1 + K3); any other reader of node_feats computes them on first access
+            final_h = h
+            atoms = PendingFeats(lambda: ops.edge_to_atom(final_h, csr, "sum"), (csr.V, h.shape[1]), h.dtype, h.device, ("edge_to_atom_sum", final_h))
+        else:
+            atoms = ops.edge_to_atom(h, csr, self.reduce)  # K1 without activation (chemprop.py:86)
         return G.update(node_feats=atoms, edge_feats=h)

@@ -431,9 +431,10 @@ def carry_graph_caches(G, caches: dict, before: dict) -> None:
         moved.key = (_tensor_key(G.edge_index), _tensor_key(G.rev_index), csr.V)
         moved.source = (G.edge_index, G.rev_index)
         G._nt_csr = moved
-    ptr = caches.get("_nt_mol_ptr")
-    if ptr is not None:
-        G._nt_mol_ptr = ptr.to(dev, non_blocking=True)
+    for attr in ("_nt_mol_ptr", "_nt_mol_edge_ptr"):
+        ptr = caches.get(attr)
+        if ptr is not None:
+            setattr(G, attr, ptr.to(dev, non_blocking=True))
     seg = caches.get("_nt_seg_csr")
     if seg:
         kept = {}
@@ -658,6 +659,9 @@ class _EmbedEdgeInit(torch.autograd.Function):
 
 
 _fuse_embedding = os.environ.get("NOTORCH_B200_FUSE_EMBED", "1") != "0"
+# a Sum / Mean / Norm read-out of a sum-reduced block is a sum over each molecule's EDGES: run it over h_L directly and leave the
+# block's node_feats a placeholder that is computed only if something reads it (agg.py)
+_fuse_readout = os.environ.get("NOTORCH_B200_FUSE_READOUT", "1") != "0"
 
 
 def embed_edge_init_supported(table_v: Tensor, table_e: Tensor, node_types: Tensor, edge_types: Tensor) -> bool:

@@ -320,3 +320,49 @@ def test_weight_gradient_accuracy_does_not_degrade_with_the_number_of_edges(E, d
     err_W, err_b = rel_err(gW, ref_W), rel_err(gb, g.double().sum(0))
     print(f"[parity] K4b E={E} d={d}: gW rel-to-max {err_W:.2e}, gb {err_b:.2e}")
     assert err_W <= REL_F32 and err_b <= REL_F32
+
+
+# ---------------------------------------------------------------- read-out summed over the molecules' edges
+@pytest.mark.parametrize("kind", ["sum", "mean", "norm"])
+def test_readout_over_edges_matches_the_two_stage_path(kind):
+    """A Sum / Mean / Norm read-out right behind a sum-reduced block (chemprop.py:86 + agg.py:27,36) on a device-collated batch:
+    H[b] = sum over the molecule's edges of h_L, in ONE contiguous segmented reduction; node_feats stays a placeholder until read.
+    Against the two-stage kernels (K1 then K3; same terms, another summation order) and against the oracle, forward and backward;
+    reading node_feats afterwards yields exactly the two-stage tensor."""
+    from notorch_b200 import BatchedGraph, ops
+    from notorch_b200.data.models.graph import PendingFeats
+    from notorch_b200.nn import ChempropBlock, Mean, Norm, Sum
+
+    d, B, depth = 64, 40, 2
+    p = oracle_inputs(B, d, depth, config=1, seed=41)
+    agg = {"sum": Sum, "mean": Mean, "norm": Norm}[kind]()
+    blk = ChempropBlock(hidden_dim=d, depth=depth).cuda()
+    _load(blk, p)
+    gH = torch.randn(B, d, generator=torch.Generator().manual_seed(2)).cuda()
+    res = {}
+    for fused in (True, False):
+        ops._fuse_readout = fused
+        try:
+            blk.zero_grad()
+            G = BatchedGraph.from_packed(p["mols"], p["x_v"], p["x_e"], device="cuda")
+            G.node_feats.requires_grad_(True)
+            G1 = blk(G)
+            assert isinstance(G1.peek("node_feats"), PendingFeats) == fused
+            H = agg(G1)
+            assert isinstance(G1.peek("node_feats"), PendingFeats) == fused  # the read-out did not materialise the atoms
+            (H * gH).sum().backward()
+            res[fused] = (H.detach().clone(), G.node_feats.grad.clone(), blk.layers[0].module.update[0].weight.grad.clone(), G1.node_feats.detach().clone())
+        finally:
+            ops._fuse_readout = True
+    for a, b, what in zip(res[True][:3], res[False][:3], ("H", "grad x_v", "grad W0")):
+        assert_close(a, b, f"{what}: over edges vs two-stage", 2e-6)
+    assert torch.equal(res[True][3], res[False][3])  # node_feats read afterwards: the same K1 launch, the same bits
+    Ws, bs = [w.double() for w in p["weights"]], [b.double() for b in p["biases"]]
+    node64, _, _ = O.block_forward(p["x_v"].double(), p["x_e"].double(), p["edge_index"], p["rev_index"], Ws, bs)
+    assert_close(res[True][0], O.readout(node64, p["batch_node_index"], B, kind), f"H ({kind}) vs fp64 oracle")
+    # a graph that was NOT collated by from_packed keeps the two-stage path (its batch_edge_index is never trusted)
+    G2 = BatchedGraph(p["x_v"].cuda(), p["x_e"].cuda(), p["edge_index"].cuda(), p["rev_index"].cuda(), batch_node_index=p["batch_node_index"].cuda(),
+                      batch_edge_index=torch.zeros_like(p["batch_edge_index"]).cuda(), size=B)
+    G3 = blk(G2)
+    assert isinstance(G3.peek("node_feats"), torch.Tensor)
+    assert_close(agg(G3), res[False][0], "H on a hand-made graph", 1e-6)
