@@ -7,6 +7,8 @@
 // SEQUENTIALLY in ascending item order (no cross-lane tree over the segment), which makes K1/K3
 // bit-identical to the reference's CPU scatter_add_ and run-to-run deterministic
 // (the stock GPU path, atomicAdd in scatter_gather_elementwise_kernel, is neither).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nt {
@@ -290,15 +292,89 @@ __global__ void __launch_bounds__(ROW_THREADS) layer_bwd_epilogue(const float* _
 // an [E,d] read and a [V,d] write per depth), every edge sums the g_m rows of the outgoing edges of ITS destination atom itself,
 // through the ELL copy of the by-source CSR (same ascending order, so the value is bit-identical to K5's). The ~2.2 extra rows
 // per edge are rows its neighbours in the same molecule read too: they come from L2 / L1, not from DRAM.
+__device__ __forceinline__ int ldg_i32_v(const int32_t* p) {
+  int r;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int4 ldg_i4_v(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg4_v(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// Dependency depth is what bounds this kernel (ncu: 83 % of the warp samples wait on a long scoreboard at full occupancy): the
+// first version walked dst[e] -> ell[v] -> rows -> sum and only THEN rev_rowptr[e] -> rev_perm[j] -> row (a loop with an
+// unknown trip count, which the compiler cannot hoist) -> g[e]: five dependent memory round trips. Here every index of level
+// two (the ELL record of the destination atom AND the first inverse-rev edge) is requested together, then every row of level
+// three (<= 4 out-edge rows, the first inverse-rev row, h[e], g[e]) - three round trips. Longer segments (degree > 4, more than
+// one inverse-rev edge: the reference's atom-offset rev_index quirk) continue through the CSR as before. REVERSED: blocks walk
+// the edges from the end, so that the tail of g_m - what K4a wrote last and what is still in L2 - is read first.
 template <int AK>
-__global__ void __launch_bounds__(ROW_THREADS) layer_bwd_epilogue_fused(const float* __restrict__ g, const float* __restrict__ h,
+__global__ void __launch_bounds__(ROW_THREADS, 5) layer_bwd_epilogue_fused(const float* __restrict__ g, const float* __restrict__ h,
                                                                          const float* __restrict__ g_m, const int32_t* __restrict__ dst,
                                                                          const int32_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_perm,
                                                                          const int4* __restrict__ src_ell, const int32_t* __restrict__ rev_rowptr,
                                                                          const int32_t* __restrict__ rev_perm, const int32_t* __restrict__ dst_rowptr,
                                                                          int d, int chunks, int64_t total, int act, float act_param, int residual,
-                                                                         int mean, float* __restrict__ g_h) {
-  int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
+                                                                         int mean, int reversed, float* __restrict__ g_h) {
+  const int64_t blk = reversed ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
+  const int64_t t = blk * ROW_THREADS + threadIdx.x;
+  if (t >= total) return;
+  const int e = (int)(t / chunks);
+  const int c = (int)(t - (int64_t)e * chunks) * 4;
+  // volatile loads: the compiler otherwise sinks the independent ones (h, g, src_rowptr) below the first use of a gathered row
+  // level 1
+  const int v = ldg_i32_v(dst + e);
+  const int lo = ldg_i32_v(rev_rowptr + e), hi = ldg_i32_v(rev_rowptr + e + 1);
+  const int64_t own = (int64_t)e * d + c;
+  const float4 hv = ldg4_stream(h + own);
+  float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (residual) gv = ldg4_stream(g + own);
+  // level 2
+  const int4 nb = ldg_i4_v(src_ell + v);
+  const int r0 = lo < hi ? ldg_i32_v(rev_perm + lo) : -1;
+  const int slo = ldg_i32_v(src_rowptr + v), shi = ldg_i32_v(src_rowptr + v + 1);
+  float cnt = 1.f;
+  if (mean) cnt = (float)max(ldg_i32_v(dst_rowptr + v + 1) - ldg_i32_v(dst_rowptr + v), 1);
+  // level 3
+  const int id[4] = {nb.x, nb.y, nb.z, nb.w};
+  float4 row[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (id[u] >= 0) row[u] = ldg4_v(g_m + (int64_t)id[u] * d + c);
+  float4 sub = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r0 >= 0) sub = ldg4_v(g_m + (int64_t)r0 * d + c);  // 0 + x == x: same bits as the accumulation from zero
+  __syncwarp(__activemask());  // scheduling fence: every load above is issued before the first use below
+  float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (id[u] >= 0) ga = add4(ga, row[u]);
+  for (int j = slo + 4; j < shi; ++j) ga = add4(ga, ldg4(g_m + (int64_t)__ldg(src_perm + j) * d + c));
+  if (mean) ga = make_float4(ga.x / cnt, ga.y / cnt, ga.z / cnt, ga.w / cnt);
+  for (int j = lo + 1; j < hi; ++j) sub = add4(sub, ldg4(g_m + (int64_t)__ldg(rev_perm + j) * d + c));
+  float4 r = make_float4(seg_act_bwd<AK>(hv.x, act, act_param) * (ga.x - sub.x), seg_act_bwd<AK>(hv.y, act, act_param) * (ga.y - sub.y),
+                         seg_act_bwd<AK>(hv.z, act, act_param) * (ga.z - sub.z), seg_act_bwd<AK>(hv.w, act, act_param) * (ga.w - sub.w));
+  if (residual) r = add4(gv, r);
+  stg4(g_h + own, r);
+}
+
+// the first form (kept for A/B timing: NOTORCH_B200_K6_VARIANT=0)
+template <int AK>
+__global__ void __launch_bounds__(ROW_THREADS) layer_bwd_epilogue_fused_v0(const float* __restrict__ g, const float* __restrict__ h,
+                                                                            const float* __restrict__ g_m, const int32_t* __restrict__ dst,
+                                                                            const int32_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_perm,
+                                                                            const int4* __restrict__ src_ell, const int32_t* __restrict__ rev_rowptr,
+                                                                            const int32_t* __restrict__ rev_perm, const int32_t* __restrict__ dst_rowptr,
+                                                                            int d, int chunks, int64_t total, int act, float act_param, int residual,
+                                                                            int mean, int reversed, float* __restrict__ g_h) {
+  const int64_t blk = reversed ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
+  const int64_t t = blk * ROW_THREADS + threadIdx.x;
   if (t >= total) return;
   const int e = (int)(t / chunks);
   const int c = (int)(t - (int64_t)e * chunks) * 4;
@@ -497,15 +573,24 @@ extern "C" int nt_layer_backward_epilogue_fused(const void* g, const void* h, co
   const int64_t total = E * chunks;
   const unsigned grid = (unsigned)cdiv(total, ROW_THREADS);
   const int4* ell4 = reinterpret_cast<const int4*>(src_ell);
-  if (act == NT_ACT_IDENTITY)
-    layer_bwd_epilogue_fused<0><<<grid, ROW_THREADS, 0, st>>>(gf, hf, gm, dst, src_rowptr, src_perm, ell4, rev_rowptr, rev_perm, dst_rowptr, (int)d, chunks,
-                                                              total, act, act_param, residual, mean, out);
-  else if (act == NT_ACT_RELU)
-    layer_bwd_epilogue_fused<1><<<grid, ROW_THREADS, 0, st>>>(gf, hf, gm, dst, src_rowptr, src_perm, ell4, rev_rowptr, rev_perm, dst_rowptr, (int)d, chunks,
-                                                              total, act, act_param, residual, mean, out);
-  else
-    layer_bwd_epilogue_fused<2><<<grid, ROW_THREADS, 0, st>>>(gf, hf, gm, dst, src_rowptr, src_perm, ell4, rev_rowptr, rev_perm, dst_rowptr, (int)d, chunks,
-                                                              total, act, act_param, residual, mean, out);
+  // NOTORCH_B200_K6_VARIANT (A/B timing; read per call): bit 0 = hoisted index loads (default on), bit 1 = reversed block order (default on)
+  const char* ve = getenv("NOTORCH_B200_K6_VARIANT");
+  const int variant = ve ? atoi(ve) : 3;
+  const int reversed = (variant >> 1) & 1;
+  const int ak = act == NT_ACT_IDENTITY ? 0 : act == NT_ACT_RELU ? 1 : 2;
+#define NT_K6_LAUNCH(KERNEL, AK)                                                                                                              \
+  KERNEL<AK><<<grid, ROW_THREADS, 0, st>>>(gf, hf, gm, dst, src_rowptr, src_perm, ell4, rev_rowptr, rev_perm, dst_rowptr, (int)d, chunks, total, act, \
+                                           act_param, residual, mean, reversed, out)
+  if (variant & 1) {
+    if (ak == 0) NT_K6_LAUNCH(layer_bwd_epilogue_fused, 0);
+    else if (ak == 1) NT_K6_LAUNCH(layer_bwd_epilogue_fused, 1);
+    else NT_K6_LAUNCH(layer_bwd_epilogue_fused, 2);
+  } else {
+    if (ak == 0) NT_K6_LAUNCH(layer_bwd_epilogue_fused_v0, 0);
+    else if (ak == 1) NT_K6_LAUNCH(layer_bwd_epilogue_fused_v0, 1);
+    else NT_K6_LAUNCH(layer_bwd_epilogue_fused_v0, 2);
+  }
+#undef NT_K6_LAUNCH
   NT_LAUNCH_CHECK("nt_layer_backward_epilogue_fused", 1);
   return NT_OK;
 }

@@ -8,8 +8,8 @@
 // feature rows of m plus HALF of the g columns, i.e. 9 instead of 14 chunks per 16 edges at d = 300 (8 instead of 12 at
 // d = 1024), which lets a K-block cover 32 edges in the same shared memory: twice the MMA work (M = 256) per handshake.
 //
-// Roles per CTA (448 threads): warps 0-3 epilogue (drain TMEM once at the end), warp 4 MMA issuer (leader CTA only; both
-// CTAs allocate tensor memory), warp 5 idle, warps 6-13 producers (cp.async copies of "their" 16-byte units, STAGES - 1
+// Roles per CTA (448 threads): warps 0-3 epilogue (drain the accumulator of every segment, see "accumulator windows" below),
+// warp 4 MMA issuer (leader CTA only; both CTAs allocate tensor memory), warp 5 idle, warps 6-13 producers (cp.async copies of "their" 16-byte units, STAGES - 1
 // K-blocks ahead, then the TF32 hi / lo split in place - a thread only touches its own units, so the raw data needs no
 // barrier). Barriers: ready[s] lives in the leader (16 producer warps arrive, the peer's remotely), empty[s] and tmem_full
 // are signalled in both CTAs by tcgen05.commit ... multicast::cluster.
@@ -213,10 +213,21 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
   const bool leader = rank == 0;
   const uint32_t bar_ready = sbase + OFF_BAR;         // [STAGES] (leader's copy is the live one)
   const uint32_t bar_empty = bar_ready + 8 * STAGES;  // [STAGES]
-  const uint32_t bar_tmem_full = bar_empty + 8 * STAGES;
-  const uint32_t bar_tmem_empty = bar_tmem_full + 8;  // leader's copy is the live one: all 8 epilogue warps of the pair arrive
-  const uint32_t tmem_slot = bar_tmem_empty + 8;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * STAGES + 2));
+  // Accumulator windows. A segment's accumulator is drained while the NEXT segment's MMAs already run into another window of
+  // tensor memory (segment parity w): with one window the issuer stood still for the whole drain (~8.8 k clk of every ~31 k clk
+  // segment at d = 300: +51 us per launch).
+  //   * at most 256 columns per segment (N tile <= 256, or a half-height unit): windows [0, 256) and [256, 512), no wait at all
+  //     beyond "the drain of segment s - 2 is over";
+  //   * N = 128 + 192 (d = 300): 640 columns do not exist, so the 192-column accumulator of MMA "b" alternates between [0, 192)
+  //     and [320, 512) and the 128-column accumulator of MMA "a" stays at [192, 320). The last K-block of a segment issues its
+  //     "a" MMAs first and commits them on their own barrier, the first K-block of the next segment issues its "b" MMAs first:
+  //     the epilogue drains "a" under those ~2.4 k clk of "b" work and only the rest of that drain is exposed.
+  const uint32_t bar_tmem_full = bar_empty + 8 * STAGES;  // [2], per window
+  const uint32_t bar_tmem_empty = bar_tmem_full + 16;     // [2]; leader's copy is the live one: all 8 epilogue warps of the pair arrive
+  const uint32_t bar_a_full = bar_tmem_empty + 16;        // the single-buffered "a" accumulator: every segment
+  const uint32_t bar_a_free = bar_a_full + 8;             // leader's copy is the live one
+  const uint32_t tmem_slot = bar_a_free + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * STAGES + 6));
 
   const Geometry& geo = p.geo;
   const int d = geo.d;
@@ -247,14 +258,19 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
   int64_t kb_hi = kb_lo + per_split;
   if (kb_hi > geo.kb_total) kb_hi = geo.kb_total;
   const int64_t nkb = kb_hi > kb_lo ? kb_hi - kb_lo : 0;
+  const bool split_ab = !half && geo.n_b > 0;  // "a" single-buffered at [192, 320), "b" alternating (see the barriers below)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_ready + 8 * s, 2 * NUM_X_WARPS);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_tmem_full, 1);
-    mbar_init(bar_tmem_empty, 2 * NUM_EPI_WARPS);
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(bar_tmem_full + 8 * w, 1);
+      mbar_init(bar_tmem_empty + 8 * w, 2 * NUM_EPI_WARPS);
+    }
+    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_free, 2 * NUM_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) {
@@ -302,24 +318,38 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
       if (accumulate) drain_add(tcol0, ncols, out_col0);
       else drain_store(tcol0, ncols, out_col0);
     };
-    for (int64_t sg = 0; sg < nseg; ++sg) {
-      mbar_wait_relaxed(bar_tmem_full, (uint32_t)(sg & 1));
-      tc_fence_after();
-      if (!half) {
-        drain(0u, geo.n_tile, 0, sg > 0);
-      } else {
-        const int hi_half = warp >> 1;
-        drain(0u, geo.n_a / 2, hi_half * (geo.n_a / 2), sg > 0);
-        if (geo.n_b > 0) drain((uint32_t)geo.n_a, geo.n_b / 2, geo.n_a + hi_half * (geo.n_b / 2), sg > 0);
+    const uint32_t a_free_leader = map_to_cta(bar_a_free, 0);
+    auto arrive_leader = [&](uint32_t local_bar, uint32_t leader_bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(local_bar);
+        else mbar_arrive_cluster(leader_bar);
       }
-      if (sg + 1 < nseg) {  // hand the accumulator back: the next segment's first MMA overwrites it
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (leader) mbar_arrive(bar_tmem_empty);
-          else mbar_arrive_cluster(empty_leader);
+    };
+    for (int64_t sg = 0; sg < nseg; ++sg) {
+      const uint32_t w = (uint32_t)(sg & 1), wph = (uint32_t)((sg >> 1) & 1);
+      if (split_ab) {
+        mbar_wait_relaxed(bar_a_full, w);
+        tc_fence_after();
+        drain(192u, geo.n_a, 0, sg > 0);
+        if (sg + 1 < nseg) arrive_leader(bar_a_free, a_free_leader);  // the next segment's "a" MMAs overwrite [192, 320)
+        mbar_wait_relaxed(bar_tmem_full + 8 * w, wph);
+        tc_fence_after();
+        drain(w ? 320u : 0u, geo.n_b, geo.n_a, sg > 0);
+      } else {
+        mbar_wait_relaxed(bar_tmem_full + 8 * w, wph);
+        tc_fence_after();
+        const uint32_t wb = w * 256u;
+        if (!half) {
+          drain(wb, geo.n_tile, 0, sg > 0);
+        } else {
+          const int hi_half = warp >> 1;
+          drain(wb, geo.n_a / 2, hi_half * (geo.n_a / 2), sg > 0);
+          if (geo.n_b > 0) drain(wb + (uint32_t)geo.n_a, geo.n_b / 2, geo.n_a + hi_half * (geo.n_b / 2), sg > 0);
         }
       }
+      if (sg + 2 < nseg) arrive_leader(bar_tmem_empty + 8 * w, empty_leader + 8 * w);  // segment sg + 2 reuses this window
     }
     if (nkb == 0 && (!half || warp < 2)) {
       for (int c = 0; c < geo.n_tile; c += 4) *reinterpret_cast<float4*>(at(c)) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -332,42 +362,60 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
       const uint32_t idesc_b = make_idesc_pair_mn(geo.n_b > 0 ? geo.n_b : 64, mma_m);
       int s = 0;
       uint32_t ph = 0;
-#pragma unroll 1
       const int seg = geo.seg_kb;
       int kb_in_seg = 0;
       uint32_t seg_idx = 0;
+      const uint32_t boff = (uint32_t)(ha / 32) * (CHUNK_BYTES >> 4);  // this CTA's columns of the second MMA follow its ha / 32 chunks of the first
+      const bool three = p.products == 3, no_mma = (p.ablate & 1) != 0;
+      // the MMAs of K-block stage `s` into accumulator `dacc` ("a": B columns from chunk 0, "b": from chunk ha / 32); one elected lane
+      auto issue_part = [&](int s_, uint32_t dacc, uint32_t bsel, uint32_t idesc, int kbs) {
+        const uint32_t st0 = sbase + s_ * STAGE_BYTES;
+        const uint32_t a_hi = mnmajor_desc_lo(st0, CHUNK_BYTES), b_hi = mnmajor_desc_lo(st0 + A_CHUNKS * CHUNK_BYTES, CHUNK_BYTES) + bsel;
+        const uint32_t a_lo = mnmajor_desc_lo(st0 + PART_BYTES, CHUNK_BYTES), b_lo = mnmajor_desc_lo(st0 + PART_BYTES + A_CHUNKS * CHUNK_BYTES, CHUNK_BYTES) + bsel;
+#pragma unroll
+        for (int j = 0; j < BLOCK_E / 8; ++j) {
+          const uint32_t k16 = j * (1024u >> 4);  // next 8 edges = the next two 4-row swizzle atoms of every chunk
+          const uint32_t acc = (kbs | j) != 0 ? 1u : 0u;
+          if (no_mma) {
+          } else if (three) {
+            umma2_tf32_lo(dacc, a_lo + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc, acc);
+            umma2_tf32_lo(dacc, a_hi + k16, b_lo + k16, MNMAJOR_SW128B32_DESC_HI, idesc, 1u);
+            umma2_tf32_lo(dacc, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc, 1u);
+          } else {
+            umma2_tf32_lo(dacc, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc, acc);
+          }
+        }
+      };
+#pragma unroll 1
       for (int64_t kb = 0; kb < nkb; ++kb) {
-        if (kb_in_seg == 0 && kb > 0) mbar_wait(bar_tmem_empty, (seg_idx - 1) & 1);  // both CTAs' epilogues have drained the previous segment
+        const uint32_t w = seg_idx & 1u;
+        // window w was last used by segment seg_idx - 2: both CTAs' epilogues must have drained it
+        if (kb_in_seg == 0 && seg_idx >= 2) mbar_wait(bar_tmem_empty + 8 * w, ((seg_idx >> 1) - 1u) & 1u);
         mbar_wait(bar_ready + 8 * s, ph);
         tc_fence_after();
         const bool seg_end = kb_in_seg + 1 == seg || kb == nkb - 1;
-        if (elect_one()) {
-          const uint32_t st0 = sbase + s * STAGE_BYTES;
-          const uint32_t a_hi = mnmajor_desc_lo(st0, CHUNK_BYTES), b_hi = mnmajor_desc_lo(st0 + A_CHUNKS * CHUNK_BYTES, CHUNK_BYTES);
-          const uint32_t a_lo = mnmajor_desc_lo(st0 + PART_BYTES, CHUNK_BYTES), b_lo = mnmajor_desc_lo(st0 + PART_BYTES + A_CHUNKS * CHUNK_BYTES, CHUNK_BYTES);
-          const uint32_t d1 = tmem_base + (uint32_t)geo.n_a;
-          const uint32_t boff = (uint32_t)(ha / 32) * (CHUNK_BYTES >> 4);  // this CTA's columns of the second MMA follow its ha / 32 chunks of the first
-#pragma unroll
-          for (int j = 0; j < BLOCK_E / 8; ++j) {
-            const uint32_t k16 = j * (1024u >> 4);  // next 8 edges = the next two 4-row swizzle atoms of every chunk
-            const uint32_t acc = (kb_in_seg | j) != 0 ? 1u : 0u;
-            if (p.ablate & 1) {
-            } else if (p.products == 3) {
-              umma2_tf32_lo(tmem_base, a_lo + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, acc);
-              umma2_tf32_lo(tmem_base, a_hi + k16, b_lo + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, 1u);
-              umma2_tf32_lo(tmem_base, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, 1u);
-              if (geo.n_b > 0) {
-                umma2_tf32_lo(d1, a_lo + k16, b_hi + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, acc);
-                umma2_tf32_lo(d1, a_hi + k16, b_lo + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, 1u);
-                umma2_tf32_lo(d1, a_hi + k16, b_hi + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, 1u);
-              }
-            } else {
-              umma2_tf32_lo(tmem_base, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc_a, acc);
-              if (geo.n_b > 0) umma2_tf32_lo(d1, a_hi + k16, b_hi + boff + k16, MNMAJOR_SW128B32_DESC_HI, idesc_b, acc);
-            }
+        const uint32_t d0 = tmem_base + (split_ab ? 192u : w * 256u);                                   // MMA "a"
+        const uint32_t d1 = tmem_base + (split_ab ? (w ? 320u : 0u) : w * 256u + (uint32_t)geo.n_a);   // MMA "b"
+        if (split_ab && kb_in_seg == 0 && seg_idx > 0) {
+          // first K-block of a segment: "b" first (its window is free), then wait until the epilogue has drained "a"
+          if (elect_one()) issue_part(s, d1, boff, idesc_b, 0);
+          __syncwarp();
+          mbar_wait(bar_a_free, (seg_idx - 1u) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_part(s, d0, 0u, idesc_a, 0);
+            if (seg_end) umma2_commit_both(bar_a_full);
+            umma2_commit_both(bar_empty + 8 * s);
+            if (seg_end) umma2_commit_both(bar_tmem_full + 8 * w);
           }
+        } else if (elect_one()) {
+          // "a" before "b"; in the last K-block of a segment "a" is committed on its own barrier so that its drain starts under
+          // the "b" MMAs
+          issue_part(s, d0, 0u, idesc_a, kb_in_seg);
+          if (split_ab && seg_end) umma2_commit_both(bar_a_full);
+          if (geo.n_b > 0) issue_part(s, d1, boff, idesc_b, kb_in_seg);
           umma2_commit_both(bar_empty + 8 * s);
-          if (seg_end) umma2_commit_both(bar_tmem_full);
+          if (seg_end) umma2_commit_both(bar_tmem_full + 8 * w);
         }
         __syncwarp();
         if (seg_end) { kb_in_seg = 0; ++seg_idx; } else ++kb_in_seg;

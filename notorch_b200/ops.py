@@ -36,6 +36,7 @@ ACT_CODES = {
 _GEMM_MODES = {"tf32x3": GEMM_TF32X3, "fp32": GEMM_FP32, "tf32": GEMM_TF32, "bf16": GEMM_BF16}
 _gemm_mode = _GEMM_MODES[os.environ.get("NOTORCH_B200_GEMM", "tf32x3").lower()]
 _validate_mode = os.environ.get("NOTORCH_B200_VALIDATE", "sync").lower()  # "sync" | "deferred" | "off"
+_side_wprep = os.environ.get("NOTORCH_B200_SIDE_WPREP", "1") != "0"  # weight images (forward + transposed) filled on a side stream under K1
 _parallel_csr = os.environ.get("NOTORCH_B200_PARALLEL_CSR", "1") != "0"  # by_src / by_dst / by_rev built on three streams
 _fuse_k5_k6 = os.environ.get("NOTORCH_B200_FUSE_K5K6", "1") != "0"  # backward epilogue sums the outgoing-edge gradients itself (no K5 launch)
 
@@ -519,13 +520,21 @@ def _gather_add_raw(base: Tensor | None, x: Tensor, idx32: Tensor, mean_rowptr: 
     return out
 
 
-def _weight_image(W: Tensor, transpose: bool) -> Tensor | None:
+def _weight_image_alloc(W: Tensor) -> Tensor | None:
     if _gemm_mode == GEMM_FP32 or W.shape[0] % 4 != 0:
         return None
-    L = _lib.lib()
-    d = W.shape[0]
-    img = torch.empty(L.nt_weight_image_bytes(d), dtype=torch.uint8, device=W.device)
-    _run("Wprep:nt_weight_prepare", L.nt_weight_prepare, _p(W), d, int(transpose), _p(img), NT_BF16 if _gemm_mode == GEMM_BF16 else NT_F32, _stream())
+    return torch.empty(_lib.lib().nt_weight_image_bytes(W.shape[0]), dtype=torch.uint8, device=W.device)
+
+
+def _weight_image_fill(W: Tensor, transpose: bool, img: Tensor | None) -> None:
+    if img is not None:
+        _run("Wprep:nt_weight_prepare", _lib.lib().nt_weight_prepare, _p(W), W.shape[0], int(transpose), _p(img),
+             NT_BF16 if _gemm_mode == GEMM_BF16 else NT_F32, _stream())
+
+
+def _weight_image(W: Tensor, transpose: bool) -> Tensor | None:
+    img = _weight_image_alloc(W)
+    _weight_image_fill(W, transpose, img)
     return img
 
 
@@ -689,18 +698,42 @@ _dropout_calls = 0
 
 def _layer_forward_raw(h: Tensor, W: Tensor, b: Tensor | None, csr: GraphCSR, act: int, act_param: float, mean: bool, residual: bool,
                        p: float, seed: int, offset: int, mode: int, save_m: bool,
-                       extreme: int = 0) -> tuple[Tensor, Tensor | None, Tensor, Tensor | None]:
+                       extreme: int = 0, img_t_out: list | None = None) -> tuple[Tensor, Tensor | None, Tensor, Tensor | None]:
     """K1 + K2 of one depth on raw tensors (no autograd): returns (h', m or None, n, arg or None).
-    ``extreme``: 0 = sum / mean (``mean``), 1 = max, 2 = min — K1 is then the arg-reduction and ``arg`` its [V, d] argument rows."""
+    ``extreme``: 0 = sum / mean (``mean``), 1 = max, 2 = min — K1 is then the arg-reduction and ``arg`` its [V, d] argument rows.
+    ``img_t_out``: a list that receives the weight image of the TRANSPOSED weight (what K4a reads), prepared here, beside the forward
+    image, on a side stream under K1 — the two small launches are then off the critical path of both passes."""
     E, d = h.shape
     L = _lib.lib()
     with torch.cuda.device(h.device):
         arg = None
+        img = img_t = None
+        join = None
+        use_img = mode != GEMM_FP32
+        if use_img and _side_wprep and _timer is None and E > 0:
+            # buffers come from the caller's stream (it is the one that reads and frees them); only the two fills run on the side
+            img = _weight_image_alloc(W)
+            img_t = _weight_image_alloc(W) if img_t_out is not None else None
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side = _side_stream(h.device, 3)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                _weight_image_fill(W, False, img)
+                _weight_image_fill(W, True, img_t)
+                join = torch.cuda.Event()
+                join.record(side)
         if extreme:
             n, arg = _seg_extreme_raw(h, csr.by_dst, act, act_param, extreme == 2)
         else:
             n = _seg_reduce_raw(h, csr.by_dst, act, act_param, mean, tag="K1")
-        img = _weight_image(W, False) if mode != GEMM_FP32 else None
+        if join is not None:
+            torch.cuda.current_stream().wait_event(join)
+        elif use_img:
+            img = _weight_image(W, False)
+        if img_t_out is not None and img_t is not None:
+            img_t_out.append(img_t)
         out = torch.empty_like(h)
         m = torch.empty_like(h) if save_m else None
         _run("K2:nt_layer_forward", L.nt_layer_forward, _p(h), _p(n), _p(csr.src), _p(csr.rev), _p(W), _p(img), _p(b), E, csr.V, d, act,
@@ -710,8 +743,10 @@ def _layer_forward_raw(h: Tensor, W: Tensor, b: Tensor | None, csr: GraphCSR, ac
 
 def _layer_backward_raw(g: Tensor, h: Tensor, m: Tensor | None, n: Tensor | None, W: Tensor, has_bias: bool, csr: GraphCSR, act: int,
                         act_param: float, mean: bool, residual: bool, p: float, seed: int, offset: int, mode: int, need_w: bool,
-                        need_h: bool, arg: Tensor | None = None) -> tuple[Tensor | None, Tensor | None, Tensor | None]:
-    """K4b, K4a, K5 + K6 of one depth on raw tensors: returns (g_h, g_W, g_b). ``arg``: argument rows of a max / min forward."""
+                        need_h: bool, arg: Tensor | None = None,
+                        img_t: Tensor | None = None) -> tuple[Tensor | None, Tensor | None, Tensor | None]:
+    """K4b, K4a, K5 + K6 of one depth on raw tensors: returns (g_h, g_W, g_b). ``arg``: argument rows of a max / min forward;
+    ``img_t``: the transposed weight image if the forward pass already prepared it."""
     E, d = h.shape
     g = g.contiguous()
     L = _lib.lib()
@@ -725,7 +760,8 @@ def _layer_backward_raw(g: Tensor, h: Tensor, m: Tensor | None, n: Tensor | None
             _run("K4b:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(g), _p(m), _p(h), _p(n), _p(csr.src), _p(csr.rev), E, csr.V, d,
                  act, act_param, p, seed, offset, _p(gW), _p(gb), _p(ws), ws.numel(), NT_F32, mode, _stream())
         if need_h:
-            img_t = _weight_image(W, True) if mode != GEMM_FP32 else None
+            if img_t is None and mode != GEMM_FP32:
+                img_t = _weight_image(W, True)
             g_m = torch.empty_like(h)
             _run("K4a:nt_layer_backward_dgrad", L.nt_layer_backward_dgrad, _p(g), _p(W), _p(img_t), E, d, p, seed, offset, _p(g_m), NT_F32,
                  mode, _stream())
@@ -767,8 +803,10 @@ class _Layer(torch.autograd.Function):
             b = _require(b, "bias", torch.float32, 1)
         # tensor-core path: K2 also writes the message tensor m, which K4b then streams as dense tiles
         save_m = _save_messages and mode != GEMM_FP32 and d % 4 == 0 and (ctx.needs_input_grad[1] or (b is not None and ctx.needs_input_grad[2]))
-        out, m, n, arg = _layer_forward_raw(h, W, b, csr, act, act_param, mean, residual, p, seed, offset, mode, save_m, extreme)
+        img_t_out: list | None = [] if (ctx.needs_input_grad[0] and mode != GEMM_FP32) else None
+        out, m, n, arg = _layer_forward_raw(h, W, b, csr, act, act_param, mean, residual, p, seed, offset, mode, save_m, extreme, img_t_out)
         ctx.save_for_backward(h, m if save_m else n, W, arg)
+        ctx.img_t = img_t_out[0] if img_t_out else None  # W is a saved tensor: autograd refuses to run backward if it was changed in place
         ctx.csr, ctx.cfg, ctx.has_bias, ctx.has_m = csr, (act, act_param, mean, residual, p, seed, offset, mode), b is not None, save_m
         return out
 
@@ -777,7 +815,7 @@ class _Layer(torch.autograd.Function):
         h, n_or_m, W, arg = ctx.saved_tensors
         m, n = (n_or_m, None) if ctx.has_m else (None, n_or_m)
         need_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
-        gh, gW, gb = _layer_backward_raw(g, h, m, n, W, ctx.has_bias, ctx.csr, *ctx.cfg, need_w, ctx.needs_input_grad[0], arg)
+        gh, gW, gb = _layer_backward_raw(g, h, m, n, W, ctx.has_bias, ctx.csr, *ctx.cfg, need_w, ctx.needs_input_grad[0], arg, ctx.img_t)
         return gh, gW, gb, None, None, None, None, None, None, None, None, None, None
 
 
