@@ -68,7 +68,7 @@ enum nt_gemm_mode {
 
 /* Bumped whenever an entry point's argument list changes; the ctypes binding (notorch_b200/_lib.py) refuses a library whose
  * nt_version() differs, so a stale .so can never be called with a newer signature table. */
-#define NT_ABI_VERSION 200
+#define NT_ABI_VERSION 201
 
 const char* nt_last_error_string(void);
 int nt_version(void); /* = NT_ABI_VERSION of the build */
@@ -237,6 +237,24 @@ int nt_layer_backward_epilogue_fused(const void* g, const void* h, const void* g
                                      const int32_t* rev_rowptr, const int32_t* rev_perm, const int32_t* dst_rowptr,
                                      int64_t E, int64_t d, int act, float act_param, int residual, int mean,
                                      void* g_h, int dtype, nt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward of the LAST depth under a sum read-out over each molecule's edges (notorch/nn/gnn/agg.py:27,36 behind
+ * chemprop.py:86,88 on a device-collated batch): the gradient reaching h_L is the broadcast g[e] = gH[mol(e)], so
+ *   gW^T = (sum_{e in b} m[e])^T gH   -> nt_seg_reduce over m, then nt_layer_backward_wgrad on B rows
+ *   gb   = sum_b |b| gH[b]            -> nt_weighted_colsum (rowptr = the molecules' edge pointers; NULL = unit weights)
+ *   g_m  = (gH W)[mol(e)]             -> nt_layer_backward_dgrad on B rows = gHW [B, d]; g_m [E, d] is never written
+ *   g_h[e] = [gH[mol e]] + act'(h[e]) * (outdeg(dst e) gHW[mol e] (/ indeg(dst e)) - sum_{e'': rev[e''] = e} gHW[mol e''])
+ * mol_of_edge [E] = batch_edge_index as int32 (molecule of every edge); src_rowptr / dst_rowptr / rev_rowptr / rev_perm as in
+ * nt_layer_backward_epilogue_fused. Requires that a molecule's edges connect only its own atoms (BatchedGraph.from_packed).
+ * ---------------------------------------------------------------------------------------------- */
+int nt_weighted_colsum(const void* x, const int32_t* rowptr, int64_t rows, int64_t d, void* out, int dtype, nt_stream_t stream);
+size_t nt_layer_backward_epilogue_pooled_workspace_bytes(int64_t E); /* 16 bytes per edge: the per-edge index record */
+int nt_layer_backward_epilogue_pooled(const void* gH, const void* gHW, const void* h, const int32_t* mol_of_edge,
+                                      const int32_t* dst, const int32_t* src_rowptr, const int32_t* rev_rowptr,
+                                      const int32_t* rev_perm, const int32_t* dst_rowptr, int64_t E, int64_t B, int64_t d,
+                                      int act, float act_param, int residual, int mean, void* g_h, void* workspace,
+                                      size_t workspace_bytes, int dtype, nt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Prediction head (row N3): the nn.Linear layers of notorch/nn/mlp.py:58-62 on the [B, d] molecule vectors, strict fp32 (FFMA),

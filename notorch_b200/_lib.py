@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnotorch_b200.so")
 
-ABI_VERSION = 200  # = NT_ABI_VERSION of include/notorch_b200.h; a library reporting another value is refused
+ABI_VERSION = 201  # = NT_ABI_VERSION of include/notorch_b200.h; a library reporting another value is refused
 
 # enums of include/notorch_b200.h
 NT_F32, NT_BF16 = 0, 1
@@ -50,6 +50,10 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "nt_layer_backward_epilogue": (_int, [_vp, _vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _int, _vp, _int, _vp]),
     "nt_layer_backward_epilogue_arg": (_int, [_vp, _vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _vp, _int, _vp]),
     "nt_layer_backward_epilogue_fused": (_int, [_vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _int, _vp, _int, _vp]),
+    "nt_weighted_colsum": (_int, [_vp, _i32p, _i64, _i64, _vp, _int, _vp]),
+    "nt_layer_backward_epilogue_pooled_workspace_bytes": (_sz, [_i64]),
+    "nt_layer_backward_epilogue_pooled": (_int, [_vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _i64, _int, _f32, _int, _int, _vp,
+                                                 _vp, _sz, _int, _vp]),
     "nt_linear_forward": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
     "nt_linear_backward_input": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
     "nt_linear_backward_weight_workspace_bytes": (_sz, [_i64, _i64, _i64]),

@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libnotorch_b200.so")
 
-SOURCES = ["api.cu", "index_kernels.cu", "rowwise_kernels.cu", "gemm_simt.cu", "gemm_pair.cu", "wgrad_tc.cu", "wgrad_pair.cu", "embed_kernels.cu", "embed_fused.cu", "readout_kernels.cu"]
+SOURCES = ["api.cu", "index_kernels.cu", "rowwise_kernels.cu", "gemm_simt.cu", "gemm_pair.cu", "wgrad_tc.cu", "wgrad_pair.cu", "embed_kernels.cu", "embed_fused.cu", "readout_kernels.cu", "pooled_backward.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

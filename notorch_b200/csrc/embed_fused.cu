@@ -15,6 +15,8 @@
 //             (A first version did one shared-memory read-modify-write per (edge, slot) on per-thread columns of private tables:
 //             661 us at BASELINE configs[1] - the dependent LDS/FADD/STS chains of nine warps per SM cannot hide their own
 //             latency. Measured, replaced.)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nt {
@@ -266,6 +268,53 @@ __global__ void __launch_bounds__(256) embed_edge_init_bwd_reduce(const float* _
   stg4(out + col0 + 4 * c, s);
 }
 
+// ---- backward on the tcgen05 weight-gradient kernel (wgrad_pair.cu) ------------------------------------------------------------
+// gT = cnt^T . g is the SAME contraction over edges as the weight gradient gW^T = m^T . g, with the count matrix in the place of the
+// messages: cnt [rows, ld] (ld = 64 or 128 >= Tv + Te, fp32, small integers) is written once by the kernel below (52 MB at BASELINE
+// configs[1], ~5 % of what the step's other kernels move) and the CTA-pair kernel streams it beside g - HBM-bound, where the
+// mma.sync kernel above is bound by the legacy tensor path's issue rate (202 us for a 246 MB read).
+__global__ void __launch_bounds__(256) embed_count_kernel(const int64_t* __restrict__ node_types, int bv, const int64_t* __restrict__ edge_types, int be,
+                                                          const int32_t* __restrict__ src, int64_t n_rows, int64_t V, int Tv, int Te, int ld_shift,
+                                                          float* __restrict__ cnt) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t r = t >> (ld_shift - 2);                 // ld / 4 threads per row, four types each
+  if (r >= n_rows) return;
+  const int q = (int)(t & ((1 << (ld_shift - 2)) - 1));
+  int64_t s = src ? (int64_t)__ldg(src + r) : r;
+  if (s < 0 || s >= V) s = 0;                            // reported by the forward pass (status flag); stay in bounds here
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < bv; ++j) {
+    int64_t k = __ldg(node_types + s * bv + j);
+    if (k < 0 || k >= Tv) k = 0;
+    if ((int)(k >> 2) == q) c[k & 3] += 1.f;
+  }
+  for (int j = 0; j < be; ++j) {
+    int64_t k = __ldg(edge_types + r * be + j);
+    if (k < 0 || k >= Te) k = 0;
+    k += Tv;
+    if ((int)(k >> 2) == q) c[k & 3] += 1.f;
+  }
+  stg4(cnt + (r << ld_shift) + 4 * q, make_float4(c[0], c[1], c[2], c[3]));
+}
+
+size_t pair_count_wgrad_workspace_bytes(int64_t E, int64_t d, int64_t ld);
+int pair_count_wgrad(const float* g, const float* cnt, int64_t E, int64_t d, int64_t ld, int64_t Tv, int64_t Te, float* g_tab_v, float* g_tab_e,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+static bool embbwd_use_tc() {  // NOTORCH_B200_EMBBWD=mma keeps the warp-level kernel (A/B timing); read per call
+  const char* e = getenv("NOTORCH_B200_EMBBWD");
+  return !(e && e[0] == 'm');
+}
+static int64_t count_ld(int64_t T) { return T <= 64 ? 64 : T <= 128 ? 128 : 0; }
+static size_t count_bytes(int64_t n_rows, int64_t ld) { return ((size_t)n_rows * ld * sizeof(float) + 1023) / 1024 * 1024; }
+// bytes of the tcgen05 path (count matrix + split-K planes); 0 when it does not apply
+static size_t embbwd_tc_workspace_bytes(int64_t n_rows, int64_t T, int64_t d) {
+  const int64_t ld = count_ld(T);
+  if (!ld || d % 4 != 0 || n_rows <= 0 || n_rows >= INT32_MAX / 2) return 0;
+  const size_t planes = pair_count_wgrad_workspace_bytes(n_rows, d, ld);
+  return planes ? count_bytes(n_rows, ld) + planes : 0;
+}
+
 // ---- launch geometry of the backward (shared by the workspace query and the launchers) ----------------------------------------
 struct EfmPlan {
   int mt;      // 16-type tiles (1, 2, 4 or 8)
@@ -307,6 +356,18 @@ static cudaError_t efm_launch(const EfmPlan& plan, const float* g, const int64_t
 // shared by nt_embed_edge_init_backward (two id sources, node ids gathered through src) and nt_embedding_bag_backward (one source)
 int embed_bwd_mma(const float* g, const int64_t* node_types, int64_t bv, const int64_t* edge_types, int64_t be, const int32_t* src, int64_t n_rows, int64_t V,
                   int64_t Tv, int64_t Te, int64_t d, float* g_tab_v, float* g_tab_e, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const size_t tc_bytes = embbwd_tc_workspace_bytes(n_rows, Tv + Te, d);
+  if (tc_bytes && workspace_bytes >= tc_bytes && embbwd_use_tc() && (g_tab_e || Te == 0) && aligned16(g) && aligned16(workspace)) {
+    const int64_t ld = count_ld(Tv + Te);
+    float* cnt = static_cast<float*>(workspace);
+    const int ld_shift = ld == 64 ? 6 : 7;
+    embed_count_kernel<<<(unsigned)cdiv(n_rows * (ld / 4), 256), 256, 0, st>>>(node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te,
+                                                                               ld_shift, cnt);
+    const size_t off = count_bytes(n_rows, ld);
+    const int rc = pair_count_wgrad(g, cnt, n_rows, d, ld, Tv, Te, g_tab_v, g_tab_e ? g_tab_e : g_tab_v, static_cast<uint8_t*>(workspace) + off,
+                                    workspace_bytes - off, st);
+    if (rc != NT_ERR_UNSUPPORTED) return rc;
+  }
   EfmPlan plan;
   if (!efm_plan(n_rows, Tv + Te, d, &plan)) return NT_ERR_UNSUPPORTED;
   if (workspace_bytes < (size_t)plan.planes * (size_t)(Tv + Te) * plan.cols * sizeof(float)) {
@@ -325,7 +386,7 @@ int embed_bwd_mma(const float* g, const int64_t* node_types, int64_t bv, const i
       default: e = efm_launch<4>(plan, g, node_types, (int)bv, edge_types, (int)be, src, n_rows, V, (int)Tv, (int)Te, (int)d, (int)col0, w, part, st); break;
     }
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(embed_bwd_mma_kernel)");
-    embed_edge_init_bwd_reduce<<<(unsigned)cdiv((int64_t)T * (w / 4), 256), 256, 0, st>>>(part, plan.grid, (int)Tv, (int)Te, (int)d, (int)col0, w, g_tab_v,
+    embed_edge_init_bwd_reduce<<<(unsigned)cdiv((int64_t)T * (w / 4), 256), 256, 0, st>>>(part, plan.planes, (int)Tv, (int)Te, (int)d, (int)col0, w, g_tab_v,
                                                                                          g_tab_e);
     launches += 2;
   }
@@ -335,8 +396,9 @@ int embed_bwd_mma(const float* g, const int64_t* node_types, int64_t bv, const i
 
 size_t embed_bwd_mma_workspace_bytes(int64_t n_rows, int64_t T, int64_t d) {
   EfmPlan plan;
-  if (!efm_plan(n_rows, T, d, &plan)) return 0;
-  return (size_t)plan.planes * (size_t)T * plan.cols * sizeof(float) + 256;
+  const size_t mma = efm_plan(n_rows, T, d, &plan) ? (size_t)plan.planes * (size_t)T * plan.cols * sizeof(float) + 256 : 0;
+  const size_t tc = embbwd_tc_workspace_bytes(n_rows, T, d);
+  return mma > tc ? mma : tc;
 }
 
 }  // namespace nt

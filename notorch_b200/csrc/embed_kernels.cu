@@ -372,9 +372,11 @@ extern "C" int nt_embedding_bag_backward(const void* g, const int64_t* idx, int6
   if (bag <= 64 && aligned16(g_table) && aligned16(workspace) && embed_bwd_mma_workspace_bytes(n, num_types, d) > 0) {
     // the common case (small vocabulary): tensor-core path shared with nt_embed_edge_init_backward (one id source, identity row map)
     static const bool classic = getenv("NOTORCH_B200_EMBBWD_CLASSIC") != nullptr && atoi(getenv("NOTORCH_B200_EMBBWD_CLASSIC")) != 0;
-    if (!classic)
-      return embed_bwd_mma(static_cast<const float*>(g), idx, bag, nullptr, 0, nullptr, n, n, num_types, 0, d, static_cast<float*>(g_table), nullptr,
-                           workspace, workspace_bytes, st);
+    if (!classic) {
+      const int rc = embed_bwd_mma(static_cast<const float*>(g), idx, bag, nullptr, 0, nullptr, n, n, num_types, 0, d, static_cast<float*>(g_table),
+                                   nullptr, workspace, workspace_bytes, st);
+      if (rc != NT_ERR_UNSUPPORTED) return rc;
+    }
   }
   float* partial = static_cast<float*>(workspace);
   int launches = 0;

@@ -41,10 +41,10 @@ __device__ __forceinline__ float seg_act_bwd(float x, int act, float p) {
 // (in-degree ~2), so the independent chains of several items are what keeps enough bytes in flight.
 constexpr int SEG_ITEMS = 2;
 
-template <bool HAS_PERM, int AK>
+template <bool HAS_PERM, int AK, int U = 2>  // U rows of every item per trip
 __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __restrict__ x, int d, int chunks, const int32_t* __restrict__ rowptr,
-                                                              const int32_t* __restrict__ perm, int64_t total, int act, float act_param,
-                                                              int mean, float scale, const float* __restrict__ base,
+                                                              const int32_t* __restrict__ perm, int64_t total, uint64_t magic, int act,
+                                                              float act_param, int mean, float scale, const float* __restrict__ base,
                                                               const float* __restrict__ dact_of, float* __restrict__ out) {
   // dact_of != nullptr (nt_seg_reduce_ex, backward form): no activation prologue; the reduced row is multiplied by act'(dact_of[s])
   const bool pre = dact_of == nullptr;
@@ -58,21 +58,21 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __r
   for (int k = 0; k < SEG_ITEMS; ++k) {
     const int64_t t = t0 + (int64_t)k * ROW_THREADS;
     const bool live = t < total;
-    s[k] = live ? (int)(t / chunks) : 0;
-    c[k] = live ? (int)(t - (int64_t)s[k] * chunks) * 4 : 0;
+    split_item(live ? t : 0, chunks, magic, s[k], c[k]);
+    c[k] *= 4;
     lo[k] = live ? __ldg(rowptr + s[k]) : 0;
     hi[k] = live ? __ldg(rowptr + s[k] + 1) : 0;
     acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     maxlen = max(maxlen, hi[k] - lo[k]);
   }
-  for (int j = 0; j < maxlen; j += 2) {
-    int r[SEG_ITEMS][2];
-    bool ok[SEG_ITEMS][2];
-    float4 v[SEG_ITEMS][2];
+  for (int j = 0; j < maxlen; j += U) {
+    int r[SEG_ITEMS][U];
+    bool ok[SEG_ITEMS][U];
+    float4 v[SEG_ITEMS][U];
 #pragma unroll
     for (int k = 0; k < SEG_ITEMS; ++k)
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int idx = lo[k] + j + u;
         ok[k][u] = idx < hi[k];
         r[k][u] = ok[k][u] ? (HAS_PERM ? __ldg(perm + idx) : idx) : 0;
@@ -80,12 +80,12 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) seg_reduce_v4(const float* __r
 #pragma unroll
     for (int k = 0; k < SEG_ITEMS; ++k)
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < U; ++u)
         if (ok[k][u]) v[k][u] = ldg4(x + (int64_t)r[k][u] * d + c[k]);
 #pragma unroll
     for (int k = 0; k < SEG_ITEMS; ++k)
 #pragma unroll
-      for (int u = 0; u < 2; ++u)  // ascending item order within the segment: bit-identical to a sequential scatter_add_
+      for (int u = 0; u < U; ++u)  // ascending item order within the segment: bit-identical to a sequential scatter_add_
         if (ok[k][u]) acc[k] = add4(acc[k], pre ? seg_act_fwd4<AK>(v[k][u], act, act_param) : v[k][u]);
   }
 #pragma unroll
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(ROW_THREADS) csr_to_ell_kernel(const int32_t* 
 template <int AK>
 __global__ void __launch_bounds__(ROW_THREADS, 4) seg_reduce_ell_v4(const float* __restrict__ x, int d, int chunks, const int32_t* __restrict__ rowptr,
                                                                    const int32_t* __restrict__ perm, const int4* __restrict__ ell, int64_t total,
-                                                                   int act, float act_param, int mean, float scale, const float* __restrict__ base,
+                                                                   uint64_t magic, int act, float act_param, int mean, float scale,
+                                                                   const float* __restrict__ base,
                                                                    const float* __restrict__ dact_of, float* __restrict__ out) {
   const bool pre = dact_of == nullptr;
   // blocks walk the segments from the END: the producer kernel wrote its output front to back, so the tail is what is still in
@@ -142,8 +143,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) seg_reduce_ell_v4(const float*
   for (int k = 0; k < SEG_ITEMS; ++k) {
     const int64_t t = t0 + (int64_t)k * ROW_THREADS;
     live[k] = t < total;
-    s[k] = live[k] ? (int)(t / chunks) : 0;
-    c[k] = live[k] ? (int)(t - (int64_t)s[k] * chunks) * 4 : 0;
+    split_item(live[k] ? t : 0, chunks, magic, s[k], c[k]);
+    c[k] *= 4;
     nb[k] = live[k] ? __ldg(ell + s[k]) : make_int4(-1, -1, -1, -1);
     lo[k] = live[k] ? __ldg(rowptr + s[k]) : 0;
     hi[k] = live[k] ? __ldg(rowptr + s[k] + 1) : 0;
@@ -211,12 +212,13 @@ __global__ void __launch_bounds__(ROW_THREADS) seg_reduce_s(const float* __restr
 // gather_add: out[i] = base[i] + scale * x[idx[i]] / max(count(idx[i]), 1)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS) gather_add_v4(const float* __restrict__ base, const float* __restrict__ x, const int32_t* __restrict__ idx,
-                                                              const int32_t* __restrict__ mean_rowptr, int d, int chunks, int64_t total, float scale,
-                                                              float* __restrict__ out) {
+                                                              const int32_t* __restrict__ mean_rowptr, int d, int chunks, int64_t total,
+                                                              uint64_t magic, float scale, float* __restrict__ out) {
   int64_t t = (int64_t)blockIdx.x * ROW_THREADS + threadIdx.x;
   if (t >= total) return;
-  int i = (int)(t / chunks);
-  int c = (int)(t - (int64_t)i * chunks) * 4;
+  int i, c;
+  split_item(t, chunks, magic, i, c);
+  c *= 4;
   int r = __ldg(idx + i);
   float4 v = ldg4(x + (int64_t)r * d + c);
   if (mean_rowptr) {
@@ -321,13 +323,14 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) layer_bwd_epilogue_fused(const
                                                                          const int32_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_perm,
                                                                          const int4* __restrict__ src_ell, const int32_t* __restrict__ rev_rowptr,
                                                                          const int32_t* __restrict__ rev_perm, const int32_t* __restrict__ dst_rowptr,
-                                                                         int d, int chunks, int64_t total, int act, float act_param, int residual,
-                                                                         int mean, int reversed, float* __restrict__ g_h) {
+                                                                         int d, int chunks, int64_t total, uint64_t magic, int act, float act_param,
+                                                                         int residual, int mean, int reversed, float* __restrict__ g_h) {
   const int64_t blk = reversed ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
   const int64_t t = blk * ROW_THREADS + threadIdx.x;
   if (t >= total) return;
-  const int e = (int)(t / chunks);
-  const int c = (int)(t - (int64_t)e * chunks) * 4;
+  int e, c;
+  split_item(t, chunks, magic, e, c);
+  c *= 4;
   // volatile loads: the compiler otherwise sinks the independent ones (h, g, src_rowptr) below the first use of a gathered row
   // level 1
   const int v = ldg_i32_v(dst + e);
@@ -371,8 +374,9 @@ __global__ void __launch_bounds__(ROW_THREADS) layer_bwd_epilogue_fused_v0(const
                                                                             const int32_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_perm,
                                                                             const int4* __restrict__ src_ell, const int32_t* __restrict__ rev_rowptr,
                                                                             const int32_t* __restrict__ rev_perm, const int32_t* __restrict__ dst_rowptr,
-                                                                            int d, int chunks, int64_t total, int act, float act_param, int residual,
-                                                                            int mean, int reversed, float* __restrict__ g_h) {
+                                                                            int d, int chunks, int64_t total, uint64_t /*magic*/, int act,
+                                                                            float act_param, int residual, int mean, int reversed,
+                                                                            float* __restrict__ g_h) {
   const int64_t blk = reversed ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
   const int64_t t = blk * ROW_THREADS + threadIdx.x;
   if (t >= total) return;
@@ -437,16 +441,17 @@ static int seg_reduce_impl(const char* fn, const void* x, int64_t d, const int32
     int chunks = (int)(d / 4);
     int64_t total = num_segments * chunks;
     unsigned grid = (unsigned)cdiv(total, ROW_THREADS * SEG_ITEMS);
+    const uint64_t magic = chunk_div_magic(total, chunks);
     const int ak = act == NT_ACT_IDENTITY ? 0 : act == NT_ACT_RELU ? 1 : 2;
 #define NT_SEG_LAUNCH(AK)                                                                                                                        \
   do {                                                                                                                                           \
     if (ell && aligned16(ell))                                                                                                                   \
-      seg_reduce_ell_v4<AK><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, reinterpret_cast<const int4*>(ell), total, act,      \
-                                                          act_param, mean, scale, bf, df, of);                                                  \
+      seg_reduce_ell_v4<AK><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, reinterpret_cast<const int4*>(ell), total, magic,    \
+                                                          act, act_param, mean, scale, bf, df, of);                                             \
     else if (perm)                                                                                                                               \
-      seg_reduce_v4<true, AK><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);   \
+      seg_reduce_v4<true, AK><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, magic, act, act_param, mean, scale, bf, df, of); \
     else                                                                                                                                         \
-      seg_reduce_v4<false, AK><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, act, act_param, mean, scale, bf, df, of);  \
+      seg_reduce_v4<false, AK><<<grid, ROW_THREADS, 0, st>>>(xf, (int)d, chunks, rowptr, perm, total, magic, act, act_param, mean, scale, bf, df, of); \
   } while (0)
     if (ak == 0) NT_SEG_LAUNCH(0);
     else if (ak == 1) NT_SEG_LAUNCH(1);
@@ -498,7 +503,8 @@ extern "C" int nt_gather_add(const void* base, const void* x, const int32_t* idx
     int chunks = (int)(d / 4);
     int64_t total = n * chunks;
     gather_add_v4<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(static_cast<const float*>(base), static_cast<const float*>(x), idx,
-                                                                              mean_rowptr, (int)d, chunks, total, scale, static_cast<float*>(out));
+                                                                              mean_rowptr, (int)d, chunks, total, chunk_div_magic(total, chunks), scale,
+                                                                              static_cast<float*>(out));
   } else {
     int64_t total = n * d;
     gather_add_s<<<(unsigned)cdiv(total, ROW_THREADS), ROW_THREADS, 0, st>>>(static_cast<const float*>(base), static_cast<const float*>(x), idx,
@@ -578,9 +584,10 @@ extern "C" int nt_layer_backward_epilogue_fused(const void* g, const void* h, co
   const int variant = ve ? atoi(ve) : 3;
   const int reversed = (variant >> 1) & 1;
   const int ak = act == NT_ACT_IDENTITY ? 0 : act == NT_ACT_RELU ? 1 : 2;
+  const uint64_t magic = chunk_div_magic(total, chunks);
 #define NT_K6_LAUNCH(KERNEL, AK)                                                                                                              \
-  KERNEL<AK><<<grid, ROW_THREADS, 0, st>>>(gf, hf, gm, dst, src_rowptr, src_perm, ell4, rev_rowptr, rev_perm, dst_rowptr, (int)d, chunks, total, act, \
-                                           act_param, residual, mean, reversed, out)
+  KERNEL<AK><<<grid, ROW_THREADS, 0, st>>>(gf, hf, gm, dst, src_rowptr, src_perm, ell4, rev_rowptr, rev_perm, dst_rowptr, (int)d, chunks, total, magic, \
+                                           act, act_param, residual, mean, reversed, out)
   if (variant & 1) {
     if (ak == 0) NT_K6_LAUNCH(layer_bwd_epilogue_fused, 0);
     else if (ak == 1) NT_K6_LAUNCH(layer_bwd_epilogue_fused, 1);

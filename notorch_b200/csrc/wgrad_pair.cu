@@ -40,7 +40,9 @@ constexpr int SMEM_BYTES = OFF_BAR + 128;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
 
 struct Geometry {
-  int d, m_units, n_tiles, n_tile, n_a, n_b, ones_row, ld_partial;
+  // d = width of B (g: the output columns o), da = width of A (m: the feature rows i). The weight gradient has da == d; the
+  // embedding-table gradient (embed_count_wgrad below) multiplies a [E, 64 | 128] count matrix with g.
+  int d, da, m_units, n_tiles, n_tile, n_a, n_b, ones_row, ld_partial;
   // The last unit of feature rows runs at HALF height (M = 128: 64 rows per CTA) when at most 128 rows of it are real
   // (d = 300: rows 256..300 incl. the all-ones bias row): half the MMA work and half the m columns to stage. Such units get
   // fewer edge splits than the full-height ones, in proportion to their cost per edge.
@@ -62,20 +64,24 @@ static int segment_kblocks() {
   return v;
 }
 
-static float half_unit_cost() {
+// cost of a half-height unit per edge relative to a full one = the ratio of the chunks each CTA stages per K-block (2 + B : 4 + B);
+// measured 0.78-0.8 at d = 300 (B = 5 chunks: 7 / 9) - the kernel is bound by its producers, not by the MMAs (1 : 2)
+static float half_unit_cost(int b_chunks) {
   static const float w = [] {
     const char* e = getenv("NOTORCH_B200_WGRAD_HALF_COST");
-    const float v = e ? (float)atof(e) : 0.78f;
-    return v > 0.05f && v <= 1.f ? v : 0.78f;
+    const float v = e ? (float)atof(e) : 0.f;
+    return v > 0.05f && v <= 1.f ? v : 0.f;
   }();
-  return w;
+  return w > 0.f ? w : (2.f + (float)b_chunks) / (4.f + (float)b_chunks);
 }
 
-static Geometry make_geometry(int64_t E, int d, int sms) {
+static Geometry make_geometry(int64_t E, int d, int sms, int da = -1, bool want_ones = true) {
   Geometry g;
+  if (da < 0) da = d;
   g.d = d;
-  g.m_units = (d + 2 * TILE_M - 1) / (2 * TILE_M);      // pair units of 256 feature rows
-  g.ones_row = (d % (2 * TILE_M) != 0) ? 1 : 0;          // a spare padded feature row of m exists: all ones -> D[d, :] = bias gradient
+  g.da = da;
+  g.m_units = (da + 2 * TILE_M - 1) / (2 * TILE_M);     // pair units of 256 feature rows
+  g.ones_row = (want_ones && da % (2 * TILE_M) != 0) ? 1 : 0;  // a spare padded feature row of m exists: all ones -> D[da, :] = bias gradient
   int n_pad = (d + 63) / 64 * 64;                        // each CTA holds half of every MMA's N, in 32-feature chunks
   if (n_pad <= MAX_N) { g.n_tile = n_pad; g.n_tiles = 1; }
   else { g.n_tile = 256; g.n_tiles = (n_pad + 255) / 256; }
@@ -84,14 +90,14 @@ static Geometry make_geometry(int64_t E, int d, int sms) {
   g.ld_partial = g.n_tiles * g.n_tile;
   g.kb_total = (E + BLOCK_E - 1) / BLOCK_E;
   static const bool allow_half = [] { const char* e = getenv("NOTORCH_B200_WGRAD_HALF"); return !(e && e[0] == '0'); }();
-  const int last_rows = d + g.ones_row - (g.m_units - 1) * 2 * TILE_M;
+  const int last_rows = da + g.ones_row - (g.m_units - 1) * 2 * TILE_M;
   g.half_last = (allow_half && last_rows <= TILE_M) ? 1 : 0;
   g.full_units = (g.m_units - g.half_last) * g.n_tiles;
   g.half_units = g.half_last * g.n_tiles;
   const int clusters = sms / 2 > 0 ? sms / 2 : 1;
   int64_t sf = 0, sl = 0;
   if (g.full_units > 0) {
-    sf = (int64_t)((float)clusters / ((float)g.full_units + half_unit_cost() * (float)g.half_units));
+    sf = (int64_t)((float)clusters / ((float)g.full_units + half_unit_cost(g.n_tile / 64) * (float)g.half_units));
     if (sf < 1) sf = 1;
     if (sf > g.kb_total) sf = g.kb_total > 0 ? g.kb_total : 1;
   }
@@ -110,7 +116,7 @@ static Geometry make_geometry(int64_t E, int d, int sms) {
 }
 
 struct Params {
-  const float* m;  // [E, d]
+  const float* m;  // [E, da]
   const float* g;  // [E, d]
   float* partial;  // [splits][m_units * 256 (i)][ld_partial (o)]
   int64_t E;
@@ -119,6 +125,7 @@ struct Params {
   uint32_t drop_thr;
   uint64_t seed, offset;
   int products;
+  int prefetch;  // K-blocks of L2 look-ahead (0 = off)
   int ablate;  // debug (NOTORCH_B200_WGRAD_ABLATE): 1 = no MMAs, 2 = no hi / lo split, 4 = no loads; results are then meaningless
 };
 
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * STAGES + 6));
 
   const Geometry& geo = p.geo;
-  const int d = geo.d;
+  const int d = geo.d, da = geo.da;
   const int pair_id = blockIdx.x >> 1;
   // full-height units first (pairs of one edge range are adjacent: the g tiles they share hit in L2), then the half-height ones
   const int n_full = geo.full_units * geo.splits;
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
       int kb_in_seg = 0;
       uint32_t seg_idx = 0;
       const uint32_t boff = (uint32_t)(ha / 32) * (CHUNK_BYTES >> 4);  // this CTA's columns of the second MMA follow its ha / 32 chunks of the first
-      const bool three = p.products == 3, no_mma = (p.ablate & 1) != 0;
+      const bool three = p.products == 3, two = p.products == 2, no_mma = (p.ablate & 1) != 0;
       // the MMAs of K-block stage `s` into accumulator `dacc` ("a": B columns from chunk 0, "b": from chunk ha / 32); one elected lane
       auto issue_part = [&](int s_, uint32_t dacc, uint32_t bsel, uint32_t idesc, int kbs) {
         const uint32_t st0 = sbase + s_ * STAGE_BYTES;
@@ -380,6 +387,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
           } else if (three) {
             umma2_tf32_lo(dacc, a_lo + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc, acc);
             umma2_tf32_lo(dacc, a_hi + k16, b_lo + k16, MNMAJOR_SW128B32_DESC_HI, idesc, 1u);
+            umma2_tf32_lo(dacc, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc, 1u);
+          } else if (two) {  // A is exact in TF32 (a matrix of small integers): its lo part is zero and is neither computed nor multiplied
+            umma2_tf32_lo(dacc, a_hi + k16, b_lo + k16, MNMAJOR_SW128B32_DESC_HI, idesc, acc);
             umma2_tf32_lo(dacc, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc, 1u);
           } else {
             umma2_tf32_lo(dacc, a_hi + k16, b_hi + k16, MNMAJOR_SW128B32_DESC_HI, idesc, acc);
@@ -430,13 +440,14 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
     constexpr int MAX_UNITS = A_CHUNKS + B_CHUNKS_MAX;  // 9
     const uint64_t stream_pol = l2_policy_evict_first();  // m and g are read once per unit: do not let them push the partial planes out of L2
     const int n_chunks = A_CHUNKS + b_chunks;
+    const int first_split = p.products == 2 ? A_CHUNKS : 0;  // exact A operand: nothing to split, the raw tile is the hi part
     const int r = pt >> 3, pos = pt & 7;
     const int c16 = ((((pos >> 1) ^ (r & 3)) << 1) | (pos & 1));  // logical 16-byte chunk inside the 128-byte feature row
     const int E_i = (int)p.E;
     const uint32_t ready_leader = map_to_cta(bar_ready, 0);
     // the all-ones feature row of m (bias gradient) lives in this CTA's A tile iff i0 <= d < i0 + 128
-    const bool ones_here = geo.ones_row && d >= i0 && d < i0 + rows_cta;
-    const int ones_chunk = ones_here ? (d - i0) / 32 : -1, ones_c16 = ones_here ? ((d - i0) % 32) / 4 : -1;
+    const bool ones_here = geo.ones_row && da >= i0 && da < i0 + rows_cta;
+    const int ones_chunk = ones_here ? (da - i0) / 32 : -1, ones_c16 = ones_here ? ((da - i0) % 32) / 4 : -1;
 
     auto feature_of = [&](int chunk) {  // first feature of this thread's unit in chunk `chunk`
       if (chunk < A_CHUNKS) return i0 + 32 * chunk + 4 * c16;
@@ -450,8 +461,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
       for (int k = 0; k < MAX_UNITS; ++k) {
         if (k < n_chunks && (k < a_chunks || k >= A_CHUNKS)) {
           const int f = feature_of(k);
-          const bool ok = e < E_i && f < d;
-          const float* src = (k < A_CHUNKS ? p.m : p.g) + (ok ? (int64_t)e * d + f : 0);
+          const int width = k < A_CHUNKS ? da : d;
+          const bool ok = e < E_i && f < width;
+          const float* src = (k < A_CHUNKS ? p.m : p.g) + (ok ? (int64_t)e * width + f : 0);
           asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst + k * CHUNK_BYTES), "l"(src), "r"(ok ? 16 : 0), "l"(stream_pol)
                        : "memory");
         }
@@ -460,8 +472,26 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
     int ls = 0, cs = 0;
     uint32_t lph = 0;
     int64_t lkb = 0;
+    // L2 look-ahead (NOTORCH_B200_WGRAD_PF=n, default off). A stage's loads are issued one K-block period before they are needed, so
+    // a period cannot be shorter than the memory latency of a K-block's rows; the 32 edge rows of a K-block are ONE contiguous span
+    // of each operand, so one thread per CTA can ask the copy engine to bring the span of K-block lkb + n into L2 ahead of time
+    // (the leader the A operand's, its peer the B operand's). Measured at BASELINE configs[1]: 284 us without, 306 / 308 / 314 / 316 us
+    // with n = 2 / 4 / 6 / 10 (d = 2048: 1134 -> 1330 us) - the prefetches compete with the demand loads for the same DRAM queues
+    // and the kernel is not latency-bound in that sense. Kept as a switch for the record, not used.
+    const int pf = p.prefetch;
+    auto prefetch_span = [&](int64_t kb) {
+      const int64_t e0 = (kb_lo + kb) * BLOCK_E;
+      if (kb >= nkb || e0 >= p.E) return;
+      const int64_t rows = p.E - e0 < BLOCK_E ? p.E - e0 : BLOCK_E;
+      const int width = leader ? da : d;
+      const float* base = (leader ? p.m : p.g) + e0 * width;
+      l2_prefetch_bulk(base, (uint32_t)(rows * width * 4));
+    };
+    if (pf > 0 && pt == 0)
+      for (int j = STAGES - 1; j < pf; ++j) prefetch_span(j);
     auto load_step = [&]() {
       if (lkb < nkb) {
+        if (pf > 0 && pt == 0) prefetch_span(lkb + pf);
         mbar_wait(bar_empty + 8 * ls, lph ^ 1);
         if (!(p.ablate & 4)) issue(lkb, ls);
       }
@@ -481,10 +511,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_pair_kernel(const Params p) 
       if (!(p.ablate & 2)) {
 #pragma unroll
       for (int k = 0; k < MAX_UNITS; ++k)  // all reads first: the in-place stores below must not serialise the units
-        if (k < n_chunks && (k < a_chunks || k >= A_CHUNKS)) v[k] = *reinterpret_cast<const float4*>(hi + k * CHUNK_BYTES);
+        if (k >= first_split && k < n_chunks && (k < a_chunks || k >= A_CHUNKS)) v[k] = *reinterpret_cast<const float4*>(hi + k * CHUNK_BYTES);
 #pragma unroll
       for (int k = 0; k < MAX_UNITS; ++k) {
-        if (k < n_chunks && (k < a_chunks || k >= A_CHUNKS)) {
+        if (k >= first_split && k < n_chunks && (k < a_chunks || k >= A_CHUNKS)) {
           if (k == ones_chunk) {
             if (c16 == ones_c16 && e < E_i) v[k].x = 1.f;
           } else if (DROP && k >= A_CHUNKS) {
@@ -553,6 +583,27 @@ __global__ void __launch_bounds__(256) wgrad_pair_reduce(const float* __restrict
   }
 }
 
+// Embedding-table gradient out of the same planes: gT[i, o] = sum_z partial[z](i, o), rows i < Tv into g_tab_v [Tv, d], the next Te
+// rows into g_tab_e [Te, d] (row-major, no transpose). One thread per (4 output columns, table row).
+__global__ void __launch_bounds__(256) wgrad_pair_reduce_tables(const float* __restrict__ partial, Geometry geo, int Tv, int Te, float* __restrict__ g_tab_v,
+                                                                float* __restrict__ g_tab_e) {
+  const int d = geo.d, rows = Tv + Te;
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int o4 = (int)(t / rows), i = (int)(t - (int64_t)o4 * rows);  // i fastest: coalesced plane reads
+  if (4 * o4 >= d) return;
+  const int64_t plane_rows = (int64_t)geo.m_units * 2 * TILE_M;
+  const int64_t plane = plane_rows * geo.ld_partial;
+  const float4* src = reinterpret_cast<const float4*>(partial) + ((int64_t)o4 * plane_rows + i);
+  const int nz = (geo.half_last && i >= (geo.m_units - 1) * 2 * TILE_M) ? geo.splits_last : geo.splits;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < nz; ++z) {
+    const float4 v = __ldg(src + z * (plane / 4));
+    s = make_float4(s.x + v.x, s.y + v.y, s.z + v.z, s.w + v.w);
+  }
+  float* out = i < Tv ? g_tab_v + (int64_t)i * d : g_tab_e + (int64_t)(i - Tv) * d;
+  *reinterpret_cast<float4*>(out + 4 * o4) = s;  // d % 4 == 0
+}
+
 }  // namespace wgp
 
 // host-only view of the work decomposition (no CUDA call): lets the CPU test suite check its invariants for any (E, d, #SMs)
@@ -569,6 +620,36 @@ size_t pair_wgrad_workspace_bytes(int64_t E, int64_t d) {
   if (sms <= 0) sms = 148;
   wgp::Geometry geo = wgp::make_geometry(E, (int)d, sms);
   return (size_t)geo.planes * geo.m_units * 2 * tc::TILE_M * geo.ld_partial * sizeof(float) + 1024;
+}
+
+static int launch_pair_kernel(wgp::Params& p, cudaStream_t st) {
+  static const int ablate = [] { const char* e = getenv("NOTORCH_B200_WGRAD_ABLATE"); return e ? atoi(e) : 0; }();
+  p.ablate = ablate;
+  const char* pfe = getenv("NOTORCH_B200_WGRAD_PF");  // read per call (A/B timing)
+  p.prefetch = pfe ? atoi(pfe) : 0;
+  if (p.prefetch < 0 || p.prefetch > 64) p.prefetch = 0;
+  static PerDeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(wgp::wgrad_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgp::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgp::wgrad_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgp::SMEM_BYTES);
+    return e;
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_pair_kernel)");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * (p.geo.full_units * p.geo.splits + p.geo.half_units * p.geo.splits_last)));
+  cfg.blockDim = dim3(wgp::THREADS);
+  cfg.dynamicSmemBytes = wgp::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = p.drop_p > 0.f ? cudaLaunchKernelEx(&cfg, wgp::wgrad_pair_kernel<true>, p) : cudaLaunchKernelEx(&cfg, wgp::wgrad_pair_kernel<false>, p);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(wgrad_pair_kernel)");
+  return NT_OK;
 }
 
 // returns NT_ERR_UNSUPPORTED when the bias gradient cannot ride along (d % 256 == 0) and gb is requested
@@ -589,39 +670,60 @@ int pair_layer_wgrad(const float* g, const float* m, int64_t E, int64_t d, float
   p.partial = static_cast<float*>(workspace);
   p.E = E;
   p.products = products;
-  static const int ablate = [] { const char* e = getenv("NOTORCH_B200_WGRAD_ABLATE"); return e ? atoi(e) : 0; }();
-  p.ablate = ablate;
   p.drop_p = drop_p;
   p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   double t = (double)drop_p * 4294967296.0;
   p.drop_thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
   p.seed = seed;
   p.offset = offset;
-
-  static PerDeviceOnce once;
-  const cudaError_t attr_err = once.run([] {
-    cudaError_t e = cudaFuncSetAttribute(wgp::wgrad_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgp::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgp::wgrad_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgp::SMEM_BYTES);
-    return e;
-  });
-  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_pair_kernel)");
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * (p.geo.full_units * p.geo.splits + p.geo.half_units * p.geo.splits_last)));
-  cfg.blockDim = dim3(wgp::THREADS);
-  cfg.dynamicSmemBytes = wgp::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = drop_p > 0.f ? cudaLaunchKernelEx(&cfg, wgp::wgrad_pair_kernel<true>, p) : cudaLaunchKernelEx(&cfg, wgp::wgrad_pair_kernel<false>, p);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(wgrad_pair_kernel)");
+  const int rc = launch_pair_kernel(p, st);
+  if (rc) return rc;
   const int64_t total = (d + (p.geo.ones_row ? 1 : 0)) * ((d + 3) / 4);  // one thread per (4 output columns, feature row)
   wgp::wgrad_pair_reduce<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(p.partial, p.geo, gW, gb);
   NT_LAUNCH_CHECK("pair_layer_wgrad", 2);
+  return NT_OK;
+}
+
+// Embedding-table gradient on the same kernel: gT[t, :] = sum_e cnt[e, t] * g[e, :] with cnt [E, ld] (ld = 64 or 128 >= Tv + Te) the
+// matrix of slot counts (embed_fused.cu builds it) in the place of the messages. Counts are small integers, exact in TF32: two
+// products (cnt * g_lo + cnt * g_hi). ld <= 128 makes every unit a half-height one, so every CTA pair takes one range of edges and
+// g is read once. (Measured the other way round as well - g as the A side, so that its features fill M = 256: 244 us against 177,
+// because the kernel's time is set by its K-blocks per pair, 156 against 87, not by its MMAs.)
+static wgp::Geometry count_geometry(int64_t E, int64_t d, int64_t ld) {
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  return wgp::make_geometry(E, (int)d, sms, (int)ld, false);
+}
+
+size_t pair_count_wgrad_workspace_bytes(int64_t E, int64_t d, int64_t ld) {
+  if (d % 4 != 0 || E <= 0 || (ld != 64 && ld != 128)) return 0;
+  const wgp::Geometry geo = count_geometry(E, d, ld);
+  if (!geo.half_last || geo.m_units != 1) return 0;  // NOTORCH_B200_WGRAD_HALF=0
+  return (size_t)geo.planes * geo.m_units * 2 * tc::TILE_M * geo.ld_partial * sizeof(float) + 1024;
+}
+
+int pair_count_wgrad(const float* g, const float* cnt, int64_t E, int64_t d, int64_t ld, int64_t Tv, int64_t Te, float* g_tab_v, float* g_tab_e,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (Tv + Te > ld || (ld != 64 && ld != 128) || d % 4 != 0) return NT_ERR_UNSUPPORTED;
+  wgp::Params p{};
+  p.geo = count_geometry(E, d, ld);
+  if (!p.geo.half_last || p.geo.m_units != 1) return NT_ERR_UNSUPPORTED;
+  if (workspace_bytes < pair_count_wgrad_workspace_bytes(E, d, ld)) {
+    set_error("pair_count_wgrad: workspace too small");
+    return NT_ERR_WORKSPACE;
+  }
+  p.m = cnt;
+  p.g = g;
+  p.partial = static_cast<float*>(workspace);
+  p.E = E;
+  p.products = 2;
+  p.drop_p = 0.f;
+  p.inv_keep = 1.f;
+  const int rc = launch_pair_kernel(p, st);
+  if (rc) return rc;
+  const int64_t total = (Tv + Te) * (d / 4);
+  wgp::wgrad_pair_reduce_tables<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(p.partial, p.geo, (int)Tv, (int)Te, g_tab_v, g_tab_e);
+  NT_LAUNCH_CHECK("pair_count_wgrad", 2);
   return NT_OK;
 }
 

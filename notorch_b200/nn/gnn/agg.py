@@ -42,13 +42,12 @@ def _readout_over_edges(G: BatchedGraph, kind: str, norm: float = 100.0) -> Tens
     h = x.origin[1]
     if eptr.device != h.device:
         return None
-    csr = getattr(G, "_nt_mol_edge_csr", None)
-    if csr is None:
-        csr = ops.SegmentCSR(eptr, None, G.batch_edge_index.to(torch.int32), len(G))
-        G._nt_mol_edge_csr = csr
+    H_sum = x.origin[2] if len(x.origin) > 2 else None  # already computed by the block's last depth (ops._LayerPooled)
+    if H_sum is None:
+        H_sum = ops.seg_reduce(h, ops.mol_edge_csr(G), "sum", tag="K3e")
     if kind == "norm":
-        return ops.seg_reduce(h, csr, "sum", 1.0 / norm, tag="K3e")
-    H = ops.seg_reduce(h, csr, "sum", tag="K3e")
+        return H_sum * (1.0 / norm)
+    H = H_sum
     if kind == "mean":  # scatter_mean = sum / clamp(count, 1) (agg.py:36): the count is the molecule's ATOM count
         cnt = getattr(G, "_nt_mol_atom_count", None)
         if cnt is None:

@@ -33,14 +33,15 @@ class ChempropLayer(nn.Module):
         self.update = nn.Sequential(w_h, nn.Dropout(p=dropout))
 
     def forward(self, edge_feats: Tensor, node_feats: Tensor, edge_index: Tensor, rev_index: Tensor, *,
-                _residual: bool = False, _csr: ops.GraphCSR | None = None) -> Tensor:
+                _residual: bool = False, _csr: ops.GraphCSR | None = None, _pool: ops.SegmentCSR | None = None) -> Tensor:
         # only len(node_feats) matters, as in the reference (chemprop.py:39); a block passes its cached CSR bundle and asks for the
-        # residual to be added inside K2
+        # residual to be added inside K2; for its last depth in front of a sum read-out it also passes the molecules' edge ranges
+        # (``_pool``) and gets (h_L, sum of h_L over each molecule's edges) back
         if _csr is None:
             _csr = ops.graph_csr_from_tensors(edge_index, rev_index, len(node_feats))
         w_h, drop = self.update
         return ops.layer(edge_feats, w_h.weight, w_h.bias, _csr, act=ops.act_code(self.act), reduce=self.reduce, residual=_residual,
-                         dropout=drop.p, training=self.training and drop.training)
+                         dropout=drop.p, training=self.training and drop.training, pool=_pool)
 
     def extra_repr(self):
         return f"(reduce): {self.reduce}"
@@ -76,15 +77,26 @@ class ChempropBlock(nn.Module):
         else:
             xv = G.node_feats
             h = ops.edge_init(xv, G.edge_feats, csr)  # K0
-        for entry in self.layers:
+        # A sum-reduced block on a device-collated batch (every molecule = a contiguous range of edges between its own atoms) defers
+        # the final edge -> atom reduction: a Sum / Mean / Norm read-out right behind it needs only sum_{e in b} h_L[e] (§5.9).
+        defer = self.reduce == "sum" and ops._fuse_readout and isinstance(G, Graph) and getattr(G, "_nt_mol_edge_ptr", None) is not None
+        pool = None
+        if defer and len(self.layers) > 0 and ops._pooled_backward and not ops._via_ops(h):
+            pool = ops.mol_edge_csr(G)  # the last depth computes that sum itself and takes the pooled backward (§5.10)
+        H_sum = None
+        for i, entry in enumerate(self.layers):
             fused_residual = isinstance(entry, Residual)
             layer = entry.module if fused_residual else entry
-            h = layer(h, xv, G.edge_index, G.rev_index, _residual=fused_residual, _csr=csr)  # xv: only its length is used
-        if self.reduce == "sum" and ops._fuse_readout and isinstance(G, Graph) and getattr(G, "_nt_mol_edge_ptr", None) is not None:
+            if pool is not None and i == len(self.layers) - 1 and isinstance(layer, ChempropLayer) and layer.reduce in ("sum", "mean"):
+                h, H_sum = layer(h, xv, G.edge_index, G.rev_index, _residual=fused_residual, _csr=csr, _pool=pool)
+            else:
+                h = layer(h, xv, G.edge_index, G.rev_index, _residual=fused_residual, _csr=csr)  # xv: only its length is used
+        if defer:
             # K1 without activation (chemprop.py:86), deferred: a Sum / Mean / Norm read-out right behind the block sums h_L over each
             # molecule's edges directly (one pass instead of K1 + K3); any other reader of node_feats computes them on first access
             final_h = h
-            atoms = PendingFeats(lambda: ops.edge_to_atom(final_h, csr, "sum"), (csr.V, h.shape[1]), h.dtype, h.device, ("edge_to_atom_sum", final_h))
+            atoms = PendingFeats(lambda: ops.edge_to_atom(final_h, csr, "sum"), (csr.V, h.shape[1]), h.dtype, h.device,
+                                 ("edge_to_atom_sum", final_h, H_sum))
         else:
             atoms = ops.edge_to_atom(h, csr, self.reduce)  # K1 without activation (chemprop.py:86)
         return G.update(node_feats=atoms, edge_feats=h)

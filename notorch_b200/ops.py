@@ -394,6 +394,16 @@ def build_graph_csr(edge_index: Tensor, rev_index: Tensor, num_nodes: int) -> Gr
     return GraphCSR(num_nodes, E, by_dst, by_src, by_rev)
 
 
+def mol_edge_csr(G) -> SegmentCSR:
+    """The molecules' contiguous edge ranges of a device-collated batch (``BatchedGraph.from_packed``) as a segment CSR without a
+    permutation; ``keys32`` = the molecule of every edge (``batch_edge_index`` as int32). Cached on the graph object."""
+    csr = getattr(G, "_nt_mol_edge_csr", None)
+    if csr is None:
+        csr = SegmentCSR(G._nt_mol_edge_ptr, None, G.batch_edge_index.to(torch.int32), len(G))
+        G._nt_mol_edge_csr = csr
+    return csr
+
+
 def peek_feats(G, name: str):
     """``G.node_feats`` / ``G.edge_feats`` without computing a pending embedding (``Graph.peek``); plain attribute on foreign graphs."""
     peek = getattr(G, "peek", None)
@@ -671,6 +681,7 @@ _fuse_embedding = os.environ.get("NOTORCH_B200_FUSE_EMBED", "1") != "0"
 # a Sum / Mean / Norm read-out of a sum-reduced block is a sum over each molecule's EDGES: run it over h_L directly and leave the
 # block's node_feats a placeholder that is computed only if something reads it (agg.py)
 _fuse_readout = os.environ.get("NOTORCH_B200_FUSE_READOUT", "1") != "0"
+_pooled_backward = os.environ.get("NOTORCH_B200_POOLED_BWD", "1") != "0"  # last depth's backward over molecules, not edges (§5.10)
 
 
 def embed_edge_init_supported(table_v: Tensor, table_e: Tensor, node_types: Tensor, edge_types: Tensor) -> bool:
@@ -819,6 +830,85 @@ class _Layer(torch.autograd.Function):
         return gh, gW, gb, None, None, None, None, None, None, None, None, None, None
 
 
+class _LayerPooled(torch.autograd.Function):
+    """The LAST message-passing depth together with the sum of h_L over each molecule's edges (chemprop.py:37-41,
+    residual.py:28 + the read-out identity of §5.9). Outputs ``(h_L, H_sum)``. When only ``H_sum`` is used downstream (a Sum / Mean /
+    Norm read-out: agg.py:27,36), the gradient of h_L is the broadcast ``g[e] = G[mol(e)]`` and the depth's backward contracts over
+    the B molecules instead of the E edges (``pooled_backward.cu``): no [E, d] gradient tensor is ever written. Anything else (h_L
+    used elsewhere, dropout, strict-fp32 mode, recompute-messages mode) takes the dense backward of ``_Layer`` - same results."""
+
+    @staticmethod
+    def forward(ctx, h: Tensor, W: Tensor, b: Tensor | None, csr: GraphCSR, pool: SegmentCSR, act: int, act_param: float, mean: bool,
+                residual: bool, p: float, seed: int, offset: int, mode: int):
+        h = _require_float(h, "edge_feats")
+        W = _require_float(W, "weight")
+        E, d = h.shape
+        if E != csr.E or pool.keys32.numel() != E:
+            raise RuntimeError(f"notorch_b200: edge_feats has {E} rows but the graph has {csr.E} edges")
+        if W.shape != (d, d):
+            raise RuntimeError(f"notorch_b200: weight {tuple(W.shape)} does not match hidden size {d}")
+        if b is not None:
+            b = _require(b, "bias", torch.float32, 1)
+        save_m = _save_messages and mode != GEMM_FP32 and d % 4 == 0 and (ctx.needs_input_grad[1] or (b is not None and ctx.needs_input_grad[2]))
+        img_t_out: list | None = [] if (ctx.needs_input_grad[0] and mode != GEMM_FP32) else None
+        out, m, n, _ = _layer_forward_raw(h, W, b, csr, act, act_param, mean, residual, p, seed, offset, mode, save_m, 0, img_t_out)
+        with torch.cuda.device(h.device):
+            H = _seg_reduce_raw(out, pool, tag="K3e")
+        ctx.save_for_backward(h, m if save_m else n, W)
+        ctx.img_t = img_t_out[0] if img_t_out else None
+        ctx.csr, ctx.pool, ctx.cfg, ctx.has_bias, ctx.has_m = csr, pool, (act, act_param, mean, residual, p, seed, offset, mode), b is not None, save_m
+        ctx.set_materialize_grads(False)
+        return out, H
+
+    @staticmethod
+    def backward(ctx, g_out: Tensor | None, g_H: Tensor | None):
+        nothing = (None,) * 13
+        if g_out is None and g_H is None:
+            return nothing
+        h, n_or_m, W = ctx.saved_tensors
+        act, act_param, mean, residual, p, seed, offset, mode = ctx.cfg
+        csr, pool = ctx.csr, ctx.pool
+        need_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        need_h = ctx.needs_input_grad[0]
+        E, d = h.shape
+        pooled = _pooled_backward and g_out is None and p == 0.0 and mode != GEMM_FP32 and d % 4 == 0 and (ctx.has_m or not need_w)
+        if not pooled:
+            # dense gradient of h_L: what reached the edge states directly plus the read-out's broadcast
+            if g_H is None:
+                g = g_out.contiguous()
+            else:
+                with torch.cuda.device(h.device):
+                    g = _gather_add_raw(None if g_out is None else g_out.contiguous(), g_H.contiguous(), pool.keys32, None, tag="K3ebwd")
+            m, n = (n_or_m, None) if ctx.has_m else (None, n_or_m)
+            gh, gW, gb = _layer_backward_raw(g, h, m, n, W, ctx.has_bias, csr, act, act_param, mean, residual, p, seed, offset, mode, need_w, need_h,
+                                             None, ctx.img_t)
+            return (gh, gW, gb) + (None,) * 10
+        G = g_H.contiguous()
+        B = G.shape[0]
+        L = _lib.lib()
+        gh = gW = gb = None
+        with torch.cuda.device(h.device):
+            if need_w:
+                M = _seg_reduce_raw(n_or_m, pool, tag="K3m")  # [B, d]: the messages summed over each molecule's edges
+                gW = torch.empty_like(W)
+                ws = _workspace(h.device, L.nt_layer_backward_wgrad_workspace_bytes(B, d), slot=1)
+                _run("K4bp:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(G), _p(M), None, None, None, None, B, 1, d, act, act_param, 0.0, 0, 0,
+                     _p(gW), None, _p(ws), ws.numel(), NT_F32, mode, _stream())
+                if ctx.has_bias:
+                    gb = torch.empty(d, dtype=W.dtype, device=W.device)
+                    _run("gbp:nt_weighted_colsum", L.nt_weighted_colsum, _p(G), _p(pool.rowptr), B, d, _p(gb), NT_F32, _stream())
+            if need_h:
+                img_t = ctx.img_t if ctx.img_t is not None else _weight_image(W, True)
+                GW = torch.empty_like(G)
+                _run("K4ap:nt_layer_backward_dgrad", L.nt_layer_backward_dgrad, _p(G), _p(W), _p(img_t), B, d, 0.0, 0, 0, _p(GW), NT_F32, mode, _stream())
+                gh = torch.empty_like(h)
+                ws6 = _workspace(h.device, L.nt_layer_backward_epilogue_pooled_workspace_bytes(E))
+                _run("K6p:nt_layer_backward_epilogue_pooled", L.nt_layer_backward_epilogue_pooled, _p(G), _p(GW), _p(h), _p(pool.keys32), _p(csr.dst),
+                     _p(csr.by_src.rowptr), _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr), E, B, d, act, act_param, int(residual),
+                     int(mean), _p(gh), _p(ws6), ws6.numel(), NT_F32, _stream())
+        return (gh, gW, gb) + (None,) * 10
+
+
 # ------------------------------------------------------------------------------------------------
 # public functional API
 # ------------------------------------------------------------------------------------------------
@@ -866,8 +956,11 @@ def readout(node_feats: Tensor, mol_csr: SegmentCSR, kind: str = "sum", norm: fl
 
 
 def layer(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, *, act: tuple[int, float] = (_lib.ACT_RELU, 0.0),
-          reduce: str = "sum", residual: bool = True, dropout: float = 0.0, training: bool = False) -> Tensor:
-    """One fused message-passing depth (K1+K2; hand-written backward K4-K6)."""
+          reduce: str = "sum", residual: bool = True, dropout: float = 0.0, training: bool = False,
+          pool: SegmentCSR | None = None) -> Tensor | tuple[Tensor, Tensor]:
+    """One fused message-passing depth (K1+K2; hand-written backward K4-K6). ``pool`` (the CSR of the molecules' contiguous edge
+    ranges): also return the sum of the new edge states over every molecule, ``(h', H_sum)`` - the form the last depth of a block
+    takes in front of a sum read-out (``_LayerPooled``)."""
     global _dropout_calls
     if reduce not in _REDUCTIONS:
         raise ValueError(f"notorch_b200: unknown reduce '{reduce}' (one of {_REDUCTIONS})")
@@ -882,6 +975,10 @@ def layer(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, *, act:
         _dropout_calls += 1
         offset = _dropout_calls
     extreme = {"max": 1, "min": 2}.get(reduce, 0)
+    if pool is not None:
+        if extreme != 0 or _via_ops(h, weight):
+            raise RuntimeError("notorch_b200: the pooled form of a depth needs a sum / mean reduction and real CUDA tensors")
+        return _LayerPooled.apply(h, weight, bias, csr, pool, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)
     if extreme == 0 and _via_ops(h, weight):
         return _torch_ops().layer_from_csr(h, weight, bias, csr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)
     return _Layer.apply(h, weight, bias, csr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode, extreme)

@@ -48,10 +48,12 @@ def wgrad(E, d, positive):
           f"  ({2.0 * E * d * (d + 1) / t / 1e6:6.1f} alg TFLOP/s)", flush=True)
 
 
-for E, d in ((100, 300), (600, 300), (1100, 300), (33000, 300), (205166, 300), (300000, 300), (37, 64), (5000, 256), (70000, 256),
-             (40000, 1024), (819000 // 4, 1024), (20000, 2048), (9000, 332), (9000, 576)):
-    for positive in (False, True):
-        wgrad(E, d, positive)
+WG_SHAPES = ((100, 300), (600, 300), (1100, 300), (33000, 300), (205166, 300), (300000, 300), (37, 64), (5000, 256), (70000, 256),
+             (40000, 1024), (819000 // 4, 1024), (20000, 2048), (9000, 332), (9000, 576))
+if "wgrad" in sys.argv or len(sys.argv) == 1:
+    for E, d in WG_SHAPES:
+        for positive in (False, True):
+            wgrad(E, d, positive)
 
 # ---------------------------------------------------------------- K6
 d = 300
@@ -79,7 +81,8 @@ def k4a_then_k6(o):  # the real sequence: K4a writes g_m front to back, K6 follo
 
 
 alg = (V + 4 * E) * d * 4 + 12 * E
-for mean in (0, 1):
+RUN_K6 = "k6" in sys.argv or len(sys.argv) == 1
+for mean in (0, 1) if RUN_K6 else ():
     for v in (0, 1, 2, 3):
         os.environ["NOTORCH_B200_K6_VARIANT"] = str(v)
         outs[v] = torch.full_like(h, float("nan"))
@@ -87,11 +90,55 @@ for mean in (0, 1):
     torch.cuda.synchronize()
     print(f"K6 mean={mean}: variants equal {all(torch.equal(outs[0], outs[v]) for v in (1, 2, 3))}")
 o = torch.empty_like(h)
-t4a = timed(lambda: _lib.check(L.nt_layer_backward_dgrad(p(g), p(W), p(img_t), E, d, 0.0, 0, 0, p(g_m), _lib.NT_F32, _lib.GEMM_TF32X3, st()), "k4a"))
+if not RUN_K6:
+    t4a = 0.0
+else:
+  t4a = timed(lambda: _lib.check(L.nt_layer_backward_dgrad(p(g), p(W), p(img_t), E, d, 0.0, 0, 0, p(g_m), _lib.NT_F32, _lib.GEMM_TF32X3, st()), "k4a"))
 print(f"K4a alone {t4a:7.1f} us")
-for v in (0, 1, 2, 3):
+for v in (0, 1, 2, 3) if RUN_K6 else ():
     os.environ["NOTORCH_B200_K6_VARIANT"] = str(v)
     t = timed(lambda: k6(o))
     t2 = timed(lambda: k4a_then_k6(o))
     print(f"K6 variant {v}: {t:7.1f} us L2 flushed ({alg / t / 1e3:6.0f} GB/s algorithmic);  after K4a: {t2 - t4a:7.1f} us", flush=True)
-os.environ.pop("NOTORCH_B200_K6_VARIANT")
+os.environ.pop("NOTORCH_B200_K6_VARIANT", None)
+
+# ---------------------------------------------------------------- embedding-table gradient: mma.sync kernel vs the tcgen05 pair kernel
+if "embbwd" in sys.argv or len(sys.argv) == 1:
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for dd, Tv, Te in ((300, 45, 13), (64, 45, 13), (1024, 100, 20), (300, 10, 3)):
+        nt_ = torch.randint(0, Tv, (V, 7), device="cuda", generator=gen)
+        et_ = torch.randint(0, Te, (E, 2), device="cuda", generator=gen)
+        gg = torch.randn(E, dd, device="cuda", generator=gen)
+        src64 = csr.src.long()
+        cnt_v = torch.zeros(E, Tv, dtype=torch.float64, device="cuda").scatter_add_(1, nt_[src64], torch.ones(E, 7, dtype=torch.float64, device="cuda"))
+        cnt_e = torch.zeros(E, Te, dtype=torch.float64, device="cuda").scatter_add_(1, et_, torch.ones(E, 2, dtype=torch.float64, device="cuda"))
+        ref_v, ref_e = cnt_v.t() @ gg.double(), cnt_e.t() @ gg.double()
+        for kind in ("mma", "tc"):
+            if kind == "mma" and Tv + Te > 64:
+                continue
+            os.environ["NOTORCH_B200_EMBBWD"] = kind
+            f = lambda: ops._embed_edge_init_backward_raw(gg, nt_, et_, csr.src, V, Tv, Te)
+            gv, ge = f(); torch.cuda.synchronize()
+            gv2, ge2 = f(); torch.cuda.synchronize()
+            ev = float((gv.double() - ref_v).abs().max() / ref_v.abs().max()); ee = float((ge.double() - ref_e).abs().max() / ref_e.abs().max())
+            t = timed(f)
+            print(f"embbwd {kind:3s} d={dd:5d} T={Tv}+{Te}: gTv {ev:.2e} gTe {ee:.2e} deterministic {torch.equal(gv, gv2) and torch.equal(ge, ge2)} {t:7.1f} us", flush=True)
+    os.environ.pop("NOTORCH_B200_EMBBWD")
+
+# ---------------------------------------------------------------- L2 look-ahead of the pair weight-gradient kernel (NOTORCH_B200_WGRAD_PF)
+if "pf" in sys.argv:
+    for pf in (0, 2, 4, 6, 10):
+        os.environ["NOTORCH_B200_WGRAD_PF"] = str(pf)
+        print(f"--- look-ahead {pf} K-blocks")
+        for E_, d_ in ((205166, 300), (204750, 1024), (20000, 2048)):
+            wgrad(E_, d_, False)
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        Tv, Te, dd = 45, 13, 300
+        nt_ = torch.randint(0, Tv, (V, 7), device="cuda", generator=gen); et_ = torch.randint(0, Te, (E, 2), device="cuda", generator=gen)
+        gg = torch.randn(E, dd, device="cuda", generator=gen)
+        ws = torch.empty(L.nt_embed_edge_init_backward_workspace_bytes(E, Tv, Te, dd), dtype=torch.uint8, device="cuda")
+        gv, ge = torch.empty(Tv, dd, device="cuda"), torch.empty(Te, dd, device="cuda")
+        f = lambda: _lib.check(L.nt_embed_edge_init_backward(p(gg), p(nt_), 7, p(et_), 2, p(csr.src), E, V, Tv, Te, dd, p(gv), p(ge), p(ws), ws.numel(),
+                                                             _lib.NT_F32, st()), "embbwd")
+        print(f"embbwd tc d=300: {timed(f):7.1f} us", flush=True)
+    os.environ.pop("NOTORCH_B200_WGRAD_PF")

@@ -28,7 +28,7 @@ def _load(blk, p):
             layer.module.update[0].bias.copy_(p["biases"][l])
 
 
-def _block_parity(p, depth, agg_kind, mode, *, rel=REL_F32, check_fp32_oracle=True, with_gE=True):
+def _block_parity(p, depth, agg_kind, mode, *, rel=REL_F32, check_fp32_oracle=True, with_gE=True, packed=False):
     """ChempropBlock + read-out through the nn modules vs the oracle: forward against the fp32 AND fp64 oracle, every gradient against
     the fp64 hand-derived backward (chemprop.py:81-88, agg.py:27,36). Prints the ReLU sign-flip count and the gradient error both
     with and without evaluating the oracle's ReLU derivative at the CUDA path's own h_l (``act_grad_at``)."""
@@ -45,7 +45,13 @@ def _block_parity(p, depth, agg_kind, mode, *, rel=REL_F32, check_fp32_oracle=Tr
     gH = torch.randn(B, d, generator=gen)
     gE = torch.randn(E, d, generator=gen) if with_gE else None
     xv, xe = p["x_v"].cuda().requires_grad_(True), p["x_e"].cuda().requires_grad_(True)
-    G = BatchedGraph(xv, xe, ei.cuda(), rev.cuda(), batch_node_index=bni.cuda(), batch_edge_index=p["batch_edge_index"].cuda(), size=B)
+    if packed:
+        # device collation (BatchedGraph.from_packed): the block defers the edge -> atom sum, its last depth also returns the sum of h_L
+        # over each molecule's edges, and - when nothing else reads h_L - takes the pooled backward
+        G = BatchedGraph.from_packed(p["mols"], xv, xe, device="cuda")
+        assert G.node_feats is xv and torch.equal(G.edge_index.cpu(), ei) and torch.equal(G.rev_index.cpu(), rev)
+    else:
+        G = BatchedGraph(xv, xe, ei.cuda(), rev.cuda(), batch_node_index=bni.cuda(), batch_edge_index=p["batch_edge_index"].cuda(), size=B)
     # the per-depth states, to count ReLU sign flips against the fp64 run (same launches the block makes)
     csr = ops.graph_csr(G)
     hs = [ops.edge_init(xv.detach(), xe.detach(), csr)]
@@ -100,6 +106,59 @@ def test_config2_full_size_elementwise():
     against the fp32 and fp64 oracle (the CPU oracle does this size in seconds)."""
     p = oracle_inputs(4096, 300, 3, config=2, seed=2)
     _block_parity(p, 3, "sum", "tf32x3", with_gE=False)  # the bench's loss touches H only
+
+
+def test_config2_full_size_elementwise_device_collated_pooled_backward():
+    """The same size through the path the bench takes: device collation, read-out summed over the molecules' edges, and the last
+    depth's backward contracted over the B molecules (gW = M^T G, g_m = (G W)[mol e]; pooled_backward.cu) - against the fp64 oracle."""
+    p = oracle_inputs(4096, 300, 3, config=2, seed=2)
+    _block_parity(p, 3, "sum", "tf32x3", with_gE=False, packed=True, check_fp32_oracle=False)
+
+
+@pytest.mark.parametrize("agg_kind,with_gE,d,depth", [("sum", False, 64, 2), ("mean", False, 64, 1), ("sum", True, 64, 2), ("mean", False, 300, 3)])
+def test_pooled_last_depth_small(agg_kind, with_gE, d, depth):
+    """Device-collated batches at small sizes: Sum and Mean read-outs, one depth (the pooled depth is also the first), and a loss that
+    also reads h_L (the gradient of h_L is then not a broadcast: the depth falls back to the dense backward)."""
+    p = oracle_inputs(48, d, depth, config=1, seed=61 + d)
+    _block_parity(p, depth, agg_kind, "tf32x3", with_gE=with_gE, packed=True)
+
+
+@pytest.mark.parametrize("reduce,residual,bias,act", [("sum", True, True, "relu"), ("mean", True, True, "relu"), ("sum", False, False, "tanh"),
+                                                      ("mean", False, True, "elu")])
+def test_pooled_depth_equals_dense_depth(reduce, residual, bias, act):
+    """ops.layer(pool=...) - (h', H_sum) with the pooled backward - against the dense formulation of the same thing (ops.layer, then the
+    segmented sum, whose backward materialises the [E, d] broadcast): forward bits equal, every gradient within the fp32 bound
+    (the contraction runs over molecules instead of edges: another summation order). Mean reduction, no residual, no bias,
+    smooth activations."""
+    import torch.nn as nn
+
+    from notorch_b200 import BatchedGraph, ops
+
+    d, B = 96, 64
+    p = oracle_inputs(B, d, 1, config=1, seed=77)
+    G = BatchedGraph.from_packed(p["mols"], p["x_v"], p["x_e"], device="cuda")
+    csr, pool = ops.graph_csr(G), ops.mol_edge_csr(G)
+    gen = torch.Generator().manual_seed(5)
+    h0 = torch.randn(p["E"], d, generator=gen).cuda()
+    W0 = ((torch.rand(d, d, generator=gen) * 2 - 1) / d ** 0.5).cuda()
+    b0 = torch.randn(d, generator=gen).cuda() / 10 if bias else None
+    gH = torch.randn(B, d, generator=gen).cuda()
+    code = ops.act_code({"relu": nn.ReLU(), "tanh": nn.Tanh(), "elu": nn.ELU()}[act])
+    res = []
+    for pooled in (True, False):
+        h, W = h0.clone().requires_grad_(True), W0.clone().requires_grad_(True)
+        b = b0.clone().requires_grad_(True) if bias else None
+        if pooled:
+            out, H = ops.layer(h, W, b, csr, act=code, reduce=reduce, residual=residual, pool=pool)
+        else:
+            out = ops.layer(h, W, b, csr, act=code, reduce=reduce, residual=residual)
+            H = ops.seg_reduce(out, pool, "sum")
+        (H * gH).sum().backward()
+        res.append((out.detach(), H.detach(), h.grad, W.grad, b.grad if bias else None))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    for a, c, what in zip(res[0][2:], res[1][2:], ("grad h", "grad W", "grad b")):
+        if a is not None:
+            assert_close(a, c, f"{what}: pooled vs dense ({reduce}, residual={residual}, {act})", 3e-6)
 
 
 def test_config2_full_size_elementwise_with_edge_cotangent():
@@ -351,12 +410,14 @@ def test_readout_over_edges_matches_the_two_stage_path(kind):
             H = agg(G1)
             assert isinstance(G1.peek("node_feats"), PendingFeats) == fused  # the read-out did not materialise the atoms
             (H * gH).sum().backward()
-            res[fused] = (H.detach().clone(), G.node_feats.grad.clone(), blk.layers[0].module.update[0].weight.grad.clone(), G1.node_feats.detach().clone())
+            last = blk.layers[-1].module.update[0]
+            res[fused] = (H.detach().clone(), G.node_feats.grad.clone(), blk.layers[0].module.update[0].weight.grad.clone(),
+                          last.weight.grad.clone(), last.bias.grad.clone(), G1.node_feats.detach().clone())
         finally:
             ops._fuse_readout = True
-    for a, b, what in zip(res[True][:3], res[False][:3], ("H", "grad x_v", "grad W0")):
-        assert_close(a, b, f"{what}: over edges vs two-stage", 2e-6)
-    assert torch.equal(res[True][3], res[False][3])  # node_feats read afterwards: the same K1 launch, the same bits
+    for a, b, what in zip(res[True][:5], res[False][:5], ("H", "grad x_v", "grad W0", "grad W of the last depth", "grad b of the last depth")):
+        assert_close(a, b, f"{what}: over edges (pooled backward) vs two-stage", 3e-6)
+    assert torch.equal(res[True][5], res[False][5])  # node_feats read afterwards: the same K1 launch, the same bits
     Ws, bs = [w.double() for w in p["weights"]], [b.double() for b in p["biases"]]
     node64, _, _ = O.block_forward(p["x_v"].double(), p["x_e"].double(), p["edge_index"], p["rev_index"], Ws, bs)
     assert_close(res[True][0], O.readout(node64, p["batch_node_index"], B, kind), f"H ({kind}) vs fp64 oracle")
@@ -366,3 +427,31 @@ def test_readout_over_edges_matches_the_two_stage_path(kind):
     G3 = blk(G2)
     assert isinstance(G3.peek("node_feats"), torch.Tensor)
     assert_close(agg(G3), res[False][0], "H on a hand-made graph", 1e-6)
+
+
+# ---------------------------------------------------------------- embedding-table gradient at sizes with several accumulation groups
+@pytest.mark.parametrize("kind", ["tc", "mma"])
+@pytest.mark.parametrize("d,Tv,Te", [(64, 45, 13), (300, 45, 13), (128, 100, 20)])
+def test_embedding_table_gradient_many_row_blocks(kind, d, Tv, Te, monkeypatch):
+    """embed.py:20-24 backward (EmbeddingBag(mode="sum") x2 through the src gather) with E = 150 k rows: every CTA of the warp-level
+    kernel runs several flush groups (its fixed-order sum has to read EVERY partial table - a defect the small fixtures hid) and
+    every CTA pair of the tcgen05 form several accumulator segments. Both against an fp64 evaluation; bit-identical across runs."""
+    from notorch_b200 import ops
+
+    if kind == "mma" and Tv + Te > 64:
+        pytest.skip("the warp-level kernel holds at most 64 types")
+    monkeypatch.setenv("NOTORCH_B200_EMBBWD", kind)
+    gen = torch.Generator(device="cuda").manual_seed(17 + d)
+    V, E = 60_000, 150_001
+    src = torch.randint(0, V, (E,), device="cuda", generator=gen)
+    nt_ = torch.randint(0, Tv, (V, 7), device="cuda", generator=gen)
+    et_ = torch.randint(0, Te, (E, 2), device="cuda", generator=gen)
+    g = torch.randn(E, d, device="cuda", generator=gen)
+    one = torch.ones(1, dtype=torch.float64, device="cuda")
+    cnt_v = torch.zeros(E, Tv, dtype=torch.float64, device="cuda").scatter_add_(1, nt_[src], one.expand(E, 7))
+    cnt_e = torch.zeros(E, Te, dtype=torch.float64, device="cuda").scatter_add_(1, et_, one.expand(E, 2))
+    ref_v, ref_e = cnt_v.t() @ g.double(), cnt_e.t() @ g.double()
+    runs = [ops._embed_edge_init_backward_raw(g, nt_, et_, src.int(), V, Tv, Te) for _ in range(2)]
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    assert_close(runs[0][0].cpu(), ref_v.cpu(), f"grad node table ({kind})")
+    assert_close(runs[0][1].cpu(), ref_e.cpu(), f"grad edge table ({kind})")
