@@ -128,7 +128,7 @@ def algorithmic_bytes(V: int, E: int, B: int, d: int, L: int, s: int = 4) -> dic
         "K3bwd": (V + B) * d * s + 4 * V,
         "K3e": (E + B) * d * s + 4 * (B + 1),  # read-out summed straight over the molecules' edge states (K1 + K3 in one pass)
         "K3ebwd": (E + B) * d * s + 4 * E,
-        "K3m": (E + B) * d * s + 4 * (B + 1),  # pooled backward of the last depth: the messages summed per molecule
+        "Kpm": (2 * E + 2 * B) * d * s + 12 * E,  # last depth on the molecules: h and h[rev] in, M and S [B, d] out
         "K6p": 2 * (E + B) * d * s + 16 * E,  # ... and its epilogue: h in, g_h out, the [B, d] gradients from L2
         "K0e": (V * 7 + E * 2) * 8 + 4 * E + E * d * s,  # fused GraphEmbedding + edge init: type ids + src in, h0 out
         "K0ebwd": (V * 7 + E * 2) * 8 + 4 * E + E * d * s,  # one pass over g_{h0}, ids again

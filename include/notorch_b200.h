@@ -249,6 +249,16 @@ int nt_layer_backward_epilogue_fused(const void* g, const void* h, const void* g
  * nt_layer_backward_epilogue_fused. Requires that a molecule's edges connect only its own atoms (BatchedGraph.from_packed).
  * ---------------------------------------------------------------------------------------------- */
 int nt_weighted_colsum(const void* x, const int32_t* rowptr, int64_t rows, int64_t d, void* out, int dtype, nt_stream_t stream);
+/* Forward of the same collapse (chemprop.py:37-41 + residual.py:28 + agg.py:27 for the LAST depth): one pass over h = h_{L-1},
+ *   M[b,:] = sum_{e in b} (outdeg(dst e) [/ indeg(dst e)] act(h[e,:]) - act(h[rev e,:]))   = sum_{e in b} m[e,:]
+ *   S[b,:] = (residual ? sum_{e in b} h[e,:] : 0) + |b| bias                                  (bias may be NULL)
+ * then H_sum = S + M . W^T through nt_dense_forward(x = M, resid = S) on B rows. mol_edge_ptr [B + 1]: the molecules' contiguous edge
+ * ranges; workspace: 8 bytes per edge. */
+size_t nt_pooled_message_sum_workspace_bytes(int64_t E);
+int nt_pooled_message_sum(const void* h, const int32_t* rev, const int32_t* dst, const int32_t* src_rowptr,
+                          const int32_t* dst_rowptr, const int32_t* mol_edge_ptr, const void* bias, int64_t E, int64_t B,
+                          int64_t d, int act, float act_param, int residual, int mean, void* M, void* S, void* workspace,
+                          size_t workspace_bytes, int dtype, nt_stream_t stream);
 size_t nt_layer_backward_epilogue_pooled_workspace_bytes(int64_t E); /* 16 bytes per edge: the per-edge index record */
 int nt_layer_backward_epilogue_pooled(const void* gH, const void* gHW, const void* h, const int32_t* mol_of_edge,
                                       const int32_t* dst, const int32_t* src_rowptr, const int32_t* rev_rowptr,

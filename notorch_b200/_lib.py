@@ -51,6 +51,8 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "nt_layer_backward_epilogue_arg": (_int, [_vp, _vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _vp, _int, _vp]),
     "nt_layer_backward_epilogue_fused": (_int, [_vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _int, _f32, _int, _int, _vp, _int, _vp]),
     "nt_weighted_colsum": (_int, [_vp, _i32p, _i64, _i64, _vp, _int, _vp]),
+    "nt_pooled_message_sum_workspace_bytes": (_sz, [_i64]),
+    "nt_pooled_message_sum": (_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p, _vp, _i64, _i64, _i64, _int, _f32, _int, _int, _vp, _vp, _vp, _sz, _int, _vp]),
     "nt_layer_backward_epilogue_pooled_workspace_bytes": (_sz, [_i64]),
     "nt_layer_backward_epilogue_pooled": (_int, [_vp, _vp, _vp, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _i64, _int, _f32, _int, _int, _vp,
                                                  _vp, _sz, _int, _vp]),

@@ -10,7 +10,15 @@
 //     g_m  = g W              = (G W)[mol(e), :]                                           (K4a on B rows; g_m [E, d] is never written)
 //     g_n[v] = sum_{e: src[e] = v} g_m[e] = outdeg(v) (G W)[mol(v)]                        (a molecule's edges connect its own atoms)
 //     g_h[e] = [G[mol e]] + act'(h[e]) * (g_n[dst e] (/ indeg) - sum_{e'': rev[e''] = e} (G W)[mol e''])      (kernel below)
-// The [E, d] tensors g, g_m and g_n are never materialised: the last depth's backward reads m once and h once and writes g_h.
+// The [E, d] tensors g, g_m and g_n are never materialised.
+//
+// The same collapse runs FORWARD (nt_pooled_message_sum below): what the read-out needs of the last depth is
+//     H_sum[b] = sum_{e in b} h_L[e] = sum_{e in b} h[e] + |b| bias + (sum_{e in b} m[e]) W^T,        h = h_{L-1}
+//     sum_{e in b} m[e] = sum_{e in b} (n[src e] - a[rev e]) = sum_{e in b} (outdeg(dst e) [/ indeg(dst e)] a[e] - a[rev e]),   a = act(h)
+// (sum_{e in b} n[src e] = sum_{v in b} outdeg(v) n[v] and n[v] = sum_{e: dst e = v} a[e] [/ indeg v]; every atom and edge involved
+// belongs to b). One pass over h with its rev gather gives M = sum m and S = sum h + |b| bias as [B, d] matrices, the Linear runs
+// on B rows (nt_dense_forward) - K1, K2 and the read-out's pass over h_L are not launched for the last depth, h_L and m_L are not
+// written, and the backward reuses M. h_L itself stays available: ChempropBlock computes it (the dense depth) only if it is read.
 // Exact algebra, another summation order (tested against the dense path and the fp64 oracle).
 #include "common.cuh"
 
@@ -66,40 +74,134 @@ __global__ void __launch_bounds__(PB_THREADS) pooled_record_kernel(const int32_t
   rec[e] = make_int4(__ldg(mol + e), __float_as_int(scale), first, hi - lo);
 }
 
-// one thread per (edge, 16-byte chunk). DRAM traffic: h[e] in, g_h[e] out; G and GW ([B, d], a few MB) stay in L2 / L1.
+// PB_ITEMS (edge, 16-byte chunk) items per thread, PB_THREADS apart. DRAM traffic: h[e] in, g_h[e] out; G and GW ([B, d], a few MB)
+// stay in L2 / L1. With ONE item per thread the kernel had 16 bytes of DRAM reads in flight per thread - 20 KB per SM against
+// ~1.5 us of latency = 2 TB/s (measured: 168 us for 0.49 GB); all level-1 loads of the four items are issued before anything is used.
+constexpr int PB_ITEMS = 4;
+
 template <int AK>
-__global__ void __launch_bounds__(PB_THREADS, 5) layer_bwd_epilogue_pooled(const float* __restrict__ G, const float* __restrict__ GW,
+__global__ void __launch_bounds__(PB_THREADS, 2) layer_bwd_epilogue_pooled(const float* __restrict__ G, const float* __restrict__ GW,
                                                                            const float* __restrict__ h, const int4* __restrict__ rec,
                                                                            const int32_t* __restrict__ mol, const int32_t* __restrict__ rev_rowptr,
                                                                            const int32_t* __restrict__ rev_perm, int d, int chunks, int64_t total,
                                                                            uint64_t magic, int act, float act_param, int residual,
                                                                            float* __restrict__ g_h) {
-  const int64_t t = (int64_t)blockIdx.x * PB_THREADS + threadIdx.x;
-  if (t >= total) return;
-  int e, c;
-  split_item(t, chunks, magic, e, c);
-  c *= 4;
-  // level 1: the edge's own row of h (the DRAM stream) and its record
-  const float4 hv = ldg4_stream(h + (int64_t)e * d + c);
-  const int4 r4 = __ldg(rec + e);
-  // level 2: the [B, d] rows (L2 / L1)
-  const float4 gw = ldg4(GW + (int64_t)r4.x * d + c);
-  float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (residual) gv = ldg4(G + (int64_t)r4.x * d + c);
-  float4 sub = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (r4.z >= 0) sub = ldg4(GW + (int64_t)r4.z * d + c);
-  if (r4.w > 1) {  // several edges' rev point here (the reference's atom-offset rev_index quirk): the rest through the CSR
-    const int lo = __ldg(rev_rowptr + e);
-    for (int j = lo + 1; j < lo + r4.w; ++j) {
-      const float4 r = ldg4(GW + (int64_t)__ldg(mol + __ldg(rev_perm + j)) * d + c);
-      sub = make_float4(sub.x + r.x, sub.y + r.y, sub.z + r.z, sub.w + r.w);
+  const int64_t t0 = (int64_t)blockIdx.x * (PB_THREADS * PB_ITEMS) + threadIdx.x;
+  int e[PB_ITEMS], c[PB_ITEMS];
+  bool live[PB_ITEMS];
+  float4 hv[PB_ITEMS], gw[PB_ITEMS], gv[PB_ITEMS], sub[PB_ITEMS];
+  int4 r4[PB_ITEMS];
+  // level 1: the edges' own rows of h (the DRAM stream) and their records
+#pragma unroll
+  for (int k = 0; k < PB_ITEMS; ++k) {
+    const int64_t t = t0 + (int64_t)k * PB_THREADS;
+    live[k] = t < total;
+    split_item(live[k] ? t : 0, chunks, magic, e[k], c[k]);
+    c[k] *= 4;
+    if (live[k]) {
+      hv[k] = ldg4_stream(h + (int64_t)e[k] * d + c[k]);
+      r4[k] = __ldg(rec + e[k]);
     }
   }
-  const float scale = __int_as_float(r4.y);
-  float4 r = make_float4(pb_act_bwd(AK, hv.x, act, act_param) * (scale * gw.x - sub.x), pb_act_bwd(AK, hv.y, act, act_param) * (scale * gw.y - sub.y),
-                         pb_act_bwd(AK, hv.z, act, act_param) * (scale * gw.z - sub.z), pb_act_bwd(AK, hv.w, act, act_param) * (scale * gw.w - sub.w));
-  if (residual) r = make_float4(gv.x + r.x, gv.y + r.y, gv.z + r.z, gv.w + r.w);
-  stg4(g_h + (int64_t)e * d + c, r);
+  // level 2: the [B, d] rows (L2 / L1)
+#pragma unroll
+  for (int k = 0; k < PB_ITEMS; ++k) {
+    gv[k] = sub[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live[k]) {
+      gw[k] = ldg4(GW + (int64_t)r4[k].x * d + c[k]);
+      if (residual) gv[k] = ldg4(G + (int64_t)r4[k].x * d + c[k]);
+      if (r4[k].z >= 0) sub[k] = ldg4(GW + (int64_t)r4[k].z * d + c[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PB_ITEMS; ++k) {
+    if (!live[k]) continue;
+    if (r4[k].w > 1) {  // several edges' rev point here (the reference's atom-offset rev_index quirk): the rest through the CSR
+      const int lo = __ldg(rev_rowptr + e[k]);
+      for (int j = lo + 1; j < lo + r4[k].w; ++j) {
+        const float4 r = ldg4(GW + (int64_t)__ldg(mol + __ldg(rev_perm + j)) * d + c[k]);
+        sub[k] = make_float4(sub[k].x + r.x, sub[k].y + r.y, sub[k].z + r.z, sub[k].w + r.w);
+      }
+    }
+    const float scale = __int_as_float(r4[k].y);
+    float4 r = make_float4(pb_act_bwd(AK, hv[k].x, act, act_param) * (scale * gw[k].x - sub[k].x),
+                           pb_act_bwd(AK, hv[k].y, act, act_param) * (scale * gw[k].y - sub[k].y),
+                           pb_act_bwd(AK, hv[k].z, act, act_param) * (scale * gw[k].z - sub[k].z),
+                           pb_act_bwd(AK, hv[k].w, act, act_param) * (scale * gw[k].w - sub[k].w));
+    if (residual) r = make_float4(gv[k].x + r.x, gv[k].y + r.y, gv[k].z + r.z, gv[k].w + r.w);
+    stg4(g_h + (int64_t)e[k] * d + c[k], r);
+  }
+}
+
+// ---- forward: M[b] = sum_{e in b} (w_e act(h[e]) - act(h[rev e])),  S[b] = [sum_{e in b} h[e]] + |b| bias -----------------------
+// per-edge record {rev[e], bits of w_e = outdeg(dst e) [/ indeg(dst e)]}: the main loop then issues its row loads without walking
+// dst -> rowptr first
+__global__ void __launch_bounds__(PB_THREADS) pooled_fwd_record_kernel(const int32_t* __restrict__ rev, const int32_t* __restrict__ dst,
+                                                                       const int32_t* __restrict__ src_rowptr, const int32_t* __restrict__ dst_rowptr,
+                                                                       int64_t E, int mean, int2* __restrict__ rec) {
+  const int64_t e = (int64_t)blockIdx.x * PB_THREADS + threadIdx.x;
+  if (e >= E) return;
+  const int v = __ldg(dst + e);
+  float w = (float)(__ldg(src_rowptr + v + 1) - __ldg(src_rowptr + v));
+  if (mean) w = w / (float)max(__ldg(dst_rowptr + v + 1) - __ldg(dst_rowptr + v), 1);
+  int r = __ldg(rev + e);
+  if (r < 0 || r >= E) r = (int)e;  // out-of-range indices are reported by nt_build_csr; stay in bounds here
+  rec[e] = make_int2(r, __float_as_int(w));
+}
+
+template <int AK>
+__device__ __forceinline__ float4 pb_act4(float4 v, int act, float p) {
+  if (AK == 0) return v;
+  if (AK == 1) return make_float4(v.x < 0.f ? 0.f : v.x, v.y < 0.f ? 0.f : v.y, v.z < 0.f ? 0.f : v.z, v.w < 0.f ? 0.f : v.w);
+  return act_fwd4(v, act, p);
+}
+
+// one thread per (molecule, 16-byte chunk); the molecule's edges are walked in ascending order, two per trip (four row loads in
+// flight per thread): sequential fp32 accumulation, deterministic
+template <int AK>
+__global__ void __launch_bounds__(PB_THREADS) pooled_message_sum_kernel(const float* __restrict__ h, const int2* __restrict__ rec,
+                                                                        const int32_t* __restrict__ eptr, const float* __restrict__ bias, int d,
+                                                                        int chunks, int64_t total, uint64_t magic, int act, float act_param,
+                                                                        int residual, float* __restrict__ M, float* __restrict__ S) {
+  const int64_t t = (int64_t)(gridDim.x - 1 - blockIdx.x) * PB_THREADS + threadIdx.x;  // from the end: the tail of h is what the producer left in L2
+  if (t >= total) return;
+  int b, c;
+  split_item(t, chunks, magic, b, c);
+  c *= 4;
+  const int lo = __ldg(eptr + b), hi = __ldg(eptr + b + 1);
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f), s = m;
+  for (int e = lo; e < hi; e += 2) {
+    const bool two = e + 1 < hi;
+    const int2 r0 = __ldg(rec + e);
+    const int2 r1 = two ? __ldg(rec + e + 1) : make_int2(0, 0);
+    const float4 h0 = ldg4_stream(h + (int64_t)e * d + c);
+    const float4 g0 = ldg4(h + (int64_t)r0.x * d + c);
+    float4 h1 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = h1;
+    if (two) {
+      h1 = ldg4_stream(h + (int64_t)(e + 1) * d + c);
+      g1 = ldg4(h + (int64_t)r1.x * d + c);
+    }
+    {
+      const float w = __int_as_float(r0.y);
+      const float4 a = pb_act4<AK>(h0, act, act_param), ar = pb_act4<AK>(g0, act, act_param);
+      m = make_float4(m.x + (w * a.x - ar.x), m.y + (w * a.y - ar.y), m.z + (w * a.z - ar.z), m.w + (w * a.w - ar.w));
+      s = make_float4(s.x + h0.x, s.y + h0.y, s.z + h0.z, s.w + h0.w);
+    }
+    if (two) {
+      const float w = __int_as_float(r1.y);
+      const float4 a = pb_act4<AK>(h1, act, act_param), ar = pb_act4<AK>(g1, act, act_param);
+      m = make_float4(m.x + (w * a.x - ar.x), m.y + (w * a.y - ar.y), m.z + (w * a.z - ar.z), m.w + (w * a.w - ar.w));
+      s = make_float4(s.x + h1.x, s.y + h1.y, s.z + h1.z, s.w + h1.w);
+    }
+  }
+  if (!residual) s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) {
+    const float n = (float)(hi - lo);
+    const float4 bv = ldg4(bias + c);
+    s = make_float4(s.x + n * bv.x, s.y + n * bv.y, s.z + n * bv.z, s.w + n * bv.w);
+  }
+  stg4(M + (int64_t)b * d + c, m);
+  stg4(S + (int64_t)b * d + c, s);
 }
 
 }  // namespace nt
@@ -143,7 +245,7 @@ extern "C" int nt_layer_backward_epilogue_pooled(const void* gH, const void* gHW
   const int chunks = (int)(d / 4);
   const int64_t total = E * chunks;
   const uint64_t magic = chunk_div_magic(total, chunks);
-  const unsigned grid = (unsigned)cdiv(total, PB_THREADS);
+  const unsigned grid = (unsigned)cdiv(total, PB_THREADS * PB_ITEMS);
   cudaStream_t st = as_stream(stream);
   const float *Gf = static_cast<const float*>(gH), *GWf = static_cast<const float*>(gHW), *hf = static_cast<const float*>(h);
   float* out = static_cast<float*>(g_h);
@@ -157,5 +259,44 @@ extern "C" int nt_layer_backward_epilogue_pooled(const void* gH, const void* gHW
   else NT_PB_LAUNCH(2);
 #undef NT_PB_LAUNCH
   NT_LAUNCH_CHECK("nt_layer_backward_epilogue_pooled", 2);
+  return NT_OK;
+}
+
+extern "C" size_t nt_pooled_message_sum_workspace_bytes(int64_t E) { return E > 0 ? (size_t)E * sizeof(int2) + 256 : 256; }
+
+extern "C" int nt_pooled_message_sum(const void* h, const int32_t* rev, const int32_t* dst, const int32_t* src_rowptr, const int32_t* dst_rowptr,
+                                     const int32_t* mol_edge_ptr, const void* bias, int64_t E, int64_t B, int64_t d, int act, float act_param,
+                                     int residual, int mean, void* M, void* S, void* workspace, size_t workspace_bytes, int dtype,
+                                     nt_stream_t stream) {
+  if (dtype != NT_F32) { set_error("nt_pooled_message_sum: only NT_F32 is implemented"); return NT_ERR_UNSUPPORTED; }
+  NT_CHECK_ARG(d > 0 && d < (1 << 20) && E >= 0 && E < INT32_MAX && B >= 0 && B < INT32_MAX, "nt_pooled_message_sum: bad sizes");
+  NT_CHECK_ARG(act >= NT_ACT_IDENTITY && act <= NT_ACT_TANH, "nt_pooled_message_sum: bad activation");
+  if (B == 0) return NT_OK;
+  NT_CHECK_ARG(mol_edge_ptr && M && S && (E == 0 || (h && rev && dst && src_rowptr)), "nt_pooled_message_sum: null pointer");
+  NT_CHECK_ARG(!mean || dst_rowptr, "nt_pooled_message_sum: mean needs dst_rowptr");
+  if (d % 4 != 0 || !aligned16(h) || !aligned16(bias) || !aligned16(M) || !aligned16(S)) {
+    set_error("nt_pooled_message_sum: needs d %% 4 == 0 and 16-byte aligned rows");
+    return NT_ERR_UNSUPPORTED;
+  }
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 7u) != 0 || workspace_bytes < nt_pooled_message_sum_workspace_bytes(E)) {
+    set_error("nt_pooled_message_sum: workspace too small (nt_pooled_message_sum_workspace_bytes)");
+    return NT_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  int2* rec = static_cast<int2*>(workspace);
+  if (E > 0) pooled_fwd_record_kernel<<<(unsigned)cdiv(E, PB_THREADS), PB_THREADS, 0, st>>>(rev, dst, src_rowptr, dst_rowptr, E, mean, rec);
+  const int chunks = (int)(d / 4);
+  const int64_t total = B * chunks;
+  const uint64_t magic = chunk_div_magic(total, chunks);
+  const unsigned grid = (unsigned)cdiv(total, PB_THREADS);
+  const float *hf = static_cast<const float*>(h), *bf = static_cast<const float*>(bias);
+  float *Mf = static_cast<float*>(M), *Sf = static_cast<float*>(S);
+#define NT_PM_LAUNCH(AK) \
+  pooled_message_sum_kernel<AK><<<grid, PB_THREADS, 0, st>>>(hf, rec, mol_edge_ptr, bf, (int)d, chunks, total, magic, act, act_param, residual, Mf, Sf)
+  if (act == NT_ACT_IDENTITY) NT_PM_LAUNCH(0);
+  else if (act == NT_ACT_RELU) NT_PM_LAUNCH(1);
+  else NT_PM_LAUNCH(2);
+#undef NT_PM_LAUNCH
+  NT_LAUNCH_CHECK("nt_pooled_message_sum", 2);
   return NT_OK;
 }

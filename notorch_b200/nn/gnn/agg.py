@@ -39,11 +39,14 @@ def _readout_over_edges(G: BatchedGraph, kind: str, norm: float = 100.0) -> Tens
     eptr = getattr(G, "_nt_mol_edge_ptr", None)
     if not (ops._fuse_readout and isinstance(x, PendingFeats) and not x.materialized and x.origin[0] == "edge_to_atom_sum" and eptr is not None):
         return None
-    h = x.origin[1]
-    if eptr.device != h.device:
+    h, h_sum = x.origin[1], x.origin[2] if len(x.origin) > 2 else None
+    if eptr.device != x.device:
         return None
-    H_sum = x.origin[2] if len(x.origin) > 2 else None  # already computed by the block's last depth (ops._LayerPooled)
-    if H_sum is None:
+    if h_sum is not None:  # the block deferred its last depth as well: sum_{e in b} h_L[e] straight from h_{L-1} (ops._LastDepthPooled)
+        H_sum = h_sum()
+    else:
+        if isinstance(h, PendingFeats):
+            h = h.materialize()
         H_sum = ops.seg_reduce(h, ops.mol_edge_csr(G), "sum", tag="K3e")
     if kind == "norm":
         return H_sum * (1.0 / norm)

@@ -21,6 +21,20 @@ from ...types import Reduction
 from ..residual import Residual
 
 
+class _Once:
+    """A value computed on first use (the collapsed last depth: only a sum read-out asks for it)."""
+
+    __slots__ = ("_fn", "_value")
+
+    def __init__(self, fn):
+        self._fn, self._value = fn, None
+
+    def __call__(self):
+        if self._fn is not None:
+            self._value, self._fn = self._fn(), None
+        return self._value
+
+
 class ChempropLayer(nn.Module):
     """One message-passing depth. Parameters live in ``update = Sequential(Linear(d, d), Dropout(p))`` so that a reference
     checkpoint loads with ``strict=True``; the modules in ``update`` are containers only — K1 + K2 compute the layer."""
@@ -33,15 +47,19 @@ class ChempropLayer(nn.Module):
         self.update = nn.Sequential(w_h, nn.Dropout(p=dropout))
 
     def forward(self, edge_feats: Tensor, node_feats: Tensor, edge_index: Tensor, rev_index: Tensor, *,
-                _residual: bool = False, _csr: ops.GraphCSR | None = None, _pool: ops.SegmentCSR | None = None) -> Tensor:
+                _residual: bool = False, _csr: ops.GraphCSR | None = None) -> Tensor:
         # only len(node_feats) matters, as in the reference (chemprop.py:39); a block passes its cached CSR bundle and asks for the
-        # residual to be added inside K2; for its last depth in front of a sum read-out it also passes the molecules' edge ranges
-        # (``_pool``) and gets (h_L, sum of h_L over each molecule's edges) back
+        # residual to be added inside K2
         if _csr is None:
             _csr = ops.graph_csr_from_tensors(edge_index, rev_index, len(node_feats))
         w_h, drop = self.update
         return ops.layer(edge_feats, w_h.weight, w_h.bias, _csr, act=ops.act_code(self.act), reduce=self.reduce, residual=_residual,
-                         dropout=drop.p, training=self.training and drop.training, pool=_pool)
+                         dropout=drop.p, training=self.training and drop.training)
+
+    def _pooled(self, edge_feats: Tensor, csr: ops.GraphCSR, pool: ops.SegmentCSR, residual: bool) -> Tensor:
+        """``sum_{e in b} h'[e]`` of this depth without computing h' (the last depth of a block under a sum read-out)."""
+        w_h, _ = self.update
+        return ops.last_depth_pooled(edge_feats, w_h.weight, w_h.bias, csr, pool, act=ops.act_code(self.act), reduce=self.reduce, residual=residual)
 
     def extra_repr(self):
         return f"(reduce): {self.reduce}"
@@ -80,23 +98,34 @@ class ChempropBlock(nn.Module):
         # A sum-reduced block on a device-collated batch (every molecule = a contiguous range of edges between its own atoms) defers
         # the final edge -> atom reduction: a Sum / Mean / Norm read-out right behind it needs only sum_{e in b} h_L[e] (§5.9).
         defer = self.reduce == "sum" and ops._fuse_readout and isinstance(G, Graph) and getattr(G, "_nt_mol_edge_ptr", None) is not None
-        pool = None
-        if defer and len(self.layers) > 0 and ops._pooled_backward and not ops._via_ops(h):
-            pool = ops.mol_edge_csr(G)  # the last depth computes that sum itself and takes the pooled backward (§5.10)
-        H_sum = None
-        for i, entry in enumerate(self.layers):
+        n_dense = len(self.layers)
+        last = None
+        if defer and n_dense > 0:
+            entry = self.layers[-1]
+            core = entry.module if isinstance(entry, Residual) else entry
+            drop = core.update[1] if isinstance(core, ChempropLayer) else None
+            if drop is not None and ops.last_depth_pooled_supported(h, drop.p, core.training and drop.training, core.reduce):
+                # ... and it does not need h_L itself: the last depth is deferred as well. The read-out gets sum_{e in b} h_L[e] from
+                # h_{L-1} on the molecules (§5.10); h_L = edge_feats (and node_feats) are computed only if something reads them.
+                last, n_dense = (core, isinstance(entry, Residual)), n_dense - 1
+        for entry in self.layers[:n_dense]:
             fused_residual = isinstance(entry, Residual)
             layer = entry.module if fused_residual else entry
-            if pool is not None and i == len(self.layers) - 1 and isinstance(layer, ChempropLayer) and layer.reduce in ("sum", "mean"):
-                h, H_sum = layer(h, xv, G.edge_index, G.rev_index, _residual=fused_residual, _csr=csr, _pool=pool)
-            else:
-                h = layer(h, xv, G.edge_index, G.rev_index, _residual=fused_residual, _csr=csr)  # xv: only its length is used
+            h = layer(h, xv, G.edge_index, G.rev_index, _residual=fused_residual, _csr=csr)  # xv: only its length is used
         if defer:
             # K1 without activation (chemprop.py:86), deferred: a Sum / Mean / Norm read-out right behind the block sums h_L over each
             # molecule's edges directly (one pass instead of K1 + K3); any other reader of node_feats computes them on first access
+            if last is not None:
+                core, fused_residual, h_prev, ei, ri = last[0], last[1], h, G.edge_index, G.rev_index
+                edges = PendingFeats(lambda: core(h_prev, xv, ei, ri, _residual=fused_residual, _csr=csr), tuple(h.shape), h.dtype, h.device,
+                                     ("last_depth", h_prev))
+                pool = ops.mol_edge_csr(G)
+                h_sum = _Once(lambda: core._pooled(h_prev, csr, pool, fused_residual))
+                atoms = PendingFeats(lambda: ops.edge_to_atom(edges.materialize(), csr, "sum"), (csr.V, h.shape[1]), h.dtype, h.device,
+                                     ("edge_to_atom_sum", edges, h_sum))
+                return G.update(node_feats=atoms, edge_feats=edges)
             final_h = h
-            atoms = PendingFeats(lambda: ops.edge_to_atom(final_h, csr, "sum"), (csr.V, h.shape[1]), h.dtype, h.device,
-                                 ("edge_to_atom_sum", final_h, H_sum))
+            atoms = PendingFeats(lambda: ops.edge_to_atom(final_h, csr, "sum"), (csr.V, h.shape[1]), h.dtype, h.device, ("edge_to_atom_sum", final_h, None))
         else:
             atoms = ops.edge_to_atom(h, csr, self.reduce)  # K1 without activation (chemprop.py:86)
         return G.update(node_feats=atoms, edge_feats=h)

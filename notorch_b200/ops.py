@@ -681,7 +681,7 @@ _fuse_embedding = os.environ.get("NOTORCH_B200_FUSE_EMBED", "1") != "0"
 # a Sum / Mean / Norm read-out of a sum-reduced block is a sum over each molecule's EDGES: run it over h_L directly and leave the
 # block's node_feats a placeholder that is computed only if something reads it (agg.py)
 _fuse_readout = os.environ.get("NOTORCH_B200_FUSE_READOUT", "1") != "0"
-_pooled_backward = os.environ.get("NOTORCH_B200_POOLED_BWD", "1") != "0"  # last depth's backward over molecules, not edges (§5.10)
+_pooled_backward = os.environ.get("NOTORCH_B200_POOLED_LAST", "1") != "0"  # last depth collapsed onto the molecules under a sum read-out (§5.10)
 
 
 def embed_edge_init_supported(table_v: Tensor, table_e: Tensor, node_types: Tensor, edge_types: Tensor) -> bool:
@@ -707,6 +707,30 @@ def embed_edge_init(table_v: Tensor, table_e: Tensor, node_types: Tensor, edge_t
 _dropout_calls = 0
 
 
+def _weight_images_begin(W: Tensor, want_transposed: bool, E: int) -> tuple[Tensor | None, Tensor | None, "torch.cuda.Event | None"]:
+    """The forward weight image and (``want_transposed``) the image of W^T that the backward reads, filled on a side stream so that
+    the two small launches run under whatever the caller launches next; the caller waits on the returned event before it reads
+    them (``None``: they were filled on the calling stream). Buffers come from the caller's stream - it is the one that reads and
+    frees them."""
+    img = _weight_image_alloc(W)
+    img_t = _weight_image_alloc(W) if want_transposed else None
+    if not (_side_wprep and _timer is None and E > 0):
+        _weight_image_fill(W, False, img)
+        _weight_image_fill(W, True, img_t)
+        return img, img_t, None
+    main = torch.cuda.current_stream()
+    fork = torch.cuda.Event()
+    fork.record(main)
+    side = _side_stream(W.device, 3)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        _weight_image_fill(W, False, img)
+        _weight_image_fill(W, True, img_t)
+        join = torch.cuda.Event()
+        join.record(side)
+    return img, img_t, join
+
+
 def _layer_forward_raw(h: Tensor, W: Tensor, b: Tensor | None, csr: GraphCSR, act: int, act_param: float, mean: bool, residual: bool,
                        p: float, seed: int, offset: int, mode: int, save_m: bool,
                        extreme: int = 0, img_t_out: list | None = None) -> tuple[Tensor, Tensor | None, Tensor, Tensor | None]:
@@ -718,31 +742,14 @@ def _layer_forward_raw(h: Tensor, W: Tensor, b: Tensor | None, csr: GraphCSR, ac
     L = _lib.lib()
     with torch.cuda.device(h.device):
         arg = None
-        img = img_t = None
-        join = None
         use_img = mode != GEMM_FP32
-        if use_img and _side_wprep and _timer is None and E > 0:
-            # buffers come from the caller's stream (it is the one that reads and frees them); only the two fills run on the side
-            img = _weight_image_alloc(W)
-            img_t = _weight_image_alloc(W) if img_t_out is not None else None
-            main = torch.cuda.current_stream()
-            fork = torch.cuda.Event()
-            fork.record(main)
-            side = _side_stream(h.device, 3)
-            side.wait_event(fork)
-            with torch.cuda.stream(side):
-                _weight_image_fill(W, False, img)
-                _weight_image_fill(W, True, img_t)
-                join = torch.cuda.Event()
-                join.record(side)
+        img, img_t, join = _weight_images_begin(W, img_t_out is not None, E) if use_img else (None, None, None)
         if extreme:
             n, arg = _seg_extreme_raw(h, csr.by_dst, act, act_param, extreme == 2)
         else:
             n = _seg_reduce_raw(h, csr.by_dst, act, act_param, mean, tag="K1")
         if join is not None:
             torch.cuda.current_stream().wait_event(join)
-        elif use_img:
-            img = _weight_image(W, False)
         if img_t_out is not None and img_t is not None:
             img_t_out.append(img_t)
         out = torch.empty_like(h)
@@ -830,16 +837,16 @@ class _Layer(torch.autograd.Function):
         return gh, gW, gb, None, None, None, None, None, None, None, None, None, None
 
 
-class _LayerPooled(torch.autograd.Function):
-    """The LAST message-passing depth together with the sum of h_L over each molecule's edges (chemprop.py:37-41,
-    residual.py:28 + the read-out identity of §5.9). Outputs ``(h_L, H_sum)``. When only ``H_sum`` is used downstream (a Sum / Mean /
-    Norm read-out: agg.py:27,36), the gradient of h_L is the broadcast ``g[e] = G[mol(e)]`` and the depth's backward contracts over
-    the B molecules instead of the E edges (``pooled_backward.cu``): no [E, d] gradient tensor is ever written. Anything else (h_L
-    used elsewhere, dropout, strict-fp32 mode, recompute-messages mode) takes the dense backward of ``_Layer`` - same results."""
+class _LastDepthPooled(torch.autograd.Function):
+    """The LAST message-passing depth as seen through a sum read-out over each molecule's edges (chemprop.py:37-41,
+    residual.py:28 + agg.py:27,36 + the identity of §5.9): ``H_sum[b] = sum_{e in b} h_L[e]`` from ``h = h_{L-1}`` WITHOUT computing
+    h_L. Forward: one pass over h gives ``M = sum_{e in b} m[e]`` and ``S = sum_{e in b} h[e] + |b| bias`` ([B, d]), the Linear runs on
+    B rows. Backward: the gradient of h_L is the broadcast ``g[e] = G[mol(e)]``, so every contraction over the E edges collapses to
+    one over the B molecules (``pooled_backward.cu``). No [E, d] tensor besides h itself is read or written, none is saved."""
 
     @staticmethod
     def forward(ctx, h: Tensor, W: Tensor, b: Tensor | None, csr: GraphCSR, pool: SegmentCSR, act: int, act_param: float, mean: bool,
-                residual: bool, p: float, seed: int, offset: int, mode: int):
+                residual: bool, mode: int):
         h = _require_float(h, "edge_feats")
         W = _require_float(W, "weight")
         E, d = h.shape
@@ -849,47 +856,40 @@ class _LayerPooled(torch.autograd.Function):
             raise RuntimeError(f"notorch_b200: weight {tuple(W.shape)} does not match hidden size {d}")
         if b is not None:
             b = _require(b, "bias", torch.float32, 1)
-        save_m = _save_messages and mode != GEMM_FP32 and d % 4 == 0 and (ctx.needs_input_grad[1] or (b is not None and ctx.needs_input_grad[2]))
-        img_t_out: list | None = [] if (ctx.needs_input_grad[0] and mode != GEMM_FP32) else None
-        out, m, n, _ = _layer_forward_raw(h, W, b, csr, act, act_param, mean, residual, p, seed, offset, mode, save_m, 0, img_t_out)
+        if mode == GEMM_FP32 or d % 4 != 0:
+            raise RuntimeError("notorch_b200: the pooled last depth needs a tensor-core GEMM mode and d % 4 == 0")
+        B = pool.num_segments
+        L = _lib.lib()
         with torch.cuda.device(h.device):
-            H = _seg_reduce_raw(out, pool, tag="K3e")
-        ctx.save_for_backward(h, m if save_m else n, W)
-        ctx.img_t = img_t_out[0] if img_t_out else None
-        ctx.csr, ctx.pool, ctx.cfg, ctx.has_bias, ctx.has_m = csr, pool, (act, act_param, mean, residual, p, seed, offset, mode), b is not None, save_m
-        ctx.set_materialize_grads(False)
-        return out, H
+            img, img_t, join = _weight_images_begin(W, ctx.needs_input_grad[0], E)
+            M = torch.empty((B, d), dtype=h.dtype, device=h.device)
+            S = torch.empty_like(M)
+            ws = _workspace(h.device, L.nt_pooled_message_sum_workspace_bytes(E))
+            _run("Kpm:nt_pooled_message_sum", L.nt_pooled_message_sum, _p(h), _p(csr.rev), _p(csr.dst), _p(csr.by_src.rowptr), _p(csr.by_dst.rowptr),
+                 _p(pool.rowptr), _p(b), E, B, d, act, act_param, int(residual), int(mean), _p(M), _p(S), _p(ws), ws.numel(), NT_F32, _stream())
+            if join is not None:
+                torch.cuda.current_stream().wait_event(join)
+            H = torch.empty_like(M)
+            _run("K2p:nt_dense_forward", L.nt_dense_forward, _p(M), _p(img), None, _p(S), B, d, 0.0, 0, 0, _p(H), NT_F32, mode, _stream())
+        ctx.save_for_backward(h, M, W)
+        ctx.img_t = img_t
+        ctx.csr, ctx.pool, ctx.cfg, ctx.has_bias = csr, pool, (act, act_param, mean, residual, mode), b is not None
+        return H
 
     @staticmethod
-    def backward(ctx, g_out: Tensor | None, g_H: Tensor | None):
-        nothing = (None,) * 13
-        if g_out is None and g_H is None:
-            return nothing
-        h, n_or_m, W = ctx.saved_tensors
-        act, act_param, mean, residual, p, seed, offset, mode = ctx.cfg
+    def backward(ctx, G: Tensor):
+        h, M, W = ctx.saved_tensors
+        act, act_param, mean, residual, mode = ctx.cfg
         csr, pool = ctx.csr, ctx.pool
         need_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         need_h = ctx.needs_input_grad[0]
         E, d = h.shape
-        pooled = _pooled_backward and g_out is None and p == 0.0 and mode != GEMM_FP32 and d % 4 == 0 and (ctx.has_m or not need_w)
-        if not pooled:
-            # dense gradient of h_L: what reached the edge states directly plus the read-out's broadcast
-            if g_H is None:
-                g = g_out.contiguous()
-            else:
-                with torch.cuda.device(h.device):
-                    g = _gather_add_raw(None if g_out is None else g_out.contiguous(), g_H.contiguous(), pool.keys32, None, tag="K3ebwd")
-            m, n = (n_or_m, None) if ctx.has_m else (None, n_or_m)
-            gh, gW, gb = _layer_backward_raw(g, h, m, n, W, ctx.has_bias, csr, act, act_param, mean, residual, p, seed, offset, mode, need_w, need_h,
-                                             None, ctx.img_t)
-            return (gh, gW, gb) + (None,) * 10
-        G = g_H.contiguous()
+        G = G.contiguous()
         B = G.shape[0]
         L = _lib.lib()
         gh = gW = gb = None
         with torch.cuda.device(h.device):
             if need_w:
-                M = _seg_reduce_raw(n_or_m, pool, tag="K3m")  # [B, d]: the messages summed over each molecule's edges
                 gW = torch.empty_like(W)
                 ws = _workspace(h.device, L.nt_layer_backward_wgrad_workspace_bytes(B, d), slot=1)
                 _run("K4bp:nt_layer_backward_wgrad", L.nt_layer_backward_wgrad, _p(G), _p(M), None, None, None, None, B, 1, d, act, act_param, 0.0, 0, 0,
@@ -906,7 +906,22 @@ class _LayerPooled(torch.autograd.Function):
                 _run("K6p:nt_layer_backward_epilogue_pooled", L.nt_layer_backward_epilogue_pooled, _p(G), _p(GW), _p(h), _p(pool.keys32), _p(csr.dst),
                      _p(csr.by_src.rowptr), _p(csr.by_rev.rowptr), _p(csr.by_rev.perm), _p(csr.by_dst.rowptr), E, B, d, act, act_param, int(residual),
                      int(mean), _p(gh), _p(ws6), ws6.numel(), NT_F32, _stream())
-        return (gh, gW, gb) + (None,) * 10
+        return (gh, gW, gb) + (None,) * 7
+
+
+def last_depth_pooled_supported(h: Tensor, dropout: float, training: bool, reduce: str) -> bool:
+    """Whether the collapsed form applies: sum / mean reduction inside the depth, no active dropout (a per-edge mask does not commute
+    with the sum over a molecule's edges), a tensor-core GEMM mode, 16-byte rows, real CUDA tensors."""
+    return (_pooled_backward and reduce in ("sum", "mean") and not (training and dropout > 0.0) and _gemm_mode != GEMM_FP32 and h.shape[1] % 4 == 0
+            and h.is_cuda and h.dtype == torch.float32 and not _via_ops(h))
+
+
+def last_depth_pooled(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, pool: SegmentCSR, *,
+                      act: tuple[int, float] = (_lib.ACT_RELU, 0.0), reduce: str = "sum", residual: bool = True) -> Tensor:
+    """``sum_{e in b} h'[e]`` for ``h' = [h +] Linear(n[src] - act(h)[rev])`` without computing h' (``_LastDepthPooled``)."""
+    if reduce not in ("sum", "mean"):
+        raise ValueError("notorch_b200: the pooled last depth needs a sum / mean reduction")
+    return _LastDepthPooled.apply(h, weight, bias, csr, pool, act[0], act[1], reduce == "mean", residual, _gemm_mode)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -956,11 +971,8 @@ def readout(node_feats: Tensor, mol_csr: SegmentCSR, kind: str = "sum", norm: fl
 
 
 def layer(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, *, act: tuple[int, float] = (_lib.ACT_RELU, 0.0),
-          reduce: str = "sum", residual: bool = True, dropout: float = 0.0, training: bool = False,
-          pool: SegmentCSR | None = None) -> Tensor | tuple[Tensor, Tensor]:
-    """One fused message-passing depth (K1+K2; hand-written backward K4-K6). ``pool`` (the CSR of the molecules' contiguous edge
-    ranges): also return the sum of the new edge states over every molecule, ``(h', H_sum)`` - the form the last depth of a block
-    takes in front of a sum read-out (``_LayerPooled``)."""
+          reduce: str = "sum", residual: bool = True, dropout: float = 0.0, training: bool = False) -> Tensor:
+    """One fused message-passing depth (K1+K2; hand-written backward K4-K6)."""
     global _dropout_calls
     if reduce not in _REDUCTIONS:
         raise ValueError(f"notorch_b200: unknown reduce '{reduce}' (one of {_REDUCTIONS})")
@@ -975,10 +987,6 @@ def layer(h: Tensor, weight: Tensor, bias: Tensor | None, csr: GraphCSR, *, act:
         _dropout_calls += 1
         offset = _dropout_calls
     extreme = {"max": 1, "min": 2}.get(reduce, 0)
-    if pool is not None:
-        if extreme != 0 or _via_ops(h, weight):
-            raise RuntimeError("notorch_b200: the pooled form of a depth needs a sum / mean reduction and real CUDA tensors")
-        return _LayerPooled.apply(h, weight, bias, csr, pool, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)
     if extreme == 0 and _via_ops(h, weight):
         return _torch_ops().layer_from_csr(h, weight, bias, csr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode)
     return _Layer.apply(h, weight, bias, csr, act[0], act[1], reduce == "mean", residual, p, seed, offset, _gemm_mode, extreme)

@@ -46,8 +46,9 @@ def _block_parity(p, depth, agg_kind, mode, *, rel=REL_F32, check_fp32_oracle=Tr
     gE = torch.randn(E, d, generator=gen) if with_gE else None
     xv, xe = p["x_v"].cuda().requires_grad_(True), p["x_e"].cuda().requires_grad_(True)
     if packed:
-        # device collation (BatchedGraph.from_packed): the block defers the edge -> atom sum, its last depth also returns the sum of h_L
-        # over each molecule's edges, and - when nothing else reads h_L - takes the pooled backward
+        # device collation (BatchedGraph.from_packed): the block defers the edge -> atom sum AND its last depth; the read-out takes
+        # sum_{e in b} h_L[e] from h_{L-1} on the molecules, forward and backward; h_L exists only because this test
+        # reads it (and, with_gE, differentiates through it: the dense depth then runs beside the collapsed one)
         G = BatchedGraph.from_packed(p["mols"], xv, xe, device="cuda")
         assert G.node_feats is xv and torch.equal(G.edge_index.cpu(), ei) and torch.equal(G.rev_index.cpu(), rev)
     else:
@@ -109,8 +110,9 @@ def test_config2_full_size_elementwise():
 
 
 def test_config2_full_size_elementwise_device_collated_pooled_backward():
-    """The same size through the path the bench takes: device collation, read-out summed over the molecules' edges, and the last
-    depth's backward contracted over the B molecules (gW = M^T G, g_m = (G W)[mol e]; pooled_backward.cu) - against the fp64 oracle."""
+    """The same size through the path the bench takes: device collation, and the last depth seen through the read-out - forward
+    (M = sum_{e in b} m[e], Linear on B rows) and backward (gW = M^T G, g_m = (G W)[mol e]; pooled_backward.cu) contracted over the
+    B molecules - against the fp64 oracle."""
     p = oracle_inputs(4096, 300, 3, config=2, seed=2)
     _block_parity(p, 3, "sum", "tf32x3", with_gE=False, packed=True, check_fp32_oracle=False)
 
@@ -118,18 +120,18 @@ def test_config2_full_size_elementwise_device_collated_pooled_backward():
 @pytest.mark.parametrize("agg_kind,with_gE,d,depth", [("sum", False, 64, 2), ("mean", False, 64, 1), ("sum", True, 64, 2), ("mean", False, 300, 3)])
 def test_pooled_last_depth_small(agg_kind, with_gE, d, depth):
     """Device-collated batches at small sizes: Sum and Mean read-outs, one depth (the pooled depth is also the first), and a loss that
-    also reads h_L (the gradient of h_L is then not a broadcast: the depth falls back to the dense backward)."""
+    also reads h_L (the dense depth then runs beside the collapsed one and both gradients add up)."""
     p = oracle_inputs(48, d, depth, config=1, seed=61 + d)
     _block_parity(p, depth, agg_kind, "tf32x3", with_gE=with_gE, packed=True)
 
 
 @pytest.mark.parametrize("reduce,residual,bias,act", [("sum", True, True, "relu"), ("mean", True, True, "relu"), ("sum", False, False, "tanh"),
                                                       ("mean", False, True, "elu")])
-def test_pooled_depth_equals_dense_depth(reduce, residual, bias, act):
-    """ops.layer(pool=...) - (h', H_sum) with the pooled backward - against the dense formulation of the same thing (ops.layer, then the
-    segmented sum, whose backward materialises the [E, d] broadcast): forward bits equal, every gradient within the fp32 bound
-    (the contraction runs over molecules instead of edges: another summation order). Mean reduction, no residual, no bias,
-    smooth activations."""
+def test_pooled_last_depth_equals_dense_depth(reduce, residual, bias, act):
+    """ops.last_depth_pooled - sum_{e in b} h'[e] straight from h, forward and backward on the molecules - against the dense
+    formulation of the same thing (ops.layer, then the segmented sum over each molecule's edges): the value and every gradient
+    within the fp32 bound (exact algebra, another summation order). Mean reduction, no residual, no bias, smooth activations;
+    molecules without edges; bit-identical across runs."""
     import torch.nn as nn
 
     from notorch_b200 import BatchedGraph, ops
@@ -145,18 +147,17 @@ def test_pooled_depth_equals_dense_depth(reduce, residual, bias, act):
     gH = torch.randn(B, d, generator=gen).cuda()
     code = ops.act_code({"relu": nn.ReLU(), "tanh": nn.Tanh(), "elu": nn.ELU()}[act])
     res = []
-    for pooled in (True, False):
+    for pooled in (True, True, False):
         h, W = h0.clone().requires_grad_(True), W0.clone().requires_grad_(True)
         b = b0.clone().requires_grad_(True) if bias else None
         if pooled:
-            out, H = ops.layer(h, W, b, csr, act=code, reduce=reduce, residual=residual, pool=pool)
+            H = ops.last_depth_pooled(h, W, b, csr, pool, act=code, reduce=reduce, residual=residual)
         else:
-            out = ops.layer(h, W, b, csr, act=code, reduce=reduce, residual=residual)
-            H = ops.seg_reduce(out, pool, "sum")
+            H = ops.seg_reduce(ops.layer(h, W, b, csr, act=code, reduce=reduce, residual=residual), pool, "sum")
         (H * gH).sum().backward()
-        res.append((out.detach(), H.detach(), h.grad, W.grad, b.grad if bias else None))
-    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
-    for a, c, what in zip(res[0][2:], res[1][2:], ("grad h", "grad W", "grad b")):
+        res.append((H.detach(), h.grad, W.grad, b.grad if bias else None))
+    assert all(torch.equal(x, y) for x, y in zip(res[0], res[1]) if x is not None)
+    for a, c, what in zip(res[0], res[2], ("H_sum", "grad h", "grad W", "grad b")):
         if a is not None:
             assert_close(a, c, f"{what}: pooled vs dense ({reduce}, residual={residual}, {act})", 3e-6)
 
