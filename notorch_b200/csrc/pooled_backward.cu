@@ -20,6 +20,8 @@
 // on B rows (nt_dense_forward) - K1, K2 and the read-out's pass over h_L are not launched for the last depth, h_L and m_L are not
 // written, and the backward reuses M. h_L itself stays available: ChempropBlock computes it (the dense depth) only if it is read.
 // Exact algebra, another summation order (tested against the dense path and the fp64 oracle).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nt {
@@ -75,12 +77,10 @@ __global__ void __launch_bounds__(PB_THREADS) pooled_record_kernel(const int32_t
 }
 
 // PB_ITEMS (edge, 16-byte chunk) items per thread, PB_THREADS apart. DRAM traffic: h[e] in, g_h[e] out; G and GW ([B, d], a few MB)
-// stay in L2 / L1. With ONE item per thread the kernel had 16 bytes of DRAM reads in flight per thread - 20 KB per SM against
-// ~1.5 us of latency = 2 TB/s (measured: 168 us for 0.49 GB); all level-1 loads of the four items are issued before anything is used.
-constexpr int PB_ITEMS = 4;
-
-template <int AK>
-__global__ void __launch_bounds__(PB_THREADS, 2) layer_bwd_epilogue_pooled(const float* __restrict__ G, const float* __restrict__ GW,
+// stay in L2 / L1; all level-1 loads of a thread's items are issued before anything is used (NOTORCH_B200_K6P_ITEMS = 1 | 2 | 4).
+// Measured (configs[1], 0.49 GB): 1 item per thread 168 us, 4 items per thread (102 registers, two CTAs per SM) 246 us - kept at one.
+template <int AK, int PB_ITEMS>
+__global__ void __launch_bounds__(PB_THREADS, PB_ITEMS == 1 ? 5 : PB_ITEMS == 2 ? 4 : 2) layer_bwd_epilogue_pooled(const float* __restrict__ G, const float* __restrict__ GW,
                                                                            const float* __restrict__ h, const int4* __restrict__ rec,
                                                                            const int32_t* __restrict__ mol, const int32_t* __restrict__ rev_rowptr,
                                                                            const int32_t* __restrict__ rev_perm, int d, int chunks, int64_t total,
@@ -130,6 +130,59 @@ __global__ void __launch_bounds__(PB_THREADS, 2) layer_bwd_epilogue_pooled(const
                            pb_act_bwd(AK, hv[k].w, act, act_param) * (scale * gw[k].w - sub[k].w));
     if (residual) r = make_float4(gv[k].x + r.x, gv[k].y + r.y, gv[k].z + r.z, gv[k].w + r.w);
     stg4(g_h + (int64_t)e[k] * d + c[k], r);
+  }
+}
+
+// Tiled form (the default; same structure as layer_bwd_epilogue_tiled in rowwise_kernels.cu): a CTA owns 32 consecutive edges, 8 threads
+// per edge read that edge's record once, then the CTA sweeps the rows in passes of eight 16-byte chunks, two passes in flight. One
+// memory round trip per pass instead of (record -> rows) per 16-byte result, and the [B, d] rows of a tile's one or two molecules
+// are served by L1. Measured at configs[1]: per-item forms 161-171 us (1, 2 items per thread; runs of 4 consecutive edges with the
+// rows re-used from registers: 171 - it is not the L2 -> SM bytes), 4 items per thread at 102 registers 243 us.
+constexpr int PBT_EDGES = 32, PBT_LANES = 8;
+
+template <int AK>
+__global__ void __launch_bounds__(PB_THREADS, 4) layer_bwd_epilogue_pooled_tiled(const float* __restrict__ G, const float* __restrict__ GW,
+                                                                                 const float* __restrict__ h, const int4* __restrict__ rec,
+                                                                                 const int32_t* __restrict__ mol, const int32_t* __restrict__ rev_rowptr,
+                                                                                 const int32_t* __restrict__ rev_perm, int d, int chunks, int64_t E, int act,
+                                                                                 float act_param, int residual, float* __restrict__ g_h) {
+  const int64_t e = (int64_t)blockIdx.x * PBT_EDGES + (threadIdx.x / PBT_LANES);
+  const int cl = threadIdx.x % PBT_LANES;
+  if (e >= E) return;
+  const int4 r4 = __ldg(rec + e);
+  const int lo = r4.w > 1 ? __ldg(rev_rowptr + e) : 0;
+  const float scale = __int_as_float(r4.y);
+  const int64_t own = e * d, rowb = (int64_t)r4.x * d, rows = (int64_t)(r4.z >= 0 ? r4.z : 0) * d;
+  constexpr int PASSES = 2;
+  for (int c0 = cl; c0 < chunks; c0 += PBT_LANES * PASSES) {
+    float4 hv[PASSES], gw[PASSES], gv[PASSES], sub[PASSES];
+    bool on[PASSES];
+#pragma unroll
+    for (int q = 0; q < PASSES; ++q) {
+      const int c = (c0 + q * PBT_LANES) * 4;
+      on[q] = c0 + q * PBT_LANES < chunks;
+      gv[q] = sub[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (on[q]) {
+        hv[q] = ldg4_stream(h + own + c);
+        gw[q] = ldg4(GW + rowb + c);
+        if (residual) gv[q] = ldg4(G + rowb + c);
+        if (r4.z >= 0) sub[q] = ldg4(GW + rows + c);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < PASSES; ++q) {
+      if (!on[q]) continue;
+      const int c = (c0 + q * PBT_LANES) * 4;
+      float4 sb = sub[q];
+      for (int j = lo + 1; j < lo + r4.w; ++j) {  // several edges' rev point here (the reference's atom-offset rev_index quirk)
+        const float4 r = ldg4(GW + (int64_t)__ldg(mol + __ldg(rev_perm + j)) * d + c);
+        sb = make_float4(sb.x + r.x, sb.y + r.y, sb.z + r.z, sb.w + r.w);
+      }
+      float4 r = make_float4(pb_act_bwd(AK, hv[q].x, act, act_param) * (scale * gw[q].x - sb.x), pb_act_bwd(AK, hv[q].y, act, act_param) * (scale * gw[q].y - sb.y),
+                             pb_act_bwd(AK, hv[q].z, act, act_param) * (scale * gw[q].z - sb.z), pb_act_bwd(AK, hv[q].w, act, act_param) * (scale * gw[q].w - sb.w));
+      if (residual) r = make_float4(gv[q].x + r.x, gv[q].y + r.y, gv[q].z + r.z, gv[q].w + r.w);
+      stg4(g_h + own + c, r);
+    }
   }
 }
 
@@ -245,18 +298,39 @@ extern "C" int nt_layer_backward_epilogue_pooled(const void* gH, const void* gHW
   const int chunks = (int)(d / 4);
   const int64_t total = E * chunks;
   const uint64_t magic = chunk_div_magic(total, chunks);
-  const unsigned grid = (unsigned)cdiv(total, PB_THREADS * PB_ITEMS);
+  const char* ie = getenv("NOTORCH_B200_K6P_ITEMS");  // A/B timing, read per call: 0 (default) = tiled form; 1 | 2 | 4 = per-item forms
+  const int items = ie ? atoi(ie) : 0;
   cudaStream_t st = as_stream(stream);
   const float *Gf = static_cast<const float*>(gH), *GWf = static_cast<const float*>(gHW), *hf = static_cast<const float*>(h);
   float* out = static_cast<float*>(g_h);
   int4* rec = static_cast<int4*>(workspace);
   pooled_record_kernel<<<(unsigned)cdiv(E, PB_THREADS), PB_THREADS, 0, st>>>(mol_of_edge, dst, src_rowptr, rev_rowptr, rev_perm, dst_rowptr, E, mean, rec);
-#define NT_PB_LAUNCH(AK)                                                                                                                           \
-  layer_bwd_epilogue_pooled<AK><<<grid, PB_THREADS, 0, st>>>(Gf, GWf, hf, rec, mol_of_edge, rev_rowptr, rev_perm, (int)d, chunks, total, magic, act, \
-                                                             act_param, residual, out)
+  if (items != 1 && items != 2 && items != 4) {
+    const unsigned tgrid = (unsigned)cdiv(E, PBT_EDGES);
+#define NT_PBT_LAUNCH(AK)                                                                                                                          \
+  layer_bwd_epilogue_pooled_tiled<AK><<<tgrid, PB_THREADS, 0, st>>>(Gf, GWf, hf, rec, mol_of_edge, rev_rowptr, rev_perm, (int)d, chunks, E, act, act_param, \
+                                                                    residual, out)
+    if (act == NT_ACT_IDENTITY) NT_PBT_LAUNCH(0);
+    else if (act == NT_ACT_RELU) NT_PBT_LAUNCH(1);
+    else NT_PBT_LAUNCH(2);
+#undef NT_PBT_LAUNCH
+    NT_LAUNCH_CHECK("nt_layer_backward_epilogue_pooled", 2);
+    return NT_OK;
+  }
+  const unsigned grid = (unsigned)cdiv(total, PB_THREADS * items);
+#define NT_PB_LAUNCH2(AK, IT)                                                                                                                         \
+  layer_bwd_epilogue_pooled<AK, IT><<<grid, PB_THREADS, 0, st>>>(Gf, GWf, hf, rec, mol_of_edge, rev_rowptr, rev_perm, (int)d, chunks, total, magic, act, \
+                                                                 act_param, residual, out)
+#define NT_PB_LAUNCH(AK)                \
+  do {                                  \
+    if (items == 2) NT_PB_LAUNCH2(AK, 2); \
+    else if (items == 4) NT_PB_LAUNCH2(AK, 4); \
+    else NT_PB_LAUNCH2(AK, 1);          \
+  } while (0)
   if (act == NT_ACT_IDENTITY) NT_PB_LAUNCH(0);
   else if (act == NT_ACT_RELU) NT_PB_LAUNCH(1);
   else NT_PB_LAUNCH(2);
+#undef NT_PB_LAUNCH2
 #undef NT_PB_LAUNCH
   NT_LAUNCH_CHECK("nt_layer_backward_epilogue_pooled", 2);
   return NT_OK;

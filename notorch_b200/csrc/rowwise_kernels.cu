@@ -185,6 +185,11 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) seg_reduce_ell_v4(const float*
   }
 }
 
+// A tiled form (a CTA owns 32 consecutive segments, the ELL record is read once into registers, the output row is swept in passes of
+// eight 16-byte chunks with eight row loads in flight per thread) was measured and NOT kept: 86.8 us against 86.9 us for the per-item
+// form above, bit-identical - the kernel is not bound by its index chain. Both deliver 4.15 TB/s (0.36 GB): what a PERMUTED walk over
+// 1200-byte rows gets from HBM3e (a sequential stream of the same bytes: 6.2-6.5 TB/s, e.g. nt_gather_add in its K1-backward form).
+
 // scalar fallback for d % 4 != 0 (or unaligned bases): one thread per (segment, element)
 __global__ void __launch_bounds__(ROW_THREADS) seg_reduce_s(const float* __restrict__ x, int d, const int32_t* __restrict__ rowptr,
                                                              const int32_t* __restrict__ perm, int64_t total, int act, float act_param, int mean,
@@ -366,6 +371,13 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) layer_bwd_epilogue_fused(const
   if (residual) r = add4(gv, r);
   stg4(g_h + own, r);
 }
+
+// A tiled form of this kernel (a CTA owns 16 / 32 consecutive edges, the index data of an edge is read once into registers, the row
+// is swept in passes of 16-byte chunk groups - what made the pooled epilogue of pooled_backward.cu and the tiled K1 below faster) was
+// measured and NOT kept: 244 us with one pass in flight (this form: 247), 326-329 us with two (80 registers, three CTAs per SM).
+// ncu of this form: 240 us, 1.41 GB of L2 -> L1 sectors + 0.25 GB of stores = 6.9 TB/s, i.e. the L2 -> SM ceiling of §5.0 (L1 hit
+// rate 9.6 %: the ~2.2 out-edge rows an edge gathers are its sibling in-edges' rows too, but siblings run on other SMs and a tile
+// did not bring them together in time).
 
 // the first form (kept for A/B timing: NOTORCH_B200_K6_VARIANT=0)
 template <int AK>

@@ -95,7 +95,7 @@ if not RUN_K6:
 else:
   t4a = timed(lambda: _lib.check(L.nt_layer_backward_dgrad(p(g), p(W), p(img_t), E, d, 0.0, 0, 0, p(g_m), _lib.NT_F32, _lib.GEMM_TF32X3, st()), "k4a"))
 print(f"K4a alone {t4a:7.1f} us")
-for v in (0, 1, 2, 3) if RUN_K6 else ():
+for v in (0, 3) if RUN_K6 else ():
     os.environ["NOTORCH_B200_K6_VARIANT"] = str(v)
     t = timed(lambda: k6(o))
     t2 = timed(lambda: k4a_then_k6(o))
@@ -142,3 +142,25 @@ if "pf" in sys.argv:
                                                              _lib.NT_F32, st()), "embbwd")
         print(f"embbwd tc d=300: {timed(f):7.1f} us", flush=True)
     os.environ.pop("NOTORCH_B200_WGRAD_PF")
+
+# ---------------------------------------------------------------- pooled epilogue variants (NOTORCH_B200_K6P_ITEMS: 0 = runs, 1 | 2 | 4 items)
+if "k6p" in sys.argv:
+    Bm = len(G)
+    pool = ops.mol_edge_csr(G)
+    GH, GHW = torch.randn(Bm, d, device="cuda"), torch.randn(Bm, d, device="cuda")
+    ws6 = torch.empty(L.nt_layer_backward_epilogue_pooled_workspace_bytes(E), dtype=torch.uint8, device="cuda")
+    outs6 = {}
+    def k6p(o, mean=0, act=1):
+        _lib.check(L.nt_layer_backward_epilogue_pooled(p(GH), p(GHW), p(h), p(pool.keys32), p(csr.dst), p(csr.by_src.rowptr), p(csr.by_rev.rowptr),
+                                                       p(csr.by_rev.perm), p(csr.by_dst.rowptr), E, Bm, d, act, 0.0, 1, mean, p(o), p(ws6), ws6.numel(),
+                                                       _lib.NT_F32, st()), "k6p")
+    for v in (1, 0, 2, 4):
+        os.environ["NOTORCH_B200_K6P_ITEMS"] = str(v)
+        outs6[v] = torch.full_like(h, float("nan")); k6p(outs6[v], 1, 3)
+    torch.cuda.synchronize()
+    print("K6p variants equal:", all(torch.equal(outs6[1], outs6[v]) for v in (0, 2, 4)))
+    o6 = torch.empty_like(h)
+    for v in (1, 0, 2, 4):
+        os.environ["NOTORCH_B200_K6P_ITEMS"] = str(v)
+        print(f"K6p variant {v}: {timed(lambda: k6p(o6)):7.1f} us", flush=True)
+    os.environ.pop("NOTORCH_B200_K6P_ITEMS")
