@@ -76,11 +76,11 @@ __global__ void __launch_bounds__(PB_THREADS) pooled_record_kernel(const int32_t
   rec[e] = make_int4(__ldg(mol + e), __float_as_int(scale), first, hi - lo);
 }
 
-// PB_ITEMS (edge, 16-byte chunk) items per thread, PB_THREADS apart. DRAM traffic: h[e] in, g_h[e] out; G and GW ([B, d], a few MB)
-// stay in L2 / L1; all level-1 loads of a thread's items are issued before anything is used (NOTORCH_B200_K6P_ITEMS = 1 | 2 | 4).
-// Measured (configs[1], 0.49 GB): 1 item per thread 168 us, 4 items per thread (102 registers, two CTAs per SM) 246 us - kept at one.
+// Per-item form (NOTORCH_B200_K6P_ITEMS=1; the tiled form below is the default): one (edge, 16-byte chunk) item per thread. DRAM
+// traffic: h[e] in, g_h[e] out; G and GW ([B, d], a few MB) stay in L2 / L1. Measured (configs[1], 0.49 GB): 168-171 us; two items
+// per thread 161 us, four (102 registers, two CTAs per SM) 243-246 us.
 template <int AK, int PB_ITEMS>
-__global__ void __launch_bounds__(PB_THREADS, PB_ITEMS == 1 ? 5 : PB_ITEMS == 2 ? 4 : 2) layer_bwd_epilogue_pooled(const float* __restrict__ G, const float* __restrict__ GW,
+__global__ void __launch_bounds__(PB_THREADS, 5) layer_bwd_epilogue_pooled(const float* __restrict__ G, const float* __restrict__ GW,
                                                                            const float* __restrict__ h, const int4* __restrict__ rec,
                                                                            const int32_t* __restrict__ mol, const int32_t* __restrict__ rev_rowptr,
                                                                            const int32_t* __restrict__ rev_perm, int d, int chunks, int64_t total,
@@ -298,14 +298,14 @@ extern "C" int nt_layer_backward_epilogue_pooled(const void* gH, const void* gHW
   const int chunks = (int)(d / 4);
   const int64_t total = E * chunks;
   const uint64_t magic = chunk_div_magic(total, chunks);
-  const char* ie = getenv("NOTORCH_B200_K6P_ITEMS");  // A/B timing, read per call: 0 (default) = tiled form; 1 | 2 | 4 = per-item forms
+  const char* ie = getenv("NOTORCH_B200_K6P_ITEMS");  // A/B timing, read per call: 0 (default) = tiled form; 1 = per-item form
   const int items = ie ? atoi(ie) : 0;
   cudaStream_t st = as_stream(stream);
   const float *Gf = static_cast<const float*>(gH), *GWf = static_cast<const float*>(gHW), *hf = static_cast<const float*>(h);
   float* out = static_cast<float*>(g_h);
   int4* rec = static_cast<int4*>(workspace);
   pooled_record_kernel<<<(unsigned)cdiv(E, PB_THREADS), PB_THREADS, 0, st>>>(mol_of_edge, dst, src_rowptr, rev_rowptr, rev_perm, dst_rowptr, E, mean, rec);
-  if (items != 1 && items != 2 && items != 4) {
+  if (items != 1) {
     const unsigned tgrid = (unsigned)cdiv(E, PBT_EDGES);
 #define NT_PBT_LAUNCH(AK)                                                                                                                          \
   layer_bwd_epilogue_pooled_tiled<AK><<<tgrid, PB_THREADS, 0, st>>>(Gf, GWf, hf, rec, mol_of_edge, rev_rowptr, rev_perm, (int)d, chunks, E, act, act_param, \
@@ -317,20 +317,13 @@ extern "C" int nt_layer_backward_epilogue_pooled(const void* gH, const void* gHW
     NT_LAUNCH_CHECK("nt_layer_backward_epilogue_pooled", 2);
     return NT_OK;
   }
-  const unsigned grid = (unsigned)cdiv(total, PB_THREADS * items);
-#define NT_PB_LAUNCH2(AK, IT)                                                                                                                         \
-  layer_bwd_epilogue_pooled<AK, IT><<<grid, PB_THREADS, 0, st>>>(Gf, GWf, hf, rec, mol_of_edge, rev_rowptr, rev_perm, (int)d, chunks, total, magic, act, \
-                                                                 act_param, residual, out)
-#define NT_PB_LAUNCH(AK)                \
-  do {                                  \
-    if (items == 2) NT_PB_LAUNCH2(AK, 2); \
-    else if (items == 4) NT_PB_LAUNCH2(AK, 4); \
-    else NT_PB_LAUNCH2(AK, 1);          \
-  } while (0)
+  const unsigned grid = (unsigned)cdiv(total, PB_THREADS);
+#define NT_PB_LAUNCH(AK)                                                                                                                            \
+  layer_bwd_epilogue_pooled<AK, 1><<<grid, PB_THREADS, 0, st>>>(Gf, GWf, hf, rec, mol_of_edge, rev_rowptr, rev_perm, (int)d, chunks, total, magic, act, \
+                                                                act_param, residual, out)
   if (act == NT_ACT_IDENTITY) NT_PB_LAUNCH(0);
   else if (act == NT_ACT_RELU) NT_PB_LAUNCH(1);
   else NT_PB_LAUNCH(2);
-#undef NT_PB_LAUNCH2
 #undef NT_PB_LAUNCH
   NT_LAUNCH_CHECK("nt_layer_backward_epilogue_pooled", 2);
   return NT_OK;

@@ -456,3 +456,28 @@ def test_embedding_table_gradient_many_row_blocks(kind, d, Tv, Te, monkeypatch):
     assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
     assert_close(runs[0][0].cpu(), ref_v.cpu(), f"grad node table ({kind})")
     assert_close(runs[0][1].cpu(), ref_e.cpu(), f"grad edge table ({kind})")
+
+
+def test_kernel_variant_switches_give_the_same_bits(monkeypatch):
+    """The A/B switches of the two backward epilogues select other thread mappings of the SAME arithmetic: K6 per-item forms
+    (NOTORCH_B200_K6_VARIANT 0..3) and the per-item pooled epilogue (NOTORCH_B200_K6P_ITEMS=1) against the defaults, bit for bit,
+    through a block's backward on a device-collated batch (dense depths + the collapsed last depth)."""
+    from notorch_b200 import BatchedGraph
+    from notorch_b200.nn import ChempropBlock, Mean
+
+    p = oracle_inputs(40, 64, 3, config=1, seed=91)
+    blk = ChempropBlock(hidden_dim=64, depth=3).cuda()
+    _load(blk, p)
+    gH = torch.randn(40, 64, generator=torch.Generator().manual_seed(4)).cuda()
+    runs = []
+    for env in ({}, {"NOTORCH_B200_K6_VARIANT": "0", "NOTORCH_B200_K6P_ITEMS": "1"}, {"NOTORCH_B200_K6_VARIANT": "1"}, {"NOTORCH_B200_K6_VARIANT": "2"}):
+        with monkeypatch.context() as mp:
+            for k, v in env.items():
+                mp.setenv(k, v)
+            blk.zero_grad()
+            xv, xe = p["x_v"].cuda().requires_grad_(True), p["x_e"].cuda().requires_grad_(True)
+            G = BatchedGraph.from_packed(p["mols"], xv, xe, device="cuda")
+            (Mean()(blk(G)) * gH).sum().backward()
+            runs.append([xv.grad.clone(), xe.grad.clone()] + [l.module.update[0].weight.grad.clone() for l in blk.layers])
+    for other in runs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(runs[0], other))
