@@ -481,3 +481,70 @@ def test_kernel_variant_switches_give_the_same_bits(monkeypatch):
             runs.append([xv.grad.clone(), xe.grad.clone()] + [l.module.update[0].weight.grad.clone() for l in blk.layers])
     for other in runs[1:]:
         assert all(torch.equal(a, b) for a, b in zip(runs[0], other))
+
+
+@pytest.mark.parametrize("case", ["bondless", "all_bondless", "single_molecule", "tf32", "bf16", "fp32_mode", "odd_d", "dropout_train", "dropout_eval", "no_residual"])
+def test_collapsed_last_depth_edge_cases(case):
+    """The collapsed last depth against the dense depth on the same device-collated batch, through the modules:
+    molecules without bonds (empty edge ranges), a batch with no edges at all, one molecule, the single-pass and bf16 GEMM modes;
+    and the cases that must fall back to the dense depth by themselves (strict-fp32 mode, d % 4 != 0, active dropout)."""
+    import torch.nn as nn
+
+    from notorch_b200 import BatchedGraph, ops
+    from notorch_b200.data.models.graph import PendingFeats
+    from notorch_b200.nn import ChempropBlock, Sum
+    from notorch_b200.synth import make_molecules
+
+    d, B, depth, drop, residual, mode, rel = 64, 24, 2, 0.0, True, "tf32x3", 3e-6
+    kw = {}
+    if case == "bondless":
+        kw = dict(bondless_every=3)
+    elif case == "all_bondless":
+        kw = dict(bondless_every=1)
+    elif case == "single_molecule":
+        B = 1
+    elif case == "tf32":
+        mode, rel = "tf32", 2e-3
+    elif case == "bf16":
+        mode, rel = "bf16", 3e-2
+    elif case == "fp32_mode":
+        mode = "fp32"
+    elif case == "odd_d":
+        d = 38
+    elif case in ("dropout_train", "dropout_eval"):
+        drop = 0.25
+    elif case == "no_residual":
+        residual = False
+    mols = make_molecules(B, 1, seed=5, **kw)
+    V, E = mols.total_atoms, mols.total_edges
+    gen = torch.Generator().manual_seed(11)
+    xv0, xe0, gH = torch.randn(V, d, generator=gen).cuda(), torch.randn(E, d, generator=gen).cuda(), torch.randn(B, d, generator=gen).cuda()
+    torch.manual_seed(3)
+    blk = ChempropBlock(hidden_dim=d, depth=depth, dropout=drop, residual=residual).cuda()
+    blk.train(case == "dropout_train")
+    ops.set_gemm_mode(mode)
+    expect_pooled = case not in ("fp32_mode", "odd_d", "dropout_train")
+    res = []
+    for pooled in (True, False):
+        ops._pooled_backward = pooled
+        try:
+            blk.zero_grad()
+            xv, xe = xv0.clone().requires_grad_(True), xe0.clone().requires_grad_(True)
+            G = BatchedGraph.from_packed(mols, xv, xe, device="cuda")
+            torch.manual_seed(7)  # the same dropout seeds and offsets in both runs
+            ops._dropout_calls = 0
+            G1 = blk(G)
+            assert isinstance(G1.peek("edge_feats"), PendingFeats) == (pooled and expect_pooled)  # deferred h_L <=> the collapsed form
+            H = Sum()(G1)
+            (H * gH).sum().backward()
+            res.append([H.detach().clone(), xv.grad.clone(), xe.grad.clone()] + [p.grad.clone() for p in blk.parameters()])
+        finally:
+            ops._pooled_backward = True
+    assert all(torch.isfinite(t).all() for t in res[0])
+    for a, b in zip(res[0], res[1]):
+        if a.numel() == 0 or float(b.abs().max()) == 0.0:  # a batch without edges: empty [0, d] tensors, exact zeros elsewhere
+            assert torch.equal(a, b)
+        elif expect_pooled:
+            assert_close(a, b, f"collapsed vs dense last depth ({case})", rel)
+        else:
+            assert torch.equal(a, b)  # both runs took the dense depth
