@@ -43,6 +43,7 @@ def _digest() -> str:
             h.update(os.path.basename(f).encode())  # never the absolute path: the tree is copied to another location on the GPU box
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(SOURCES).encode())  # a file that exists in csrc/ but is not linked yet must not read as "fresh"
     return h.hexdigest()
 
 
