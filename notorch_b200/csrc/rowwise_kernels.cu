@@ -377,7 +377,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) layer_bwd_epilogue_fused(const
 // measured and NOT kept: 244 us with one pass in flight (this form: 247), 326-329 us with two (80 registers, three CTAs per SM).
 // ncu of this form: 240 us, 1.41 GB of L2 -> L1 sectors + 0.25 GB of stores = 6.9 TB/s, i.e. the L2 -> SM ceiling of §5.0 (L1 hit
 // rate 9.6 %: the ~2.2 out-edge rows an edge gathers are its sibling in-edges' rows too, but siblings run on other SMs and a tile
-// did not bring them together in time).
+// did not bring them together in time). A per-molecule form (one CTA per molecule of a device-collated batch: its g_m rows staged once
+// in shared memory - a sequential read - and the out-edge sums served from there, bit-identical) measured 408 us: copy, barrier and
+// sweep of a 50-edge molecule serialise inside a CTA and three such CTAs per SM keep too few loads in flight. Not kept either.
 
 // the first form (kept for A/B timing: NOTORCH_B200_K6_VARIANT=0)
 template <int AK>
