@@ -50,6 +50,8 @@ def wgrad(E, d, positive):
 
 WG_SHAPES = ((100, 300), (600, 300), (1100, 300), (33000, 300), (205166, 300), (300000, 300), (37, 64), (5000, 256), (70000, 256),
              (40000, 1024), (819000 // 4, 1024), (20000, 2048), (9000, 332), (9000, 576))
+if "wgrad1" in sys.argv:  # the headline shape only (e.g. under NOTORCH_B200_WGRAD_HALF_COST / _SEG sweeps: those are read once per process)
+    wgrad(205166, 300, False)
 if "wgrad" in sys.argv or len(sys.argv) == 1:
     for E, d in WG_SHAPES:
         for positive in (False, True):
