@@ -20,6 +20,11 @@ void nt_debug_set_trace_buffer(void* device_u64_buffer);
  * k_blocks_per_split, k_blocks_per_split_last}; a K-block is 32 edges. For tests of the split logic. */
 int nt_debug_wgrad_geometry(int64_t E, int64_t d, int num_sms, int64_t* out12);
 
+/* Host-only (no CUDA call): the (row, chunk) split of the flattened item index t = row * chunks + chunk as the row kernels compute
+ * it - a multiply-high by ceil(2^64 / chunks) when the item count `total` fits 32 bits (magic = 0: the general 64-bit division).
+ * out3 = {magic != 0, row, chunk}. For the CPU test of that arithmetic. */
+int nt_debug_split_item(int64_t total, int64_t chunks, int64_t t, int64_t* out3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "nt_kernel_launch_count": (C.c_longlong, []),
     "nt_debug_set_trace_buffer": (None, [_vp]),
     "nt_debug_wgrad_geometry": (_int, [_i64, _i64, _int, _i64p]),
+    "nt_debug_split_item": (_int, [_i64, _i64, _i64, _i64p]),
     "nt_device_supported": (_int, []),
     "nt_collate_workspace_bytes": (_sz, [_i64]),
     "nt_collate": (_int, [_i32p, _i32p, _i64, _i32p, _i32p, _i64, _i64, _int, _i64p, _i64p, _i64p, _i64p, _i32p, _i32p, _vp, _sz, _vp]),

@@ -94,6 +94,25 @@ extern "C" int nt_debug_wgrad_geometry(int64_t E, int64_t d, int num_sms_, int64
 
 extern "C" void nt_debug_set_trace_buffer(void* device_u64_buffer) { pair_set_trace_buffer(device_u64_buffer); }
 
+// host restatement of split_item (common.cuh): unsigned __int128 stands in for __umul64hi
+extern "C" int nt_debug_split_item(int64_t total, int64_t chunks, int64_t t, int64_t* out3) {
+  NT_CHECK_ARG(total > 0 && chunks > 0 && chunks < (1 << 20) && t >= 0 && t < total && out3, "nt_debug_split_item: bad arguments");
+  const uint64_t magic = chunk_div_magic(total, (int)chunks);
+  int64_t row, chunk;
+  if (magic) {
+    const uint32_t q = (uint32_t)(((unsigned __int128)(uint64_t)t * magic) >> 64);
+    row = (int32_t)q;
+    chunk = (int32_t)((uint32_t)t - q * (uint32_t)chunks);
+  } else {
+    row = t / chunks;
+    chunk = t - row * chunks;
+  }
+  out3[0] = magic != 0;
+  out3[1] = row;
+  out3[2] = chunk;
+  return NT_OK;
+}
+
 extern "C" int nt_device_supported(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;

@@ -220,3 +220,31 @@ def test_wgrad_pair_geometry_invariants():
                 if full_u + half_u <= clusters and kb_total >= clusters:
                     assert pairs <= clusters, (sms, d, E, list(out))
     assert L.nt_debug_wgrad_geometry(10, 6, 148, out) != 0  # d % 4 != 0 is not the tensor-core path
+
+
+def test_chunk_split_by_multiply_high_is_exact():
+    """Every HBM-bound row kernel turns its flat work-item index t into (row, 16-byte chunk) with a multiply-high by
+    ceil(2^64 / chunks) instead of an emulated 64-bit division (common.cuh: split_item). Host restatement of that arithmetic
+    (nt_debug_split_item) against Python's divmod: item counts up to 2^32 - 1, chunk counts incl. powers of two, 75 (d = 300),
+    primes and the largest supported, t at every boundary; above 2^32 items (and for chunks == 1) the general division is used."""
+    import ctypes
+    import random
+
+    from notorch_b200 import _lib
+
+    L = _lib.lib()
+    out = (ctypes.c_int64 * 3)()
+    rng = random.Random(7)
+    for chunks in (1, 2, 3, 4, 7, 16, 64, 75, 83, 256, 512, 1000, 4099, 65536, (1 << 20) - 1):
+        for total in (chunks, 12345 * chunks, (1 << 31) - 1, (1 << 32) - 1, (1 << 32), (1 << 33) + 5):
+            if total < chunks:
+                continue
+            ts = {0, chunks - 1, chunks, total - 1, total // 2, (total // chunks) * chunks - 1, max((total // chunks) * chunks - chunks, 0)}
+            ts |= {rng.randrange(total) for _ in range(40)}
+            for t in ts:
+                if not 0 <= t < total:
+                    continue
+                assert L.nt_debug_split_item(total, chunks, t, out) == 0
+                fast, row, chunk = list(out)
+                assert fast == (1 if (chunks > 1 and total < (1 << 32)) else 0)
+                assert (row, chunk) == divmod(t, chunks), (total, chunks, t, row, chunk)
