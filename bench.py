@@ -933,7 +933,11 @@ def run_ours(args, wl, batch):
                         else "ONE NCCL all-reduce (AVG) after backward, captured in the step graph" if launch_mode == "cuda_graph" and args.graph_collective == "on"
                         else "NCCL all-reduce (AVG), eager" + (" between two graphs" if launch_mode == "cuda_graph" else "")),
                     "embedding": "fused into the edge initialisation (nt_embed_edge_init)" if ops._fuse_embedding else "separate kernels",
-                    "step": "collate+CSR, GraphEmbedding+edge init, ChempropBlock, readout, loss, backward, grad all-reduce (N>1), fused Adam"},
+                    "step": "collate+CSR, GraphEmbedding+edge init, ChempropBlock, readout, loss, backward, grad all-reduce (N>1), fused Adam",
+                    "last_depth": ("collapsed onto the molecules (DESIGN.md 5.10): the loss reads the block through the sum read-out only, so the last depth "
+                                   "computes sum_{e in b} h_L[e] and its gradients on [B, d] matrices; same outputs and gradients as the dense depth "
+                                   "(tests), h_L itself is not materialised; NOTORCH_B200_POOLED_LAST=0 runs it dense")
+                                  if ops._pooled_backward and ops._fuse_readout and not wl.get("inference") else "dense"},
             "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "eager_cuda_baseline": eager, "allreduce_check": ar_check, "kernels": kernels,
         }
