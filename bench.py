@@ -843,6 +843,38 @@ def run_ours(args, wl, batch):
                "inputs": "int64 atom/bond type ids [V,7],[E,2] + packed int32 topology (counts, local edge_index, local rev_index), pinned host memory; "
                          "the copy of step t+1 overlaps the compute of step t (two device buffers, copy stream); the loss is read back every step"}
 
+    # ---- the same step with the last depth run DENSE (DESIGN.md 5.10 switched off), same process, same batch: what the collapse is worth ----
+    dense_last = None
+    if world == 1 and not args.no_sustained and ops._pooled_backward and ops._fuse_readout and not wl.get("inference"):
+        try:
+            ops._pooled_backward = False
+            if use_graph and False in graphs:
+                gd = capture(resident, False)
+                torch.cuda.synchronize()
+                for _ in range(3):
+                    gd[0].replay()
+                torch.cuda.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for _ in range(args.steps):
+                    gd[0].replay()
+                ev1.record()
+                torch.cuda.synchronize()
+                ms_d = ev0.elapsed_time(ev1)
+                del gd
+            else:
+                for _ in range(3):
+                    step(resident, False)
+                ops._pooled_backward = False
+                ms_d, _ = timed(args.steps, resident, False)
+            dense_last = {"value": batch * args.steps / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d / args.steps,
+                          "what": "the same step with NOTORCH_B200_POOLED_LAST=0: the last depth as K1 + K2 / K4b + K4a + K6 over the edges"}
+        except Exception as exc:  # an extra figure, never a requirement
+            print(f"bench.py: dense-last-depth leg failed ({type(exc).__name__}: {exc})", file=sys.stderr)
+        finally:
+            ops._pooled_backward = True
+            ops.set_index_validation("off" if launch_mode == "cuda_graph" else "deferred")
+
     ops.set_index_validation("deferred")
     # ---- per-kernel CUDA-event timing (a separate instrumented pass over the same steps, launched eagerly) ----
     roof = kernels = None
@@ -939,7 +971,7 @@ def run_ours(args, wl, batch):
                                    "(tests), h_L itself is not materialised; NOTORCH_B200_POOLED_LAST=0 runs it dense")
                                   if ops._pooled_backward and ops._fuse_readout and not wl.get("inference") else "dense"},
             "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "eager_cuda_baseline": eager, "allreduce_check": ar_check, "kernels": kernels,
+            "eager_cuda_baseline": eager, "dense_last_depth": dense_last, "allreduce_check": ar_check, "kernels": kernels,
         }
         _emit(line)
     _shutdown(world, graphs)
