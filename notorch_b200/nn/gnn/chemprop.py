@@ -12,6 +12,7 @@ Arithmetic (the reference's, not textbook chemprop — SURVEY.md §0 item 2):
 """
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
 from torch import Tensor
 
@@ -117,11 +118,19 @@ class ChempropBlock(nn.Module):
             # molecule's edges directly (one pass instead of K1 + K3); any other reader of node_feats computes them on first access
             if last is not None:
                 core, fused_residual, h_prev, ei, ri = last[0], last[1], h, G.edge_index, G.rev_index
-                edges = PendingFeats(lambda: core(h_prev, xv, ei, ri, _residual=fused_residual, _csr=csr), tuple(h.shape), h.dtype, h.device,
-                                     ("last_depth", h_prev))
+                grad_mode = torch.is_grad_enabled()
+
+                def deferred(fn):  # whenever it runs, it runs in the autograd mode this forward was called in
+                    def run():
+                        with torch.set_grad_enabled(grad_mode):
+                            return fn()
+                    return run
+
+                edges = PendingFeats(deferred(lambda: core(h_prev, xv, ei, ri, _residual=fused_residual, _csr=csr)), tuple(h.shape), h.dtype,
+                                     h.device, ("last_depth", h_prev))
                 pool = ops.mol_edge_csr(G)
-                h_sum = _Once(lambda: core._pooled(h_prev, csr, pool, fused_residual))
-                atoms = PendingFeats(lambda: ops.edge_to_atom(edges.materialize(), csr, "sum"), (csr.V, h.shape[1]), h.dtype, h.device,
+                h_sum = _Once(deferred(lambda: core._pooled(h_prev, csr, pool, fused_residual)))
+                atoms = PendingFeats(deferred(lambda: ops.edge_to_atom(edges.materialize(), csr, "sum")), (csr.V, h.shape[1]), h.dtype, h.device,
                                      ("edge_to_atom_sum", edges, h_sum))
                 return G.update(node_feats=atoms, edge_feats=edges)
             final_h = h

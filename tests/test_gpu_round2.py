@@ -548,3 +548,23 @@ def test_collapsed_last_depth_edge_cases(case):
             assert_close(a, b, f"collapsed vs dense last depth ({case})", rel)
         else:
             assert torch.equal(a, b)  # both runs took the dense depth
+
+
+def test_deferred_last_depth_keeps_the_autograd_mode_of_the_forward_call():
+    """edge_feats of a block's output is computed on first access when the last depth was deferred; reading it later
+    under torch.no_grad() must still give a tensor that is connected to the graph of the forward call (and vice versa)."""
+    from notorch_b200 import BatchedGraph
+    from notorch_b200.nn import ChempropBlock
+
+    p = oracle_inputs(8, 32, 2, config=1, seed=3)
+    blk = ChempropBlock(hidden_dim=32, depth=2).cuda()
+    xv, xe = p["x_v"].cuda().requires_grad_(True), p["x_e"].cuda()
+    G1 = blk(BatchedGraph.from_packed(p["mols"], xv, xe, device="cuda"))
+    with torch.no_grad():
+        h_L = G1.edge_feats
+    assert h_L.requires_grad and h_L.grad_fn is not None
+    h_L.sum().backward()
+    assert xv.grad is not None and float(xv.grad.abs().sum()) > 0
+    with torch.no_grad():
+        G2 = blk(BatchedGraph.from_packed(p["mols"], xv, xe, device="cuda"))
+    assert not G2.edge_feats.requires_grad and torch.equal(G2.edge_feats, h_L.detach())
