@@ -96,7 +96,8 @@ if not RUN_K6:
     t4a = 0.0
 else:
   t4a = timed(lambda: _lib.check(L.nt_layer_backward_dgrad(p(g), p(W), p(img_t), E, d, 0.0, 0, 0, p(g_m), _lib.NT_F32, _lib.GEMM_TF32X3, st()), "k4a"))
-print(f"K4a alone {t4a:7.1f} us")
+if RUN_K6:
+    print(f"K4a alone {t4a:7.1f} us")
 for v in (0, 3) if RUN_K6 else ():
     os.environ["NOTORCH_B200_K6_VARIANT"] = str(v)
     t = timed(lambda: k6(o))
